@@ -1,0 +1,115 @@
+/* pidnet_b200 -- C ABI of the B200-native PIDNet forward engine (libpidnet_b200.so).
+ *
+ * The reference (Bzdeco/pidnet) has no FFI layer: its operator boundary for this path is the
+ * nn.Module call protocol of models/pidnet.py.  Each entry point below names the reference
+ * interface it stands in for; the Python shim `pidnet_b200/pidnet.py` keeps the nn.Module surface
+ * (same class / constructors / state_dict keys / output contract) and forwards to these symbols
+ * through ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions: every function returns 0 on success or a negative error code; the message is
+ * available from pidnet_last_error() (thread-local).  Nothing throws across the boundary.  Device
+ * pointers are plain `void*` / `float*` in the caller's CUDA context (primary context of the current
+ * device); `stream` is a cudaStream_t passed as void*.  A handle is bound to one device and is not
+ * re-entrant (one process / one handle per GPU -- the reference's DataParallel thread-per-replica
+ * model, tools/train.py:136, is replaced by one process per GPU).
+ */
+#ifndef PIDNET_B200_H_
+#define PIDNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pidnet_engine pidnet_engine;
+
+/* Constructor arguments of the reference model: PIDNet.__init__(m, n, num_classes, planes, ppm_planes,
+ * head_planes, augment), models/pidnet.py:19.  get_pred_model / get_seg_model (pidnet.py:184-227) map
+ * model names onto these. */
+typedef struct pidnet_cfg {
+  int m;           /* 2 (S/M) or 3 (L) */
+  int n;           /* 3 (S/M) or 4 (L) */
+  int num_classes; /* 19 Cityscapes, 11 CamVid */
+  int planes;      /* 32 S, 64 M/L */
+  int ppm_planes;  /* 96 S/M, 112 L */
+  int head_planes; /* 128 S/M, 256 L */
+  int augment;     /* 1: forward returns [x_extra_p, x_, x_extra_d] (pidnet.py:177-180) */
+} pidnet_cfg;
+
+const char* pidnet_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+int pidnet_abi_version(void);
+
+/* replaces PIDNet.__init__ (models/pidnet.py:19-100): creates an engine for one model topology. */
+int pidnet_create(const pidnet_cfg* cfg, pidnet_engine** out);
+int pidnet_destroy(pidnet_engine* h);
+
+/* replaces nn.Module.load_state_dict for one tensor (models/pidnet.py:193-214, tools/eval.py:68-78):
+ * `key` is the reference state_dict key (e.g. "layer3.0.conv1.weight"),
+ * `host_data` a contiguous fp32 HOST array of `shape[0..ndim)`.  Integer buffers
+ * (num_batches_tracked) are not needed and are ignored.  Marks the plan dirty. */
+int pidnet_set_param(pidnet_engine* h, const char* key, const float* host_data, const int64_t* shape, int ndim);
+
+/* Eval-mode plan for input [N,3,H,W] (H, W multiples of 8; pidnet.py:138-139): folds every BatchNorm
+ * (eps 1e-5, model_utils.py:8) into its conv in fp32/fp64 on the host, packs weights K-major bf16,
+ * lays activations out in one HBM arena (NHWC bf16), encodes the TMA tensor maps.  `arena_bytes`
+ * (optional) receives the device bytes the engine allocated. */
+int pidnet_plan(pidnet_engine* h, int N, int H, int W, size_t* arena_bytes);
+
+/* replaces PIDNet.forward (models/pidnet.py:136-182) in eval mode.
+ *   x_nchw   : device fp32 [N,3,H,W]
+ *   out_main : device fp32 [N,num_classes,H/8,W/8]   (x_)
+ *   out_p    : device fp32 [N,num_classes,H/8,W/8]   (x_extra_p; augment only, else NULL)
+ *   out_d    : device fp32 [N,1,H/8,W/8]             (x_extra_d; augment only, else NULL)
+ * All work is enqueued on `stream` (side streams fork/join on it with events); no host sync and no
+ * allocation inside.  use_graph != 0 replays a CUDA graph captured for these pointers. */
+int pidnet_forward(pidnet_engine* h, void* stream, const float* x_nchw, float* out_main, float* out_p, float* out_d,
+                   int use_graph);
+
+/* Kernel launches issued by one forward (for bench.py's `gpu_launches`). */
+int pidnet_num_launches(pidnet_engine* h);
+/* Algorithmic conv FLOPs (2*MACs, no padding waste) of one forward at the planned shape. */
+double pidnet_conv_flops(pidnet_engine* h);
+
+/* Options (set before pidnet_plan): "conv_impl" = 0 tcgen05 (default) | 1 SIMT restatement (debug
+ * cross-check); "lanes" = 1 | 3 concurrent branch streams (default 3). */
+int pidnet_set_option(pidnet_engine* h, const char* name, int value);
+
+/* Debug: copy a named intermediate (e.g. "layer3", "pag3", "spp"; see engine.cu) to the host as fp32
+ * NCHW.  `shape4` receives N,C,H,W; `host_out` may be NULL to query the shape only. */
+int pidnet_debug_tensor(pidnet_engine* h, const char* name, float* host_out, int64_t* shape4);
+
+/* ---- single-op entry points (kernel-level parity tests; device pointers, NHWC bf16 unless noted) ---- */
+
+/* nn.Conv2d (+folded affine, +residual, +ReLU) on one NHWC bf16 tensor.  w: host fp32 [Cout][Cin/groups][k][k]
+ * (already BN-folded), bias: host fp32 [Cout] or NULL, res: device NHWC bf16 [N,Ho,Wo,Cout] or NULL.
+ * out_nhwc (bf16) or out_nchw_f32 (exactly one non-NULL).  k in {1,3}, pad = k/2, stride in {1,2}.
+ * impl: 0 tcgen05, 1 SIMT. */
+int pidnet_op_conv2d(void* stream, const void* x_nhwc, int N, int H, int W, int Cin, const float* w, const float* bias,
+                     int Cout, int k, int stride, int groups, const void* res, int relu, void* out_nhwc,
+                     float* out_nchw_f32, int impl);
+/* conv1.0 + BN + ReLU of the stem: fp32 NCHW image -> bf16 NHWC (pidnet.py:25-27). w: host [Cout][3][3][3]. */
+int pidnet_op_stem(void* stream, const float* x_nchw, int N, int H, int W, const float* w, const float* bias, int Cout,
+                   void* out_nhwc);
+/* PagFM fuse: x [N,H,W,C], low [N,h,w,2C+8] = [y|z|t|pad] -> out [N,H,W,C]. */
+int pidnet_op_pag(void* stream, const void* x, const void* low, void* out, int N, int H, int W, int C, int h, int w,
+                  int relu);
+/* out = act(s*(a + bilinear(b)) + t); a/b/s/t optional (NULL). b is [N,h,w,C]. s,t device fp32 [C]. */
+int pidnet_op_upadd(void* stream, const void* a, const void* b, void* out, int N, int H, int W, int C, int h, int w,
+                    const float* s, const float* t, int relu);
+/* AvgPool2d(k,stride,pad,count_include_pad) (k==0: global) + affine + ReLU. */
+int pidnet_op_pool(void* stream, const void* x, void* out, int N, int H, int W, int C, int k, int stride, int pad,
+                   const float* s, const float* t, int relu);
+/* Light_Bag operand producer: out [N,H,W,2C]. */
+int pidnet_op_lightbag(void* stream, const void* p, const void* i_low, const void* d, void* out, int N, int H, int W,
+                       int C, int h, int w);
+/* Bag blend + BN + ReLU: out [N,H,W,C]. */
+int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d, void* out, int N, int H, int W, int C,
+                  int h, int w, const float* s, const float* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIDNET_B200_H_ */

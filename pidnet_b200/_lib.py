@@ -1,0 +1,67 @@
+"""ctypes binding of libpidnet_b200.so (the C ABI declared in include/pidnet_b200.h).
+
+There is no CPU / PyTorch fallback: if the library is missing or a call fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libpidnet_b200.so')
+
+
+class Cfg(C.Structure):
+    _fields_ = [('m', C.c_int), ('n', C.c_int), ('num_classes', C.c_int), ('planes', C.c_int),
+                ('ppm_planes', C.c_int), ('head_planes', C.c_int), ('augment', C.c_int)]
+
+
+_vp, _fp, _i, _i64p = C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); mirrors include/pidnet_b200.h one to one (tests check the list)
+SIGNATURES = {
+    'pidnet_last_error': (C.c_char_p, []),
+    'pidnet_abi_version': (_i, []),
+    'pidnet_create': (_i, [C.POINTER(Cfg), C.POINTER(_vp)]),
+    'pidnet_destroy': (_i, [_vp]),
+    'pidnet_set_param': (_i, [_vp, C.c_char_p, _vp, _i64p, _i]),
+    'pidnet_plan': (_i, [_vp, _i, _i, _i, C.POINTER(C.c_size_t)]),
+    'pidnet_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    'pidnet_num_launches': (_i, [_vp]),
+    'pidnet_conv_flops': (C.c_double, [_vp]),
+    'pidnet_set_option': (_i, [_vp, C.c_char_p, _i]),
+    'pidnet_debug_tensor': (_i, [_vp, C.c_char_p, _vp, _i64p]),
+    'pidnet_op_conv2d': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i]),
+    'pidnet_op_stem': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    'pidnet_op_pag': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i]),
+    'pidnet_op_upadd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i]),
+    'pidnet_op_pool': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i]),
+    'pidnet_op_lightbag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
+    'pidnet_op_bag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building it is `python -m pidnet_b200.build`); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'pidnet_b200: {LIB_PATH} is missing -- build it with `python -m pidnet_b200.build` '
+            '(there is no CPU or PyTorch fallback)')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().pidnet_last_error()
+        raise RuntimeError('pidnet_b200: ' + (msg.decode() if msg else f'error {rc}'))

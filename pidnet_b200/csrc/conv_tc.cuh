@@ -1,0 +1,59 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), NHWC bf16 -> fp32 TMEM accumulators.
+//
+//   D[pixel, cout] = act( sum_{src, tap, cin} A_src[pixel + tap, cin] * W[cout, (src,tap,cin)] + bias[cout] (+ R[pixel, cout]) )
+//
+// * M tile = 128 output pixels = a TN x TH x TW patch of the NHWC output; one TMA 4-D box load per
+//   (tap, 64/32-channel chunk) brings the shifted input patch (zero-filled outside the image ==
+//   the conv padding) into a 128-row K-major SWIZZLE_128B/64B tile that tcgen05.mma consumes directly.
+// * stride-2 convs read one of four "parity" tensor maps (the even/odd sub-lattices of the input),
+//   so every load is a plain dense box; 1x1 convs are the 1-tap case; a second source appends
+//   K-slices (the 1x1 downsample of a residual block, or a channel concat) to the same accumulator.
+// * BatchNorm is folded into W/bias on the host; bias, residual add and ReLU run on the TMEM->register
+//   epilogue; the bf16 tile is staged in swizzled smem and written with TMA (clipped at ragged edges),
+//   or written as fp32 NCHW planes for the logits.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace pidnet {
+
+constexpr int kConvMaxMaps = 6;
+constexpr int kConvMaxTaps = 9;
+
+struct ConvSrc {
+  int ntaps;                    // 1 (1x1) or up to 9 (3x3)
+  int chunks;                   // ceil(Cin / BK)
+  uint32_t taps[kConvMaxTaps];  // map index | (dh+8) << 8 | (dw+8) << 16
+};
+
+enum ConvOutMode { kOutNHWCbf16 = 0, kOutNCHWf32 = 1 };
+
+struct ConvParams {
+  CUtensorMap tmA[kConvMaxMaps];  // activation maps
+  CUtensorMap tmB;                // packed weights [Cout_pad][Ktot], K-major
+  CUtensorMap tmR;                // residual (same geometry as tmD)
+  CUtensorMap tmD;                // output
+  ConvSrc src[2];
+  int nsrc;
+  int tiles_w, tiles_h;  // tiles per (TN-image group) along W and H
+  int TW, TH, TN;
+  int N, Ho, Wo, Cout;
+  int relu, has_res, out_mode;
+  const float* bias;  // [Cout_pad] fp32
+  float* out_f32;     // kOutNCHWf32 destination [N][Cout][Ho][Wo]
+};
+
+struct ConvLaunch {
+  ConvParams p;
+  int BN, BK;
+  dim3 grid;
+};
+
+// Launches the kernel instance for (BN, BK); returns cudaError_t.
+cudaError_t conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);
+// One-time: opt in to large dynamic shared memory for all instances.
+cudaError_t conv_tc_init();
+size_t conv_tc_smem_bytes(int BN, int BK);
+
+}  // namespace pidnet

@@ -1,0 +1,1212 @@
+// pidnet_b200 engine: eval-mode planner for PIDNet (BN folding, weight packing, HBM arena, TMA tensor
+// maps, three branch lanes joined by events, optional CUDA-graph replay) behind the C ABI of
+// include/pidnet_b200.h.  The dataflow follows models/pidnet.py:136-182 of the reference; the fusion
+// plan is described in DESIGN.md.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pidnet_b200.h"
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+namespace pidnet {
+
+// ----------------------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+struct Err : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+[[noreturn]] static void fail(const std::string& m) { throw Err(m); }
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess) fail(std::string(#call) + ": " + cudaGetErrorString(e__));                \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) fail("cuTensorMapEncodeTiled entry point not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+static CUtensorMapSwizzle swizzle_for(int bytes) {
+  switch (bytes) {
+    case 128: return CU_TENSOR_MAP_SWIZZLE_128B;
+    case 64: return CU_TENSOR_MAP_SWIZZLE_64B;
+    case 32: return CU_TENSOR_MAP_SWIZZLE_32B;
+  }
+  fail("bad swizzle span");
+}
+// bf16 tensor of rank `rank` (dims fastest first, strides in BYTES for dims 1..rank-1)
+static CUtensorMap encode_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                              const uint32_t* box, int swizzle_bytes) {
+  CUtensorMap m;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (dims[i] == 0) fail("tensor map: zero dim");
+    if (box[i] == 0 || box[i] > 256) fail("tensor map: bad box");
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gs[i] = strides_b[i];
+    if (gs[i] % 16 != 0) fail("tensor map: stride not multiple of 16 B");
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) fail("tensor map: base not 16 B aligned");
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(swizzle_bytes),
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
+// ----------------------------------------------------------------------------------------- host helpers
+static inline uint16_t f2bf(float f) {  // round to nearest even
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct HostParam {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+struct Affine {
+  std::vector<float> s, t;
+};
+
+struct T {  // NHWC bf16 view
+  bf16* ptr = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;
+  long ps = 0;    // pixel stride (elements)
+  int prod = -1;  // index of the producing op (-1: external)
+  View view() const { return View{ptr, N, H, W, C, ps}; }
+};
+
+struct RunArgs {
+  const float* x;
+  float* out[3];  // main, p, d
+};
+
+struct Op {
+  std::string name;
+  int lane = 0;
+  std::vector<int> deps;  // producer ops on other lanes
+  bool record = false;
+  std::function<cudaError_t(cudaStream_t, const RunArgs&)> fn;
+};
+
+struct ConvSrcSpec {
+  T in;
+  std::vector<float> w;  // [Cout][Cin][k][k] fp32, BN-folded
+  int k = 1, stride = 1;
+};
+
+// ----------------------------------------------------------------------------------------- builder
+struct Builder {
+  bool dry = true;
+  int conv_impl = 0;
+  int num_sms = 148;
+  size_t act_cur = 0, wt_cur = 0;
+  uint8_t* act_base = nullptr;
+  uint8_t* wt_base = nullptr;
+  std::vector<uint8_t> wt_host;
+  std::vector<Op> ops;
+  int lane = 0;
+  double flops = 0;
+  std::map<std::string, T> named;
+
+  void reset(bool dry_) {
+    dry = dry_;
+    act_cur = wt_cur = 0;
+    ops.clear();
+    named.clear();
+    lane = 0;
+    flops = 0;
+    if (!dry) wt_host.assign(wt_host.size(), 0);
+  }
+  void* alloc_act(size_t bytes) {
+    size_t off = act_cur;
+    act_cur = align_up(act_cur + bytes, 1024);
+    return act_base + off;
+  }
+  // device copy of host data (uploaded in one memcpy when the plan is finished)
+  void* alloc_wt(const void* src, size_t bytes) {
+    size_t off = wt_cur;
+    wt_cur = align_up(wt_cur + bytes, 256);
+    if (!dry) {
+      if (wt_cur > wt_host.size()) fail("weight arena overflow");
+      std::memcpy(wt_host.data() + off, src, bytes);
+    }
+    return wt_base + off;
+  }
+  const float* upload_f32(const std::vector<float>& v) {
+    return reinterpret_cast<const float*>(alloc_wt(v.data(), v.size() * sizeof(float)));
+  }
+  T new_tensor(int N, int H, int W, int C) {
+    if (C % 8 != 0) fail("channel count must be a multiple of 8 (got " + std::to_string(C) + ")");
+    T t;
+    t.N = N; t.H = H; t.W = W; t.C = C; t.ps = C;
+    t.ptr = reinterpret_cast<bf16*>(alloc_act(static_cast<size_t>(N) * H * W * C * 2));
+    return t;
+  }
+  static T slice(const T& t, int coff, int C) {
+    if (coff % 8 != 0 || C % 8 != 0 || coff + C > t.C) fail("bad channel slice");
+    T s = t;
+    s.ptr = t.ptr + coff;
+    s.C = C;
+    return s;
+  }
+  int add_op(const std::string& name, std::vector<const T*> inputs,
+             std::function<cudaError_t(cudaStream_t, const RunArgs&)> fn) {
+    Op op;
+    op.name = name;
+    op.lane = lane;
+    for (const T* t : inputs)
+      if (t && t->prod >= 0 && ops[t->prod].lane != lane) {
+        op.deps.push_back(t->prod);
+        ops[t->prod].record = true;
+      }
+    op.fn = std::move(fn);
+    ops.push_back(std::move(op));
+    return static_cast<int>(ops.size()) - 1;
+  }
+
+  // --------------------------------------------------------------------------------- conv
+  static void choose_tile(int N, int H, int W, bool nchw, int& TN, int& TH, int& TW) {
+    long best = -1;
+    for (int tw = 128; tw >= 1; tw >>= 1) {
+      for (int th = 128 / tw; th >= 1; th >>= 1) {
+        const int tn = 128 / (tw * th);
+        if (nchw && tw < 32 && tw < W) continue;
+        if (tn > 1 && (th < H || tw < W)) continue;  // batch several images only when one tile covers an image
+        const long tiles = static_cast<long>(cdiv(W, tw)) * cdiv(H, th) * cdiv(N, tn);
+        const long cost = tiles * 100000 + static_cast<long>(th + 2) * (tw + 2) * 10 + (128 - tw) / 16;
+        if (best < 0 || cost < best) {
+          best = cost;
+          TN = tn; TH = th; TW = tw;
+        }
+      }
+    }
+  }
+
+  // out = act( sum_src conv(src) + bias (+res) ); writes `out` (bf16 NHWC view) or the fp32 NCHW runtime
+  // output `out_slot` (0..2).  Returns the output view (invalid ptr for NCHW slots).
+  T conv(const std::string& name, const std::vector<ConvSrcSpec>& srcs, const std::vector<float>& bias, int Cout,
+         bool relu, const T* res, const T* out_view, int out_slot) {
+    if (srcs.empty() || srcs.size() > 2) fail(name + ": 1 or 2 sources supported");
+    const T& in0 = srcs[0].in;
+    const int N = in0.N;
+    const int Ho = cdiv(in0.H, srcs[0].stride), Wo = cdiv(in0.W, srcs[0].stride);
+    bool flat = out_slot < 0;
+    int BK = 32;
+    for (const auto& s : srcs) {
+      if (s.k != 1 && s.k != 3) fail(name + ": kernel size must be 1 or 3");
+      if (s.stride != 1 && s.stride != 2) fail(name + ": stride must be 1 or 2");
+      if (cdiv(s.in.H, s.stride) != Ho || cdiv(s.in.W, s.stride) != Wo || s.in.N != N)
+        fail(name + ": source geometry mismatch");
+      if (static_cast<long>(s.w.size()) != static_cast<long>(Cout) * s.in.C * s.k * s.k)
+        fail(name + ": weight size mismatch");
+      if (s.k != 1 || s.stride != 1) flat = false;
+      if (s.in.C > 32) BK = 64;
+      flops += 2.0 * N * Ho * Wo * Cout * s.in.C * s.k * s.k;
+    }
+    T out;
+    if (out_slot < 0) {
+      out = out_view ? *out_view : new_tensor(N, Ho, Wo, Cout);
+      if (out.N != N || out.H != Ho || out.W != Wo || out.C != Cout) fail(name + ": output view mismatch");
+    } else {
+      out.N = N; out.H = Ho; out.W = Wo; out.C = Cout;
+    }
+    if (res && (res->N != N || res->H != Ho || res->W != Wo || res->C != Cout)) fail(name + ": residual mismatch");
+
+    // logical tiling geometry
+    const int gN = flat ? 1 : N, gH = flat ? 1 : Ho, gW = flat ? N * Ho * Wo : Wo;
+    int TN, TH, TW;
+    choose_tile(gN, gH, gW, out_slot >= 0, TN, TH, TW);
+    const int tiles_w = cdiv(gW, TW), tiles_h = cdiv(gH, TH), tiles_n = cdiv(gN, TN);
+    const int m_tiles = tiles_w * tiles_h * tiles_n;
+    int BN = Cout >= 128 ? 128 : (Cout > 32 ? 64 : 32);
+    while (BN > 32 && static_cast<long>(m_tiles) * cdiv(Cout, BN) < num_sms) BN >>= 1;
+    const int n_tiles = cdiv(Cout, BN);
+    const int Cout_pad = n_tiles * BN;
+
+    ConvLaunch L;
+    std::memset(&L, 0, sizeof(L));
+    ConvRefParams R;
+    std::memset(&R, 0, sizeof(R));
+    L.BN = BN; L.BK = BK;
+    L.grid = dim3(m_tiles, n_tiles, 1);
+    ConvParams& p = L.p;
+    p.nsrc = static_cast<int>(srcs.size());
+    p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+    p.TW = TW; p.TH = TH; p.TN = TN;
+    p.N = gN; p.Ho = gH; p.Wo = gW; p.Cout = Cout;
+    p.relu = relu ? 1 : 0;
+    p.has_res = res ? 1 : 0;
+    p.out_mode = out_slot >= 0 ? kOutNCHWf32 : kOutNHWCbf16;
+
+    // ---- activation maps + tap tables
+    int nmaps = 0;
+    struct TapW { int r, s; };
+    std::vector<std::vector<TapW>> kept(srcs.size());
+    for (size_t si = 0; si < srcs.size(); ++si) {
+      const ConvSrcSpec& s = srcs[si];
+      const T& in = s.in;
+      ConvSrc& cs = p.src[si];
+      cs.chunks = cdiv(in.C, BK);
+      cs.ntaps = 0;
+      int map_of[2][2] = {{-1, -1}, {-1, -1}};
+      for (int r = 0; r < s.k; ++r)
+        for (int q = 0; q < s.k; ++q) {
+          int hp = 0, wp = 0, dh = 0, dw = 0;
+          if (s.k == 3) {
+            if (s.stride == 1) { dh = r - 1; dw = q - 1; }
+            else { hp = (r == 1) ? 0 : 1; dh = (r == 0) ? -1 : 0; wp = (q == 1) ? 0 : 1; dw = (q == 0) ? -1 : 0; }
+          }
+          // geometry of the (sub-)lattice this tap reads
+          const int st = s.stride;
+          const int LW = (in.W - wp + st - 1) / st, LH = (in.H - hp + st - 1) / st;
+          if (LW <= 0 || LH <= 0) continue;  // tap lies entirely in the padding
+          if (map_of[hp][wp] < 0) {
+            if (nmaps >= kConvMaxMaps) fail(name + ": too many tensor maps");
+            const bf16* base = in.ptr + (static_cast<long>(hp) * in.W + wp) * in.ps;
+            RefMap rm;
+            rm.ptr = base; rm.C = in.C;
+            if (flat) {
+              rm.W = N * in.H * in.W; rm.H = 1; rm.N = 1;
+              rm.sW = in.ps; rm.sH = 0; rm.sN = 0;
+            } else {
+              rm.W = LW; rm.H = LH; rm.N = N;
+              rm.sW = static_cast<long>(st) * in.ps;
+              rm.sH = static_cast<long>(st) * in.W * in.ps;
+              rm.sN = static_cast<long>(in.H) * in.W * in.ps;
+            }
+            R.maps[nmaps] = rm;
+            if (!dry) {
+              const uint64_t big = static_cast<uint64_t>(rm.W) * rm.sW * 2;
+              uint64_t dims[4] = {static_cast<uint64_t>(rm.C), static_cast<uint64_t>(rm.W),
+                                  static_cast<uint64_t>(rm.H), static_cast<uint64_t>(rm.N)};
+              uint64_t strides[3] = {static_cast<uint64_t>(rm.sW) * 2,
+                                     flat ? big : static_cast<uint64_t>(rm.sH) * 2,
+                                     flat ? big : static_cast<uint64_t>(rm.sN) * 2};
+              uint32_t box[4] = {static_cast<uint32_t>(BK), static_cast<uint32_t>(TW), static_cast<uint32_t>(TH),
+                                 static_cast<uint32_t>(TN)};
+              p.tmA[nmaps] = encode_map(base, 4, dims, strides, box, BK * 2);
+            }
+            map_of[hp][wp] = nmaps++;
+          }
+          if (cs.ntaps >= kConvMaxTaps) fail(name + ": too many taps");
+          cs.taps[cs.ntaps++] = static_cast<uint32_t>(map_of[hp][wp]) | (static_cast<uint32_t>(dh + 8) << 8) |
+                                (static_cast<uint32_t>(dw + 8) << 16);
+          kept[si].push_back(TapW{r, q});
+        }
+      if (cs.ntaps == 0) fail(name + ": source has no taps");
+    }
+
+    // ---- packed weights [Cout_pad][Ktot] bf16, K order == the kernel's (src, tap, chunk, channel)
+    long Ktot = 0;
+    for (int si = 0; si < p.nsrc; ++si) Ktot += static_cast<long>(p.src[si].ntaps) * p.src[si].chunks * BK;
+    std::vector<uint16_t> wpk;
+    if (!dry) {
+      wpk.assign(static_cast<size_t>(Cout_pad) * Ktot, 0);
+      long kofs = 0;
+      for (size_t si = 0; si < srcs.size(); ++si) {
+        const ConvSrcSpec& s = srcs[si];
+        const int Cin = s.in.C, kk = s.k * s.k, chunks = p.src[si].chunks;
+        for (size_t ti = 0; ti < kept[si].size(); ++ti) {
+          const int r = kept[si][ti].r, q = kept[si][ti].s;
+          for (int co = 0; co < Cout; ++co) {
+            uint16_t* dst = wpk.data() + static_cast<size_t>(co) * Ktot + kofs + static_cast<long>(ti) * chunks * BK;
+            const float* wsrc = s.w.data() + static_cast<size_t>(co) * Cin * kk + r * s.k + q;
+            for (int ci = 0; ci < Cin; ++ci) dst[ci] = f2bf(wsrc[static_cast<size_t>(ci) * kk]);
+          }
+        }
+        kofs += static_cast<long>(kept[si].size()) * chunks * BK;
+      }
+    }
+    const bf16* wdev =
+        reinterpret_cast<const bf16*>(alloc_wt(wpk.data(), static_cast<size_t>(Cout_pad) * Ktot * 2));
+    std::vector<float> bpad(Cout_pad, 0.f);
+    for (int c = 0; c < Cout && c < static_cast<int>(bias.size()); ++c) bpad[c] = bias[c];
+    const float* bdev = upload_f32(bpad);
+    p.bias = bdev;
+
+    if (!dry) {
+      uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(Cout_pad)};
+      uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};
+      uint32_t box[2] = {static_cast<uint32_t>(BK), static_cast<uint32_t>(BN)};
+      p.tmB = encode_map(wdev, 2, dims, strides, box, BK * 2);
+      const int SC = BN < 64 ? BN : 64;
+      auto out_map = [&](const T& t) {
+        uint64_t dims4[4], str[3];
+        dims4[0] = static_cast<uint64_t>(t.C);
+        if (flat) {
+          const uint64_t rows = static_cast<uint64_t>(N) * Ho * Wo;
+          dims4[1] = rows; dims4[2] = 1; dims4[3] = 1;
+          str[0] = static_cast<uint64_t>(t.ps) * 2; str[1] = rows * t.ps * 2; str[2] = rows * t.ps * 2;
+        } else {
+          dims4[1] = Wo; dims4[2] = Ho; dims4[3] = N;
+          str[0] = static_cast<uint64_t>(t.ps) * 2;
+          str[1] = static_cast<uint64_t>(Wo) * t.ps * 2;
+          str[2] = static_cast<uint64_t>(Ho) * Wo * t.ps * 2;
+        }
+        uint32_t box4[4] = {static_cast<uint32_t>(SC), static_cast<uint32_t>(TW), static_cast<uint32_t>(TH),
+                            static_cast<uint32_t>(TN)};
+        return encode_map(t.ptr, 4, dims4, str, box4, SC * 2);
+      };
+      if (out_slot < 0) p.tmD = out_map(out);
+      if (res) p.tmR = out_map(*res);
+    }
+    // ---- SIMT restatement parameters
+    for (int si = 0; si < p.nsrc; ++si) R.src[si] = p.src[si];
+    R.nsrc = p.nsrc; R.BK = BK; R.wpk = wdev; R.Ktot = Ktot; R.bias = bdev;
+    R.N = gN; R.Ho = gH; R.Wo = gW; R.Cout = Cout; R.relu = p.relu; R.out_mode = p.out_mode;
+    if (res) {
+      R.res.ptr = res->ptr;
+      R.res.sW = res->ps; R.res.sH = flat ? 0 : static_cast<long>(Wo) * res->ps;
+      R.res.sN = flat ? 0 : static_cast<long>(Ho) * Wo * res->ps;
+    }
+    if (out_slot < 0) {
+      R.out = out.ptr;
+      R.o_sW = out.ps; R.o_sH = flat ? 0 : static_cast<long>(Wo) * out.ps;
+      R.o_sN = flat ? 0 : static_cast<long>(Ho) * Wo * out.ps;
+    }
+
+    std::vector<const T*> ins;
+    for (const auto& s : srcs) ins.push_back(&s.in);
+    if (res) ins.push_back(res);
+    const int impl = conv_impl;
+    const int idx = add_op(name, ins, [L, R, impl, out_slot](cudaStream_t st, const RunArgs& a) mutable {
+      if (impl == 0) {
+        if (out_slot >= 0) L.p.out_f32 = a.out[out_slot];
+        return conv_tc_launch(L, st);
+      }
+      if (out_slot >= 0) R.out_f32 = a.out[out_slot];
+      return conv_ref_launch(R, st);
+    });
+    out.prod = idx;
+    return out;
+  }
+};
+
+// ----------------------------------------------------------------------------------------- engine
+struct Engine {
+  pidnet_cfg cfg{};
+  std::map<std::string, HostParam> params;
+  Builder b;
+  bool planned = false;
+  int N = 0, H = 0, W = 0;
+  int lanes = 3;
+  int conv_impl = 0;
+  cudaStream_t side[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> events;  // one per op that records
+  std::vector<int> ev_of_op;
+  cudaEvent_t ev_start = nullptr, ev_join[2] = {nullptr, nullptr};
+  // graph cache
+  cudaGraphExec_t gexec = nullptr;
+  RunArgs gargs{};
+
+  ~Engine() { release(); }
+  void release() {
+    if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+    for (auto e : events) cudaEventDestroy(e);
+    events.clear();
+    if (ev_start) { cudaEventDestroy(ev_start); ev_start = nullptr; }
+    for (int i = 0; i < 2; ++i) {
+      if (ev_join[i]) { cudaEventDestroy(ev_join[i]); ev_join[i] = nullptr; }
+      if (side[i]) { cudaStreamDestroy(side[i]); side[i] = nullptr; }
+    }
+    if (b.act_base) { cudaFree(b.act_base); b.act_base = nullptr; }
+    if (b.wt_base) { cudaFree(b.wt_base); b.wt_base = nullptr; }
+    planned = false;
+  }
+
+  // ---- parameters
+  const HostParam& P(const std::string& k) const {
+    auto it = params.find(k);
+    if (it == params.end()) fail("missing parameter '" + k + "'");
+    return it->second;
+  }
+  bool has(const std::string& k) const { return params.count(k) != 0; }
+  Affine bn(const std::string& p) const {  // eval BatchNorm as y = s*x + t  (eps 1e-5)
+    const auto &g = P(p + ".weight").data, &be = P(p + ".bias").data, &mu = P(p + ".running_mean").data,
+               &var = P(p + ".running_var").data;
+    Affine a;
+    a.s.resize(g.size());
+    a.t.resize(g.size());
+    for (size_t i = 0; i < g.size(); ++i) {
+      const double s = static_cast<double>(g[i]) / std::sqrt(static_cast<double>(var[i]) + 1e-5);
+      a.s[i] = static_cast<float>(s);
+      a.t[i] = static_cast<float>(static_cast<double>(be[i]) - static_cast<double>(mu[i]) * s);
+    }
+    return a;
+  }
+  static Affine slice(const Affine& a, int off, int n) {
+    Affine r;
+    r.s.assign(a.s.begin() + off, a.s.begin() + off + n);
+    r.t.assign(a.t.begin() + off, a.t.begin() + off + n);
+    return r;
+  }
+  // conv weight scaled per output channel by `post` (the BN that FOLLOWS the conv); bias folded likewise
+  void fold(const std::string& conv, const Affine* post, std::vector<float>& w, std::vector<float>& bias) const {
+    const HostParam& hw = P(conv + ".weight");
+    const int Cout = static_cast<int>(hw.shape[0]);
+    const size_t per = hw.data.size() / Cout;
+    w = hw.data;
+    bias.assign(Cout, 0.f);
+    if (has(conv + ".bias")) bias = P(conv + ".bias").data;
+    if (post) {
+      for (int co = 0; co < Cout; ++co) {
+        for (size_t i = 0; i < per; ++i) w[co * per + i] *= post->s[co];
+        bias[co] = bias[co] * post->s[co] + post->t[co];
+      }
+    }
+  }
+  ConvSrcSpec src_of(const T& in, const std::string& conv, const Affine* post, int k, int stride,
+                     std::vector<float>* bias_acc) const {
+    ConvSrcSpec s;
+    s.in = in; s.k = k; s.stride = stride;
+    std::vector<float> bias;
+    fold(conv, post, s.w, bias);
+    const HostParam& hw = P(conv + ".weight");
+    if (hw.shape.size() != 4 || hw.shape[1] != in.C || hw.shape[2] != k)
+      fail("weight '" + conv + "' does not match its input (" + std::to_string(in.C) + " ch)");
+    if (bias_acc) {
+      if (bias_acc->empty()) *bias_acc = bias;
+      else for (size_t i = 0; i < bias.size(); ++i) (*bias_acc)[i] += bias[i];
+    }
+    return s;
+  }
+
+  // ---- blocks (fused forms of model_utils.py BasicBlock / Bottleneck / segmenthead)
+  T conv_bn(const std::string& name, const T& x, const std::string& conv, const std::string& bnp, int k, int stride,
+            bool relu) {
+    Affine a = bn(bnp);
+    std::vector<float> bias;
+    ConvSrcSpec s = src_of(x, conv, &a, k, stride, &bias);
+    return b.conv(name, {s}, bias, static_cast<int>(P(conv + ".weight").shape[0]), relu, nullptr, nullptr, -1);
+  }
+  // tail conv of a residual block: conv+bn (+ 1x1 downsample conv+bn as extra K slices | + identity residual)
+  T block_tail(const std::string& p, const T& mid, const std::string& conv, const std::string& bnp, int k, const T& x,
+               int stride, bool relu) {
+    Affine a = bn(p + "." + bnp);
+    std::vector<float> bias;
+    std::vector<ConvSrcSpec> srcs;
+    srcs.push_back(src_of(mid, p + "." + conv, &a, k, 1, &bias));
+    const int Cout = static_cast<int>(P(p + "." + conv + ".weight").shape[0]);
+    if (has(p + ".downsample.0.weight")) {
+      Affine d = bn(p + ".downsample.1");
+      srcs.push_back(src_of(x, p + ".downsample.0", &d, 1, stride, &bias));
+      return b.conv(p + "." + conv + "+ds", srcs, bias, Cout, relu, nullptr, nullptr, -1);
+    }
+    return b.conv(p + "." + conv + "+res", srcs, bias, Cout, relu, &x, nullptr, -1);
+  }
+  T basic_block(const std::string& p, const T& x, int stride, bool relu_out) {
+    T mid = conv_bn(p + ".conv1", x, p + ".conv1", p + ".bn1", 3, stride, true);
+    return block_tail(p, mid, "conv2", "bn2", 3, x, stride, relu_out);
+  }
+  T bottleneck(const std::string& p, const T& x, int stride, bool relu_out) {
+    T a = conv_bn(p + ".conv1", x, p + ".conv1", p + ".bn1", 1, 1, true);
+    T c = conv_bn(p + ".conv2", a, p + ".conv2", p + ".bn2", 3, stride, true);
+    return block_tail(p, c, "conv3", "bn3", 1, x, stride, relu_out);
+  }
+  // _make_layer (pidnet.py:103-121); `relu_last`: what the single stored form of the layer output must be
+  T layer(const std::string& p, T x, bool bott, int blocks, int stride, bool relu_last) {
+    for (int i = 0; i < blocks; ++i) {
+      const bool last = i == blocks - 1;
+      // block 0 keeps the block default (BasicBlock: relu, Bottleneck: no relu); middle blocks relu
+      bool relu = last ? relu_last : (i == 0 ? !bott : true);
+      if (blocks == 1) relu = relu_last;
+      const std::string bp = p + "." + std::to_string(i);
+      x = bott ? bottleneck(bp, x, i == 0 ? stride : 1, relu) : basic_block(bp, x, i == 0 ? stride : 1, relu);
+    }
+    return x;
+  }
+  T affine_relu(const std::string& name, const T& x, const Affine& a, const T* out_view) {
+    T out = out_view ? *out_view : b.new_tensor(x.N, x.H, x.W, x.C);
+    const float* s = b.upload_f32(a.s);
+    const float* t = b.upload_f32(a.t);
+    View xv = x.view(), ov = out.view();
+    out.prod = b.add_op(name, {&x}, [xv, ov, s, t](cudaStream_t st, const RunArgs&) {
+      return upadd_launch(xv, View{nullptr, 0, 0, 0, 0, 0}, ov, s, t, 1, st);
+    });
+    return out;
+  }
+  // out = act(s*(a + U(blow)) + t)
+  T upadd(const std::string& name, const T& a, const T& blow, const Affine* aff, bool relu, const T* out_view) {
+    T out = out_view ? *out_view : b.new_tensor(a.N, a.H, a.W, a.C);
+    const float* s = aff ? b.upload_f32(aff->s) : nullptr;
+    const float* t = aff ? b.upload_f32(aff->t) : nullptr;
+    View av = a.view(), bv = blow.view(), ov = out.view();
+    const int r = relu ? 1 : 0;
+    out.prod = b.add_op(name, {&a, &blow}, [av, bv, ov, s, t, r](cudaStream_t st, const RunArgs&) {
+      return upadd_launch(av, bv, ov, s, t, r, st);
+    });
+    return out;
+  }
+  // segmenthead (model_utils.py:100-112): `xin` must already hold relu(bn1(x)); writes fp32 NCHW slot
+  void seghead_tail(const std::string& p, const T& xin, int slot) {
+    T h = conv_bn(p + ".conv1", xin, p + ".conv1", p + ".bn2", 3, 1, true);
+    std::vector<float> bias;
+    ConvSrcSpec s = src_of(h, p + ".conv2", nullptr, 1, 1, &bias);
+    b.conv(p + ".conv2", {s}, bias, static_cast<int>(P(p + ".conv2.weight").shape[0]), false, nullptr, nullptr, slot);
+  }
+
+  // PagFM (model_utils.py:292-312) with compressionK folded in: one low-res 1x1 conv from the I-branch
+  // tensor produces [y | z | t] (see DESIGN.md "PagFM algebra"), then the fuse kernel.
+  T pag(const std::string& pg, const std::string& comp, const T& xhi, const T& ilow) {
+    const int C2 = xhi.C, Ci = ilow.C, Pm = static_cast<int>(P(pg + ".f_x.0.weight").shape[0]);
+    const Affine ac = bn(comp + ".1"), ax = bn(pg + ".f_x.1"), ay = bn(pg + ".f_y.1");
+    const auto& Wc = P(comp + ".0.weight").data;     // [C2][Ci]
+    const auto& Wx = P(pg + ".f_x.0.weight").data;   // [Pm][C2]
+    const auto& Wy = P(pg + ".f_y.0.weight").data;   // [Pm][C2]
+    // y = Yw I + yb
+    std::vector<double> Yw(static_cast<size_t>(C2) * Ci), yb(C2);
+    for (int c = 0; c < C2; ++c) {
+      for (int i = 0; i < Ci; ++i) Yw[static_cast<size_t>(c) * Ci + i] = static_cast<double>(ac.s[c]) * Wc[static_cast<size_t>(c) * Ci + i];
+      yb[c] = ac.t[c];
+    }
+    // G = Ax^T Ay  (C2 x C2), g0 = Ax^T ty ; r = tx^T Ay (1 x C2), r0 = tx . ty
+    std::vector<double> G(static_cast<size_t>(C2) * C2, 0.0), g0(C2, 0.0), r(C2, 0.0);
+    double r0 = 0.0;
+    for (int m = 0; m < Pm; ++m) {
+      for (int a = 0; a < C2; ++a) {
+        const double axv = static_cast<double>(ax.s[m]) * Wx[static_cast<size_t>(m) * C2 + a];
+        for (int c = 0; c < C2; ++c) G[static_cast<size_t>(a) * C2 + c] += axv * (static_cast<double>(ay.s[m]) * Wy[static_cast<size_t>(m) * C2 + c]);
+        g0[a] += axv * ay.t[m];
+      }
+      for (int c = 0; c < C2; ++c) r[c] += static_cast<double>(ax.t[m]) * (static_cast<double>(ay.s[m]) * Wy[static_cast<size_t>(m) * C2 + c]);
+      r0 += static_cast<double>(ax.t[m]) * ay.t[m];
+    }
+    const int CL = 2 * C2 + 8;
+    ConvSrcSpec s;
+    s.in = ilow; s.k = 1; s.stride = 1;
+    s.w.assign(static_cast<size_t>(CL) * Ci, 0.f);
+    std::vector<float> bias(CL, 0.f);
+    for (int c = 0; c < C2; ++c) {
+      for (int i = 0; i < Ci; ++i) s.w[static_cast<size_t>(c) * Ci + i] = static_cast<float>(Yw[static_cast<size_t>(c) * Ci + i]);
+      bias[c] = static_cast<float>(yb[c]);
+    }
+    for (int a = 0; a < C2; ++a) {  // z = G y + g0
+      double bz = g0[a];
+      for (int c = 0; c < C2; ++c) bz += G[static_cast<size_t>(a) * C2 + c] * yb[c];
+      bias[C2 + a] = static_cast<float>(bz);
+      for (int i = 0; i < Ci; ++i) {
+        double acc = 0.0;
+        for (int c = 0; c < C2; ++c) acc += G[static_cast<size_t>(a) * C2 + c] * Yw[static_cast<size_t>(c) * Ci + i];
+        s.w[static_cast<size_t>(C2 + a) * Ci + i] = static_cast<float>(acc);
+      }
+    }
+    {  // t = r y + r0
+      double bt = r0;
+      for (int c = 0; c < C2; ++c) bt += r[c] * yb[c];
+      bias[2 * C2] = static_cast<float>(bt);
+      for (int i = 0; i < Ci; ++i) {
+        double acc = 0.0;
+        for (int c = 0; c < C2; ++c) acc += r[c] * Yw[static_cast<size_t>(c) * Ci + i];
+        s.w[static_cast<size_t>(2 * C2) * Ci + i] = static_cast<float>(acc);
+      }
+    }
+    T low = b.conv(pg + ".low", {s}, bias, CL, false, nullptr, nullptr, -1);
+    T out = b.new_tensor(xhi.N, xhi.H, xhi.W, C2);
+    View xv = xhi.view(), lv = low.view(), ov = out.view();
+    out.prod = b.add_op(pg + ".fuse", {&xhi, &low}, [xv, lv, ov](cudaStream_t st, const RunArgs&) {
+      return pag_fuse_launch(xv, lv, ov, 1, st);
+    });
+    return out;
+  }
+
+  T pool_affine(const std::string& name, const T& x, int k, int stride, int pad, const Affine& a) {
+    const int oh = k == 0 ? 1 : (x.H + 2 * pad - k) / stride + 1;
+    const int ow = k == 0 ? 1 : (x.W + 2 * pad - k) / stride + 1;
+    if (oh < 1 || ow < 1) fail(name + ": pooled map is empty");
+    T out = b.new_tensor(x.N, oh, ow, x.C);
+    const float* s = b.upload_f32(a.s);
+    const float* t = b.upload_f32(a.t);
+    View xv = x.view(), ov = out.view();
+    out.prod = b.add_op(name, {&x}, [xv, ov, k, stride, pad, s, t](cudaStream_t st, const RunArgs&) {
+      return pool_affine_launch(xv, ov, k, stride, pad, s, t, 1, st);
+    });
+    return out;
+  }
+  T conv_plain(const std::string& name, const T& x, const std::string& conv, const Affine* post, int k, bool relu,
+               const T* out_view) {
+    std::vector<float> bias;
+    ConvSrcSpec s = src_of(x, conv, post, k, 1, &bias);
+    return b.conv(name, {s}, bias, static_cast<int>(P(conv + ".weight").shape[0]), relu, nullptr, out_view, -1);
+  }
+
+  // PAPPM (model_utils.py:247-265) / DAPPM (:174-194).  Pre-activation BNs are applied by the producers.
+  T spp(const T& x) {
+    const bool large = cfg.m == 3;
+    const int ppm = cfg.ppm_planes, outp = cfg.planes * 4;
+    static const int pk[3] = {5, 9, 17}, pstr[3] = {2, 4, 8}, pp[3] = {2, 4, 8};
+    // scale branches: BN -> ReLU (after the pool) then 1x1
+    T a0 = affine_relu("spp.scale0.bnrelu", x, bn("spp.scale0.0"), nullptr);
+    T s0 = conv_plain("spp.scale0.conv", a0, "spp.scale0.2", nullptr, 1, false, nullptr);
+    T sk[4];
+    for (int k = 0; k < 4; ++k) {
+      const std::string sp = "spp.scale" + std::to_string(k + 1);
+      T ak = k < 3 ? pool_affine(sp + ".pool", x, pk[k], pstr[k], pp[k], bn(sp + ".1"))
+                   : pool_affine(sp + ".pool", x, 0, 1, 0, bn(sp + ".1"));
+      sk[k] = conv_plain(sp + ".conv", ak, sp + ".3", nullptr, 1, false, nullptr);
+    }
+    const Affine acomp = bn("spp.compression.0");
+    T comp_in = b.new_tensor(x.N, x.H, x.W, 5 * ppm);
+    if (!large) {
+      const Affine asp = bn("spp.scale_process.0");
+      T sp_in = b.new_tensor(x.N, x.H, x.W, 4 * ppm);
+      for (int k = 0; k < 4; ++k) {
+        T dst = Builder::slice(sp_in, k * ppm, ppm);
+        Affine a = slice(asp, k * ppm, ppm);
+        T w = upadd("spp.scale" + std::to_string(k + 1) + ".upadd", s0, sk[k], &a, true, &dst);
+        sp_in.prod = w.prod;  // all four writers are on this lane; the last one orders the consumer
+      }
+      T c0 = Builder::slice(comp_in, 0, ppm);
+      affine_relu("spp.x_.bnrelu", s0, slice(acomp, 0, ppm), &c0);
+      // grouped 3x3 (groups=4, model_utils.py:230) as four convs on channel slices; epilogue applies the
+      // compression BN slice + ReLU
+      const HostParam& gw = P("spp.scale_process.2.weight");  // [4*ppm][ppm][3][3]
+      for (int g = 0; g < 4; ++g) {
+        ConvSrcSpec s;
+        s.in = Builder::slice(sp_in, g * ppm, ppm);
+        s.k = 3; s.stride = 1;
+        const size_t per = static_cast<size_t>(ppm) * 9;
+        s.w.assign(gw.data.begin() + static_cast<size_t>(g) * ppm * per, gw.data.begin() + static_cast<size_t>(g + 1) * ppm * per);
+        std::vector<float> bias(ppm);
+        for (int co = 0; co < ppm; ++co) {
+          const float sc = acomp.s[ppm + g * ppm + co];
+          for (size_t i = 0; i < per; ++i) s.w[co * per + i] *= sc;
+          bias[co] = acomp.t[ppm + g * ppm + co];
+        }
+        T dst = Builder::slice(comp_in, ppm + g * ppm, ppm);
+        T w = b.conv("spp.scale_process.g" + std::to_string(g), {s}, bias, ppm, true, nullptr, &dst, -1);
+        comp_in.prod = w.prod;
+      }
+    } else {
+      T prev = s0;
+      T c0 = Builder::slice(comp_in, 0, ppm);
+      affine_relu("spp.x0.bnrelu", s0, slice(acomp, 0, ppm), &c0);
+      for (int k = 0; k < 4; ++k) {
+        const std::string pr = "spp.process" + std::to_string(k + 1);
+        Affine a = bn(pr + ".0");
+        T yin = upadd(pr + ".upadd", prev, sk[k], &a, true, nullptr);
+        prev = conv_plain(pr + ".conv", yin, pr + ".2", nullptr, 3, false, nullptr);
+        T dst = Builder::slice(comp_in, (k + 1) * ppm, ppm);
+        T w = affine_relu(pr + ".bnrelu", prev, slice(acomp, (k + 1) * ppm, ppm), &dst);
+        comp_in.prod = w.prod;
+      }
+    }
+    T sc_in = affine_relu("spp.shortcut.bnrelu", x, bn("spp.shortcut.0"), nullptr);
+    std::vector<float> bias;
+    std::vector<ConvSrcSpec> srcs;
+    srcs.push_back(src_of(comp_in, "spp.compression.2", nullptr, 1, 1, &bias));
+    srcs.push_back(src_of(sc_in, "spp.shortcut.2", nullptr, 1, 1, &bias));
+    return b.conv("spp.compression+shortcut", srcs, bias, outp, false, nullptr, nullptr, -1);
+  }
+
+  // ---- the net (pidnet.py:136-182)
+  void build() {
+    const int Pn = cfg.planes, m = cfg.m, n = cfg.n;
+    const bool large = m == 3;
+    const int L0 = 0, LP = lanes == 3 ? 1 : 0, LD = lanes == 3 ? 2 : 0;
+    if (H % 8 || W % 8) fail("H and W must be multiples of 8");
+    b.conv_impl = conv_impl;
+
+    // stem conv1.0 + BN + ReLU : fp32 NCHW -> bf16 NHWC
+    b.lane = L0;
+    T x1 = b.new_tensor(N, cdiv(H, 2), cdiv(W, 2), Pn);
+    {
+      Affine a = bn("conv1.1");
+      std::vector<float> w, bias;
+      fold("conv1.0", &a, w, bias);  // [P][3][3][3]
+      if (P("conv1.0.weight").shape[1] != 3) fail("conv1.0 must have 3 input channels");
+      std::vector<float> wt(static_cast<size_t>(27) * Pn);
+      for (int co = 0; co < Pn; ++co)
+        for (int k = 0; k < 27; ++k) wt[static_cast<size_t>(k) * Pn + co] = w[static_cast<size_t>(co) * 27 + k];
+      const float* wd = b.upload_f32(wt);
+      const float* bd = b.upload_f32(bias);
+      View ov = x1.view();
+      const int n_ = N, h_ = H, w_ = W;
+      b.flops += 2.0 * N * x1.H * x1.W * Pn * 27;
+      x1.prod = b.add_op("conv1.0", {}, [ov, wd, bd, n_, h_, w_](cudaStream_t st, const RunArgs& a) {
+        return stem_conv_launch(a.x, n_, h_, w_, ov, wd, bd, st);
+      });
+    }
+    T x = conv_bn("conv1.3", x1, "conv1.3", "conv1.4", 3, 2, true);
+    b.named["conv1"] = x;
+    x = layer("layer1", x, false, m, 1, true);
+    b.named["layer1"] = x;
+    x = layer("layer2", x, false, m, 2, true);
+    b.named["layer2"] = x;
+    const T x8 = x;
+
+    b.lane = LP;
+    T xp = layer("layer3_", x8, false, m, 1, false);
+    b.named["layer3_"] = xp;
+    b.lane = LD;
+    T xd = basic_block("layer3_d", x8, 1, false);
+    b.named["layer3_d"] = xd;
+
+    b.lane = L0;
+    T xi = layer("layer3", x8, false, n, 2, true);
+    b.named["layer3"] = xi;
+    b.lane = LP;
+    xp = pag("pag3", "compression3", xp, xi);
+    b.named["pag3"] = xp;
+    const T temp_p = xp;
+    b.lane = LD;
+    {
+      T d3 = conv_bn("diff3", xi, "diff3.0", "diff3.1", 3, 1, false);
+      xd = upadd("diff3.upadd", xd, d3, nullptr, true, nullptr);
+      b.named["xd3"] = xd;
+    }
+    b.lane = L0;
+    T xi4 = layer("layer4", xi, false, n, 2, true);
+    b.named["layer4"] = xi4;
+    b.lane = LP;
+    xp = layer("layer4_", xp, false, m, 1, false);
+    b.named["layer4_"] = xp;
+    b.lane = LD;
+    xd = large ? basic_block("layer4_d", xd, 1, false) : layer("layer4_d", xd, true, 1, 1, false);
+    b.named["layer4_d"] = xd;
+    b.lane = LP;
+    xp = pag("pag4", "compression4", xp, xi4);
+    b.named["pag4"] = xp;
+    b.lane = LD;
+    {
+      T d4 = conv_bn("diff4", xi4, "diff4.0", "diff4.1", 3, 1, false);
+      xd = upadd("diff4.upadd", xd, d4, nullptr, true, nullptr);
+      b.named["xd4"] = xd;
+    }
+    const T temp_d = xd;
+    b.lane = LP;
+    xp = layer("layer5_", xp, true, 1, 1, false);
+    b.named["layer5_"] = xp;
+    if (cfg.augment) {
+      T hp = affine_relu("seghead_p.bn1", temp_p, bn("seghead_p.bn1"), nullptr);
+      seghead_tail("seghead_p", hp, 1);
+    }
+    b.lane = LD;
+    xd = layer("layer5_d", xd, true, 1, 1, false);
+    b.named["layer5_d"] = xd;
+    if (cfg.augment) {
+      T hd = affine_relu("seghead_d.bn1", temp_d, bn("seghead_d.bn1"), nullptr);
+      seghead_tail("seghead_d", hd, 2);
+    }
+    b.lane = L0;
+    T x5 = layer("layer5", xi4, true, 2, 2, false);
+    b.named["layer5"] = x5;
+    T sp = spp(x5);
+    b.named["spp"] = sp;
+
+    // dfm + final_layer.bn1/ReLU folded into its epilogue
+    const Affine a1 = bn("final_layer.bn1");
+    T f;
+    if (!large) {
+      const int C4 = 4 * Pn;
+      T uv = b.new_tensor(N, xp.H, xp.W, 2 * C4);
+      View pv = xp.view(), iv = sp.view(), dv = xd.view(), ov = uv.view();
+      uv.prod = b.add_op("dfm.uv", {&xp, &sp, &xd}, [pv, iv, dv, ov](cudaStream_t st, const RunArgs&) {
+        return lightbag_uv_launch(pv, iv, dv, ov, st);
+      });
+      const Affine ap = bn("dfm.conv_p.1"), ai = bn("dfm.conv_i.1");
+      const auto &Wp = P("dfm.conv_p.0.weight").data, &Wi = P("dfm.conv_i.0.weight").data;
+      ConvSrcSpec s;
+      s.in = uv; s.k = 1; s.stride = 1;
+      s.w.resize(static_cast<size_t>(C4) * 2 * C4);
+      std::vector<float> bias(C4);
+      for (int co = 0; co < C4; ++co) {
+        for (int ci = 0; ci < C4; ++ci) {
+          s.w[static_cast<size_t>(co) * 2 * C4 + ci] = a1.s[co] * ap.s[co] * Wp[static_cast<size_t>(co) * C4 + ci];
+          s.w[static_cast<size_t>(co) * 2 * C4 + C4 + ci] = a1.s[co] * ai.s[co] * Wi[static_cast<size_t>(co) * C4 + ci];
+        }
+        bias[co] = a1.s[co] * (ap.t[co] + ai.t[co]) + a1.t[co];
+      }
+      f = b.conv("dfm.conv_p+conv_i", {s}, bias, C4, true, nullptr, nullptr, -1);
+    } else {
+      const Affine ab = bn("dfm.conv.0");
+      T a = b.new_tensor(N, xp.H, xp.W, xp.C);
+      const float* s_ = b.upload_f32(ab.s);
+      const float* t_ = b.upload_f32(ab.t);
+      View pv = xp.view(), iv = sp.view(), dv = xd.view(), ov = a.view();
+      a.prod = b.add_op("dfm.blend", {&xp, &sp, &xd}, [pv, iv, dv, ov, s_, t_](cudaStream_t st, const RunArgs&) {
+        return bag_blend_launch(pv, iv, dv, ov, s_, t_, st);
+      });
+      f = conv_plain("dfm.conv", a, "dfm.conv.2", &a1, 3, true, nullptr);
+    }
+    b.named["dfm"] = f;
+    seghead_tail("final_layer", f, 0);
+  }
+
+  void plan(int N_, int H_, int W_) {
+    release();
+    N = N_; H = H_; W = W_;
+    cudaDeviceProp prop;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaGetDeviceProperties(&prop, dev));
+    b.num_sms = prop.multiProcessorCount;
+    if (conv_impl == 0) {
+      if (prop.major != 10) fail("the tcgen05 conv path needs an sm_100 GPU (found sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+      CK(conv_tc_init());
+    }
+    b.reset(true);
+    build();  // dry pass: sizes only
+    const size_t act_bytes = b.act_cur, wt_bytes = b.wt_cur;
+    CK(cudaMalloc(&b.act_base, std::max<size_t>(act_bytes, 1024)));
+    CK(cudaMalloc(&b.wt_base, std::max<size_t>(wt_bytes, 1024)));
+    b.wt_host.assign(wt_bytes, 0);
+    b.reset(false);
+    build();
+    if (b.act_cur != act_bytes || b.wt_cur != wt_bytes) fail("planner passes disagree");
+    CK(cudaMemcpy(b.wt_base, b.wt_host.data(), wt_bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemset(b.act_base, 0, act_bytes));
+    b.wt_host.clear();
+    b.wt_host.shrink_to_fit();
+    // streams / events
+    for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+    ev_of_op.assign(b.ops.size(), -1);
+    for (size_t i = 0; i < b.ops.size(); ++i)
+      if (b.ops[i].record) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev_of_op[i] = static_cast<int>(events.size());
+        events.push_back(e);
+      }
+    planned = true;
+  }
+
+  void enqueue(cudaStream_t stream, const RunArgs& a) {
+    bool used[3] = {true, false, false};
+    for (const Op& op : b.ops) used[op.lane] = true;
+    CK(cudaEventRecord(ev_start, stream));
+    for (int l = 1; l < 3; ++l)
+      if (used[l]) CK(cudaStreamWaitEvent(side[l - 1], ev_start, 0));
+    for (size_t i = 0; i < b.ops.size(); ++i) {
+      const Op& op = b.ops[i];
+      cudaStream_t s = op.lane == 0 ? stream : side[op.lane - 1];
+      for (int d : op.deps) CK(cudaStreamWaitEvent(s, events[ev_of_op[d]], 0));
+      cudaError_t e = op.fn(s, a);
+      if (e != cudaSuccess) fail("launch of '" + op.name + "' failed: " + cudaGetErrorString(e));
+      if (op.record) CK(cudaEventRecord(events[ev_of_op[i]], s));
+    }
+    for (int l = 1; l < 3; ++l)
+      if (used[l]) {
+        CK(cudaEventRecord(ev_join[l - 1], side[l - 1]));
+        CK(cudaStreamWaitEvent(stream, ev_join[l - 1], 0));
+      }
+  }
+
+  void forward(cudaStream_t stream, const RunArgs& a, bool use_graph) {
+    if (!planned) fail("pidnet_forward called before pidnet_plan");
+    if (!a.x || !a.out[0]) fail("null input/output pointer");
+    if (cfg.augment && (!a.out[1] || !a.out[2])) fail("augment=1 needs out_p and out_d");
+    if (!use_graph) {
+      enqueue(stream, a);
+      return;
+    }
+    if (!gexec || std::memcmp(&gargs, &a, sizeof(RunArgs)) != 0) {
+      if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        enqueue(stream, a);
+      } catch (...) {
+        cudaStreamEndCapture(stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      CK(cudaStreamEndCapture(stream, &g));
+      cudaError_t e = cudaGraphInstantiate(&gexec, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) { gexec = nullptr; fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+      gargs = a;
+    }
+    CK(cudaGraphLaunch(gexec, stream));
+  }
+};
+
+// ----------------------------------------------------------------------------------------- C ABI glue
+template <class F>
+static int guard(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  } catch (...) {
+    g_err = "unknown error";
+    return -2;
+  }
+}
+
+static T ext_tensor(const void* ptr, int N, int H, int W, int C) {
+  T t;
+  t.ptr = reinterpret_cast<bf16*>(const_cast<void*>(ptr));
+  t.N = N; t.H = H; t.W = W; t.C = C; t.ps = C;
+  return t;
+}
+
+}  // namespace pidnet
+
+using namespace pidnet;
+
+struct pidnet_engine {
+  Engine e;
+};
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* pidnet_last_error(void) { return g_err.c_str(); }
+int pidnet_abi_version(void) { return 1; }
+
+int pidnet_create(const pidnet_cfg* cfg, pidnet_engine** out) {
+  return guard([&] {
+    if (!cfg || !out) fail("null argument");
+    if (!((cfg->m == 2 && cfg->n >= 1) || (cfg->m == 3 && cfg->n >= 1))) fail("m must be 2 (S/M) or 3 (L)");
+    if (cfg->planes % 8 || cfg->ppm_planes % 8 || cfg->head_planes % 8) fail("planes/ppm_planes/head_planes must be multiples of 8");
+    if (cfg->num_classes < 1) fail("num_classes must be positive");
+    pidnet_engine* h = new pidnet_engine();
+    h->e.cfg = *cfg;
+    *out = h;
+  });
+}
+
+int pidnet_destroy(pidnet_engine* h) {
+  return guard([&] { delete h; });
+}
+
+int pidnet_set_param(pidnet_engine* h, const char* key, const float* host_data, const int64_t* shape, int ndim) {
+  return guard([&] {
+    if (!h || !key || !host_data) fail("null argument");
+    HostParam p;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+      p.shape.push_back(shape[i]);
+      n *= static_cast<size_t>(shape[i]);
+    }
+    p.data.assign(host_data, host_data + n);
+    h->e.params[key] = std::move(p);
+    h->e.planned = false;
+  });
+}
+
+int pidnet_set_option(pidnet_engine* h, const char* name, int value) {
+  return guard([&] {
+    if (!h || !name) fail("null argument");
+    const std::string k = name;
+    if (k == "conv_impl") h->e.conv_impl = value;
+    else if (k == "lanes") h->e.lanes = value == 3 ? 3 : 1;
+    else fail("unknown option '" + k + "'");
+    h->e.planned = false;
+  });
+}
+
+int pidnet_plan(pidnet_engine* h, int N, int H, int W, size_t* arena_bytes) {
+  return guard([&] {
+    if (!h) fail("null handle");
+    if (N < 1 || H < 8 || W < 8) fail("bad input shape");
+    h->e.plan(N, H, W);
+    if (arena_bytes) *arena_bytes = h->e.b.act_cur + h->e.b.wt_cur;
+  });
+}
+
+int pidnet_forward(pidnet_engine* h, void* stream, const float* x, float* out_main, float* out_p, float* out_d,
+                   int use_graph) {
+  return guard([&] {
+    if (!h) fail("null handle");
+    RunArgs a{x, {out_main, out_p, out_d}};
+    h->e.forward(reinterpret_cast<cudaStream_t>(stream), a, use_graph != 0);
+  });
+}
+
+int pidnet_num_launches(pidnet_engine* h) { return h ? static_cast<int>(h->e.b.ops.size()) : -1; }
+double pidnet_conv_flops(pidnet_engine* h) { return h ? h->e.b.flops : -1.0; }
+
+int pidnet_debug_tensor(pidnet_engine* h, const char* name, float* host_out, int64_t* shape4) {
+  return guard([&] {
+    if (!h || !name) fail("null argument");
+    auto it = h->e.b.named.find(name);
+    if (it == h->e.b.named.end()) fail(std::string("no tensor named '") + name + "'");
+    const T& t = it->second;
+    if (shape4) { shape4[0] = t.N; shape4[1] = t.C; shape4[2] = t.H; shape4[3] = t.W; }
+    if (!host_out) return;
+    CK(cudaDeviceSynchronize());
+    const size_t npix = static_cast<size_t>(t.N) * t.H * t.W;
+    std::vector<uint16_t> tmp(npix * t.ps);
+    CK(cudaMemcpy(tmp.data(), t.ptr, (npix - 1) * t.ps * 2 + static_cast<size_t>(t.C) * 2, cudaMemcpyDeviceToHost));
+    for (int n = 0; n < t.N; ++n)
+      for (int c = 0; c < t.C; ++c)
+        for (int y = 0; y < t.H; ++y)
+          for (int x = 0; x < t.W; ++x)
+            host_out[((static_cast<size_t>(n) * t.C + c) * t.H + y) * t.W + x] =
+                bf2f(tmp[((static_cast<size_t>(n) * t.H + y) * t.W + x) * t.ps + c]);
+  });
+}
+
+// ---- single-op entry points
+int pidnet_op_conv2d(void* stream, const void* x, int N, int H, int W, int Cin, const float* w, const float* bias,
+                     int Cout, int k, int stride, int groups, const void* res, int relu, void* out_nhwc,
+                     float* out_nchw_f32, int impl) {
+  return guard([&] {
+    if (!x || !w || (!out_nhwc == !out_nchw_f32)) fail("bad arguments");
+    if (groups < 1 || Cin % groups || Cout % groups) fail("bad groups");
+    if (groups > 1 && out_nchw_f32) fail("grouped conv with NCHW output is not supported");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (impl == 0) CK(conv_tc_init());
+    const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
+    const int cig = Cin / groups, cog = Cout / groups;
+    Builder b;
+    cudaDeviceProp prop;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaGetDeviceProperties(&prop, dev));
+    b.num_sms = prop.multiProcessorCount;
+    b.conv_impl = impl;
+    T xin = ext_tensor(x, N, H, W, Cin);
+    T rt, ot;
+    if (res) rt = ext_tensor(res, N, Ho, Wo, Cout);
+    if (out_nhwc) ot = ext_tensor(out_nhwc, N, Ho, Wo, Cout);
+    auto build = [&] {
+      for (int g = 0; g < groups; ++g) {
+        ConvSrcSpec s;
+        s.in = groups > 1 ? Builder::slice(xin, g * cig, cig) : xin;
+        s.k = k; s.stride = stride;
+        const size_t per = static_cast<size_t>(cig) * k * k;
+        s.w.assign(w + static_cast<size_t>(g) * cog * per, w + static_cast<size_t>(g + 1) * cog * per);
+        std::vector<float> bs(cog, 0.f);
+        if (bias) bs.assign(bias + g * cog, bias + (g + 1) * cog);
+        T rs, os;
+        if (res) rs = groups > 1 ? Builder::slice(rt, g * cog, cog) : rt;
+        if (out_nhwc) os = groups > 1 ? Builder::slice(ot, g * cog, cog) : ot;
+        b.conv("op_conv2d", {s}, bs, cog, relu != 0, res ? &rs : nullptr, out_nhwc ? &os : nullptr,
+               out_nchw_f32 ? 0 : -1);
+      }
+    };
+    b.reset(true);
+    build();
+    const size_t wt_bytes = b.wt_cur;
+    CK(cudaMalloc(&b.wt_base, std::max<size_t>(wt_bytes, 1024)));
+    b.wt_host.assign(wt_bytes, 0);
+    b.reset(false);
+    try {
+      build();
+      CK(cudaMemcpyAsync(b.wt_base, b.wt_host.data(), wt_bytes, cudaMemcpyHostToDevice, st));
+      RunArgs a{nullptr, {out_nchw_f32, nullptr, nullptr}};
+      for (auto& op : b.ops) {
+        cudaError_t e = op.fn(st, a);
+        if (e != cudaSuccess) fail(std::string("conv launch failed: ") + cudaGetErrorString(e));
+      }
+      CK(cudaStreamSynchronize(st));
+    } catch (...) {
+      cudaFree(b.wt_base);
+      throw;
+    }
+    CK(cudaFree(b.wt_base));
+  });
+}
+
+int pidnet_op_stem(void* stream, const float* x, int N, int H, int W, const float* w, const float* bias, int Cout,
+                   void* out) {
+  return guard([&] {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    std::vector<float> wt(static_cast<size_t>(27) * Cout), bs(Cout, 0.f);
+    for (int co = 0; co < Cout; ++co)
+      for (int k = 0; k < 27; ++k) wt[static_cast<size_t>(k) * Cout + co] = w[static_cast<size_t>(co) * 27 + k];
+    if (bias) bs.assign(bias, bias + Cout);
+    float* d = nullptr;
+    CK(cudaMalloc(&d, (wt.size() + bs.size()) * 4));
+    CK(cudaMemcpyAsync(d, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + wt.size(), bs.data(), bs.size() * 4, cudaMemcpyHostToDevice, st));
+    T o = ext_tensor(out, N, cdiv(H, 2), cdiv(W, 2), Cout);
+    cudaError_t e = stem_conv_launch(x, N, H, W, o.view(), d, d + wt.size(), st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d);
+    CK(e);
+    CK(e2);
+  });
+}
+
+int pidnet_op_pag(void* stream, const void* x, const void* low, void* out, int N, int H, int W, int C, int h, int w,
+                  int relu) {
+  return guard([&] {
+    CK(pag_fuse_launch(ext_tensor(x, N, H, W, C).view(), ext_tensor(low, N, h, w, 2 * C + 8).view(),
+                       ext_tensor(out, N, H, W, C).view(), relu, reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
+
+int pidnet_op_upadd(void* stream, const void* a, const void* bb, void* out, int N, int H, int W, int C, int h, int w,
+                    const float* s, const float* t, int relu) {
+  return guard([&] {
+    View av = a ? ext_tensor(a, N, H, W, C).view() : View{nullptr, 0, 0, 0, 0, 0};
+    View bv = bb ? ext_tensor(bb, N, h, w, C).view() : View{nullptr, 0, 0, 0, 0, 0};
+    CK(upadd_launch(av, bv, ext_tensor(out, N, H, W, C).view(), s, t, relu, reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
+
+int pidnet_op_pool(void* stream, const void* x, void* out, int N, int H, int W, int C, int k, int stride, int pad,
+                   const float* s, const float* t, int relu) {
+  return guard([&] {
+    const int oh = k == 0 ? 1 : (H + 2 * pad - k) / stride + 1, ow = k == 0 ? 1 : (W + 2 * pad - k) / stride + 1;
+    CK(pool_affine_launch(ext_tensor(x, N, H, W, C).view(), ext_tensor(out, N, oh, ow, C).view(), k, stride, pad, s, t,
+                          relu, reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
+
+int pidnet_op_lightbag(void* stream, const void* p, const void* i_low, const void* d, void* out, int N, int H, int W,
+                       int C, int h, int w) {
+  return guard([&] {
+    CK(lightbag_uv_launch(ext_tensor(p, N, H, W, C).view(), ext_tensor(i_low, N, h, w, C).view(),
+                          ext_tensor(d, N, H, W, C).view(), ext_tensor(out, N, H, W, 2 * C).view(),
+                          reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
+
+int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d, void* out, int N, int H, int W, int C,
+                  int h, int w, const float* s, const float* t) {
+  return guard([&] {
+    CK(bag_blend_launch(ext_tensor(p, N, H, W, C).view(), ext_tensor(i_low, N, h, w, C).view(),
+                        ext_tensor(d, N, H, W, C).view(), ext_tensor(out, N, H, W, C).view(), s, t,
+                        reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,394 @@
+// HBM-bound fused kernels: 128-bit vectorised NHWC bf16 access, fp32 math.
+#include "kernels.cuh"
+
+namespace pidnet {
+
+namespace {
+
+struct F8 {
+  float v[8];
+};
+
+__device__ __forceinline__ F8 ld8(const bf16* p) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  F8 r;
+  r.v[0] = __uint_as_float(u.x << 16); r.v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  r.v[2] = __uint_as_float(u.y << 16); r.v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  r.v[4] = __uint_as_float(u.z << 16); r.v[5] = __uint_as_float(u.z & 0xFFFF0000u);
+  r.v[6] = __uint_as_float(u.w << 16); r.v[7] = __uint_as_float(u.w & 0xFFFF0000u);
+  return r;
+}
+__device__ __forceinline__ uint32_t pk(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st8(bf16* p, const F8& f) {
+  uint4 o;
+  o.x = pk(f.v[0], f.v[1]); o.y = pk(f.v[2], f.v[3]); o.z = pk(f.v[4], f.v[5]); o.w = pk(f.v[6], f.v[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+// torch upsample_bilinear2d, align_corners=False: src = max(0, scale*(dst+0.5)-0.5), scale = in/out (fp32)
+struct Lerp {
+  int i0, i1;
+  float l;
+};
+__device__ __forceinline__ Lerp lerp_of(int dst, int in, int out) {
+  const float scale = static_cast<float>(in) / static_cast<float>(out);
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  Lerp r;
+  r.i0 = static_cast<int>(src);
+  if (r.i0 > in - 1) r.i0 = in - 1;
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.l = src - static_cast<float>(r.i0);
+  return r;
+}
+
+// bilinear sample of 8 channels of a low-res view at hi-res pixel (h, w) of an (H, W) grid
+__device__ __forceinline__ F8 sample8(const View& b, int n, const Lerp& lh, const Lerp& lw, int c) {
+  const bf16* base = b.ptr + static_cast<long>(n) * b.H * b.W * b.ps + c;
+  const F8 v00 = ld8(base + (static_cast<long>(lh.i0) * b.W + lw.i0) * b.ps);
+  const F8 v01 = ld8(base + (static_cast<long>(lh.i0) * b.W + lw.i1) * b.ps);
+  const F8 v10 = ld8(base + (static_cast<long>(lh.i1) * b.W + lw.i0) * b.ps);
+  const F8 v11 = ld8(base + (static_cast<long>(lh.i1) * b.W + lw.i1) * b.ps);
+  const float w00 = (1.f - lh.l) * (1.f - lw.l), w01 = (1.f - lh.l) * lw.l;
+  const float w10 = lh.l * (1.f - lw.l), w11 = lh.l * lw.l;
+  F8 r;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) r.v[e] = w00 * v00.v[e] + w01 * v01.v[e] + w10 * v10.v[e] + w11 * v11.v[e];
+  return r;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// --------------------------------------------------------------------------- stem
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, int N, int H, int W, View out,
+                                                        const float* __restrict__ w, const float* __restrict__ bias) {
+  extern __shared__ float ws[];  // [27][Cout] + [Cout]
+  const int Cout = out.C;
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) ws[27 * Cout + i] = bias[i];
+  __syncthreads();
+  const int groups = Cout >> 3;
+  const long total = static_cast<long>(N) * out.H * out.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  long pix = idx / groups;
+  const int ow = static_cast<int>(pix % out.W);
+  pix /= out.W;
+  const int oh = static_cast<int>(pix % out.H);
+  const int n = static_cast<int>(pix / out.H);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = ws[27 * Cout + cg * 8 + e];
+  const float* xn = x + static_cast<long>(n) * 3 * H * W;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(xn + (static_cast<long>(ci) * H + ih) * W + iw);
+        const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * 3 + r) * 3 + s) * Cout + cg * 8);
+        const float4 wa = wp[0], wb = wp[1];
+        acc[0] += v * wa.x; acc[1] += v * wa.y; acc[2] += v * wa.z; acc[3] += v * wa.w;
+        acc[4] += v * wb.x; acc[5] += v * wb.y; acc[6] += v * wb.z; acc[7] += v * wb.w;
+      }
+    }
+  }
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = fmaxf(acc[e], 0.f);
+  st8(out.ptr + ((static_cast<long>(n) * out.H + oh) * out.W + ow) * out.ps + cg * 8, o);
+}
+
+// --------------------------------------------------------------------------- PagFM fuse
+template <int LP>  // lanes per pixel = C/8
+__global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View out, int relu) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long npix = static_cast<long>(x.N) * x.H * x.W;
+  long pix = gid / LP;
+  const int cg = static_cast<int>(gid % LP);
+  const bool valid = pix < npix;
+  if (!valid) pix = npix - 1;
+  const int w = static_cast<int>(pix % x.W);
+  const long t1 = pix / x.W;
+  const int h = static_cast<int>(t1 % x.H);
+  const int n = static_cast<int>(t1 / x.H);
+  const int C = x.C;
+  const Lerp lh = lerp_of(h, low.H, x.H), lw = lerp_of(w, low.W, x.W);
+  const F8 xv = ld8(x.ptr + pix * x.ps + cg * 8);
+  const F8 yv = sample8(low, n, lh, lw, cg * 8);
+  const F8 zv = sample8(low, n, lh, lw, C + cg * 8);
+  float dot = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dot += xv.v[e] * zv.v[e];
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  // scalar term t (channel 2C of `low`)
+  const bf16* tb = low.ptr + static_cast<long>(n) * low.H * low.W * low.ps + 2 * C;
+  const float t00 = __bfloat162float(tb[(static_cast<long>(lh.i0) * low.W + lw.i0) * low.ps]);
+  const float t01 = __bfloat162float(tb[(static_cast<long>(lh.i0) * low.W + lw.i1) * low.ps]);
+  const float t10 = __bfloat162float(tb[(static_cast<long>(lh.i1) * low.W + lw.i0) * low.ps]);
+  const float t11 = __bfloat162float(tb[(static_cast<long>(lh.i1) * low.W + lw.i1) * low.ps]);
+  const float tt = (1.f - lh.l) * ((1.f - lw.l) * t00 + lw.l * t01) + lh.l * ((1.f - lw.l) * t10 + lw.l * t11);
+  const float g = sigmoidf_(dot + tt);
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float v = (1.f - g) * xv.v[e] + g * yv.v[e];
+    o.v[e] = relu ? fmaxf(v, 0.f) : v;
+  }
+  if (valid) st8(out.ptr + pix * out.ps + cg * 8, o);
+}
+
+// --------------------------------------------------------------------------- upadd / affine
+__global__ void __launch_bounds__(256) upadd_kernel(View a, View b, View out, const float* __restrict__ s,
+                                                    const float* __restrict__ t, int relu) {
+  const int groups = out.C >> 3;
+  const long total = static_cast<long>(out.N) * out.H * out.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long pix = idx / groups;
+  const int w = static_cast<int>(pix % out.W);
+  const long t1 = pix / out.W;
+  const int h = static_cast<int>(t1 % out.H);
+  const int n = static_cast<int>(t1 / out.H);
+  F8 v;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v.v[e] = 0.f;
+  if (a.ptr) v = ld8(a.ptr + pix * a.ps + cg * 8);
+  if (b.ptr) {
+    const Lerp lh = lerp_of(h, b.H, out.H), lw = lerp_of(w, b.W, out.W);
+    const F8 u = sample8(b, n, lh, lw, cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v.v[e] += u.v[e];
+  }
+  if (s) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v.v[e] = v.v[e] * __ldg(s + cg * 8 + e) + __ldg(t + cg * 8 + e);
+  }
+  if (relu) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v.v[e] = fmaxf(v.v[e], 0.f);
+  }
+  st8(out.ptr + pix * out.ps + cg * 8, v);
+}
+
+// --------------------------------------------------------------------------- avg pool + affine
+// one block per output pixel; thread = (channel group, window split); smem reduce over the splits
+__global__ void __launch_bounds__(256) pool_affine_kernel(View x, View out, int k, int stride, int pad,
+                                                          const float* __restrict__ s, const float* __restrict__ t,
+                                                          int relu) {
+  extern __shared__ float red[];  // [splits][groups*8]
+  const int groups = x.C >> 3;
+  const int splits = blockDim.x / groups;
+  const int cg = threadIdx.x % groups;
+  const int sp = threadIdx.x / groups;
+  const int opix = blockIdx.x;
+  const int ow = opix % out.W;
+  const int oh = (opix / out.W) % out.H;
+  const int n = opix / (out.W * out.H);
+  int h0, h1, w0, w1;
+  float div;
+  if (k == 0) {
+    h0 = 0; h1 = x.H; w0 = 0; w1 = x.W;
+    div = static_cast<float>(x.H * x.W);
+  } else {
+    h0 = oh * stride - pad; w0 = ow * stride - pad;
+    h1 = min(h0 + k, x.H); w1 = min(w0 + k, x.W);
+    h0 = max(h0, 0); w0 = max(w0, 0);
+    div = static_cast<float>(k * k);  // count_include_pad=True: windows never leave the padded image here
+  }
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (sp < splits) {
+    const int ww = w1 - w0;
+    const int cnt = (h1 - h0) * ww;
+    const bf16* base = x.ptr + static_cast<long>(n) * x.H * x.W * x.ps + cg * 8;
+    for (int i = sp; i < cnt; i += splits) {
+      const int ih = h0 + i / ww, iw = w0 + i % ww;
+      const F8 v = ld8(base + (static_cast<long>(ih) * x.W + iw) * x.ps);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v.v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[(sp * groups + cg) * 8 + e] = acc[e];
+  }
+  __syncthreads();
+  if (sp == 0) {
+    F8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = 0.f;
+      for (int q = 0; q < splits; ++q) v += red[(q * groups + cg) * 8 + e];
+      v = v / div;
+      if (s) v = v * __ldg(s + cg * 8 + e) + __ldg(t + cg * 8 + e);
+      o.v[e] = relu ? fmaxf(v, 0.f) : v;
+    }
+    st8(out.ptr + static_cast<long>(opix) * out.ps + cg * 8, o);
+  }
+}
+
+// --------------------------------------------------------------------------- Light_Bag / Bag
+__global__ void __launch_bounds__(256) lightbag_uv_kernel(View p, View il, View d, View out) {
+  const int groups = p.C >> 3;
+  const long total = static_cast<long>(p.N) * p.H * p.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long pix = idx / groups;
+  const int w = static_cast<int>(pix % p.W);
+  const long t1 = pix / p.W;
+  const int h = static_cast<int>(t1 % p.H);
+  const int n = static_cast<int>(t1 / p.H);
+  const Lerp lh = lerp_of(h, il.H, p.H), lw = lerp_of(w, il.W, p.W);
+  const F8 iv = sample8(il, n, lh, lw, cg * 8);
+  const F8 pv = ld8(p.ptr + pix * p.ps + cg * 8);
+  const F8 dv = ld8(d.ptr + pix * d.ps + cg * 8);
+  F8 u, v;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float g = sigmoidf_(dv.v[e]);
+    u.v[e] = (1.f - g) * iv.v[e] + pv.v[e];
+    v.v[e] = iv.v[e] + g * pv.v[e];
+  }
+  st8(out.ptr + pix * out.ps + cg * 8, u);
+  st8(out.ptr + pix * out.ps + p.C + cg * 8, v);
+}
+
+__global__ void __launch_bounds__(256) bag_blend_kernel(View p, View il, View d, View out, const float* __restrict__ s,
+                                                        const float* __restrict__ t) {
+  const int groups = p.C >> 3;
+  const long total = static_cast<long>(p.N) * p.H * p.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long pix = idx / groups;
+  const int w = static_cast<int>(pix % p.W);
+  const long t1 = pix / p.W;
+  const int h = static_cast<int>(t1 % p.H);
+  const int n = static_cast<int>(t1 / p.H);
+  const Lerp lh = lerp_of(h, il.H, p.H), lw = lerp_of(w, il.W, p.W);
+  const F8 iv = sample8(il, n, lh, lw, cg * 8);
+  const F8 pv = ld8(p.ptr + pix * p.ps + cg * 8);
+  const F8 dv = ld8(d.ptr + pix * d.ps + cg * 8);
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float g = sigmoidf_(dv.v[e]);
+    const float a = g * pv.v[e] + (1.f - g) * iv.v[e];
+    o.v[e] = fmaxf(a * __ldg(s + cg * 8 + e) + __ldg(t + cg * 8 + e), 0.f);
+  }
+  st8(out.ptr + pix * out.ps + cg * 8, o);
+}
+
+// --------------------------------------------------------------------------- SIMT reference conv
+__global__ void __launch_bounds__(128) conv_ref_kernel(const ConvRefParams p) {
+  const long total = static_cast<long>(p.N) * p.Ho * p.Wo * p.Cout;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co = static_cast<int>(idx % p.Cout);
+  long pix = idx / p.Cout;
+  const int ow = static_cast<int>(pix % p.Wo);
+  pix /= p.Wo;
+  const int oh = static_cast<int>(pix % p.Ho);
+  const int n = static_cast<int>(pix / p.Ho);
+  float acc = 0.f;
+  const bf16* wrow = p.wpk + static_cast<long>(co) * p.Ktot;
+  long kbase = 0;
+  for (int s = 0; s < p.nsrc; ++s) {
+    const ConvSrc& src = p.src[s];
+    for (int t = 0; t < src.ntaps; ++t) {
+      const uint32_t tap = src.taps[t];
+      const RefMap& m = p.maps[tap & 0xFF];
+      const int ih = oh + static_cast<int>((tap >> 8) & 0xFF) - 8;
+      const int iw = ow + static_cast<int>((tap >> 16) & 0xFF) - 8;
+      const bool in = ih >= 0 && ih < m.H && iw >= 0 && iw < m.W;
+      if (in) {
+        const bf16* a = m.ptr + n * m.sN + ih * m.sH + iw * m.sW;
+        for (int c = 0; c < m.C; ++c) acc += __bfloat162float(a[c]) * __bfloat162float(wrow[kbase + c]);
+      }
+      kbase += static_cast<long>(src.chunks) * p.BK;
+    }
+  }
+  acc += p.bias[co];
+  if (p.res.ptr) acc += __bfloat162float(p.res.ptr[n * p.res.sN + oh * p.res.sH + ow * p.res.sW + co]);
+  if (p.relu) acc = fmaxf(acc, 0.f);
+  if (p.out_mode == kOutNHWCbf16)
+    p.out[n * p.o_sN + oh * p.o_sH + ow * p.o_sW + co] = __float2bfloat16_rn(acc);
+  else
+    p.out_f32[((static_cast<long>(n) * p.Cout + co) * p.Ho + oh) * p.Wo + ow] = acc;
+}
+
+inline unsigned blocks_for(long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+}  // namespace
+
+cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, const float* w, const float* bias,
+                             cudaStream_t st) {
+  const long total = static_cast<long>(N) * out.H * out.W * (out.C / 8);
+  const size_t smem = static_cast<size_t>(28 * out.C) * sizeof(float);
+  stem_conv_kernel<<<blocks_for(total, 256), 256, smem, st>>>(x, N, H, W, out, w, bias);
+  return cudaGetLastError();
+}
+
+cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t st) {
+  const int LP = x.C / 8;
+  const long total = static_cast<long>(x.N) * x.H * x.W * LP;
+  const unsigned nb = blocks_for(total, 256);
+  switch (LP) {
+    case 1: pag_fuse_kernel<1><<<nb, 256, 0, st>>>(x, low, out, relu); break;
+    case 2: pag_fuse_kernel<2><<<nb, 256, 0, st>>>(x, low, out, relu); break;
+    case 4: pag_fuse_kernel<4><<<nb, 256, 0, st>>>(x, low, out, relu); break;
+    case 8: pag_fuse_kernel<8><<<nb, 256, 0, st>>>(x, low, out, relu); break;
+    case 16: pag_fuse_kernel<16><<<nb, 256, 0, st>>>(x, low, out, relu); break;
+    case 32: pag_fuse_kernel<32><<<nb, 256, 0, st>>>(x, low, out, relu); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t upadd_launch(View a, View b, View out, const float* s, const float* t, int relu, cudaStream_t st) {
+  const long total = static_cast<long>(out.N) * out.H * out.W * (out.C / 8);
+  upadd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, b, out, s, t, relu);
+  return cudaGetLastError();
+}
+
+cudaError_t pool_affine_launch(View x, View out, int k, int stride, int pad, const float* s, const float* t, int relu,
+                               cudaStream_t st) {
+  const int groups = x.C / 8;
+  if (groups > 256 || groups < 1) return cudaErrorInvalidValue;
+  const int splits = 256 / groups;
+  const int threads = splits * groups;
+  const size_t smem = static_cast<size_t>(threads) * 8 * sizeof(float);
+  pool_affine_kernel<<<out.N * out.H * out.W, threads, smem, st>>>(x, out, k, stride, pad, s, t, relu);
+  return cudaGetLastError();
+}
+
+cudaError_t lightbag_uv_launch(View p, View i_low, View d, View out, cudaStream_t st) {
+  const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
+  lightbag_uv_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out);
+  return cudaGetLastError();
+}
+
+cudaError_t bag_blend_launch(View p, View i_low, View d, View out, const float* s, const float* t, cudaStream_t st) {
+  const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
+  bag_blend_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out, s, t);
+  return cudaGetLastError();
+}
+
+cudaError_t conv_ref_launch(const ConvRefParams& p, cudaStream_t st) {
+  const long total = static_cast<long>(p.N) * p.Ho * p.Wo * p.Cout;
+  conv_ref_kernel<<<blocks_for(total, 128), 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace pidnet

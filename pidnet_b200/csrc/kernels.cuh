@@ -1,0 +1,66 @@
+// HBM-bound fused kernels of the PIDNet path + the SIMT reference conv (debug / cross-check path).
+// All activations are NHWC bf16 with an explicit pixel stride so that channel slices of a wider
+// (concat) buffer can be read/written in place; math is fp32, one rounding per stored value.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "conv_tc.cuh"
+
+namespace pidnet {
+
+typedef __nv_bfloat16 bf16;
+
+// A strided NHWC view (ptr already includes the channel offset).
+struct View {
+  bf16* ptr;
+  int N, H, W, C;
+  long ps;  // pixel stride in elements (>= C)
+};
+
+// ---- stem: fp32 NCHW image -> 3x3 s2 p1 conv (+bias, BN folded) + ReLU -> bf16 NHWC   (pidnet.py:25-27)
+// w: [27][Cout] fp32 with k = (ci*3 + r)*3 + s ; bias: [Cout]
+cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, const float* w, const float* bias,
+                             cudaStream_t st);
+
+// ---- PagFM fuse (model_utils.py:292-312 after the low-res algebra of DESIGN.md):
+//   low = [y | z | t | pad] at (h,w);  s = <x, U(z)> + U(t);  g = sigmoid(s);  out = relu((1-g) x + g U(y))
+cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t st);
+
+// ---- generic elementwise: out = act(s * (a + U(b)) + t)   (a, b, s/t optional; U = bilinear, align_corners=False)
+cudaError_t upadd_launch(View a, View b, View out, const float* s, const float* t, int relu, cudaStream_t st);
+
+// ---- average pool (count_include_pad) + affine + ReLU; k == 0 means global average pool
+cudaError_t pool_affine_launch(View x, View out, int k, int stride, int pad, const float* s, const float* t, int relu,
+                               cudaStream_t st);
+
+// ---- Light_Bag operand producer (model_utils.py:328-334): e = sigmoid(d);
+//   out[..., 0:C] = (1-e) U(i) + p ;  out[..., C:2C] = U(i) + e p
+cudaError_t lightbag_uv_launch(View p, View i_low, View d, View out, cudaStream_t st);
+
+// ---- Bag blend (model_utils.py:375-377) + the pre-activation BN/ReLU of dfm.conv:
+//   out = relu(s * (e p + (1-e) U(i)) + t)
+cudaError_t bag_blend_launch(View p, View i_low, View d, View out, const float* s, const float* t, cudaStream_t st);
+
+// ---- SIMT restatement of conv_tc's contract on raw pointers (same packed weights / tap tables).
+struct RefMap {
+  const bf16* ptr;
+  int C, W, H, N;
+  long sW, sH, sN;  // strides in elements
+};
+struct ConvRefParams {
+  RefMap maps[kConvMaxMaps];
+  ConvSrc src[2];
+  int nsrc, BK;
+  const bf16* wpk;  // [Cout_pad][Ktot]
+  long Ktot;
+  const float* bias;
+  RefMap res;       // residual view (ptr == nullptr -> none)
+  bf16* out;        // NHWC view
+  long o_sW, o_sH, o_sN;
+  float* out_f32;   // NCHW
+  int N, Ho, Wo, Cout, relu, out_mode;
+};
+cudaError_t conv_ref_launch(const ConvRefParams& p, cudaStream_t st);
+
+}  // namespace pidnet
