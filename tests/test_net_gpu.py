@@ -1,11 +1,14 @@
 """Whole-network parity: the engine (through PIDNet.forward -> C ABI) vs the CPU oracle on the same
 seeded weights and inputs.
 
-Tolerances (bf16 engine, fp32 oracle): north star asks rel. error <= 2e-2 and argmax agreement
->= 99.9 % on trained-like weights (tests/test_trained_parity_gpu.py).  On RANDOM-INIT weights bf16
-rounding alone gives ~1.5-2.5e-2 rel-L2 for ANY implementation (torch's own
-all-bf16 forward measures 1.9-2.2e-2), so here the bound is 4e-2 on the logits, 3e-2 on every named
-intermediate, and the tcgen05 and SIMT conv paths must agree with each other to 1e-2.
+Tolerances (bf16 engine, fp32 oracle): the north star asks rel. error <= 2e-2 and argmax agreement
+>= 99.9 % on the logits -- asserted on trained-like weights in tests/test_trained_parity_gpu.py.
+These tests use seeded synthetic weights (oracle.make_state_dict) and add a sharper LOCAL check:
+every oracle stage is recomputed in fp32 from the engine's own stage inputs and must match the
+engine's stage output to LOCAL_TOL = 1e-2 rel-L2 (half the north-star bf16 bound; one bf16 rounding
+per stored tensor measures 2-6e-3).  End to end (error accumulated over ~60 bf16-stored tensors) the
+logits must stay within E2E_TOL = 5e-2 on these untrained weights (torch's own all-bf16 forward measures
+~2e-2 on S; the deeper L accumulates ~3e-2).
 """
 import pytest
 import torch
@@ -15,8 +18,8 @@ from pidnet_b200 import PIDNet
 
 pytestmark = pytest.mark.gpu
 
-NAMED = ['conv1', 'layer1', 'layer2', 'layer3_', 'layer3_d', 'layer3', 'pag3', 'xd3', 'layer4', 'layer4_',
-         'layer4_d', 'pag4', 'xd4', 'layer5_', 'layer5_d', 'layer5', 'spp', 'dfm']
+LOCAL_TOL = 1e-2
+E2E_TOL = 5e-2
 
 
 def _dev():
@@ -38,16 +41,24 @@ def build(name, ncls, augment, seed, dev, **opts):
     return model, sd
 
 
-def report(model, taps):
+def stage_report(model, sd, x, got):
+    """For every oracle stage: (name, local rel-L2, end-to-end rel-L2).
+
+    local = engine stage output vs the ORACLE stage recomputed in fp32 from the ENGINE's own stage
+    inputs (isolates each fused kernel group); end-to-end = vs the oracle run from the image."""
+    taps = {}
+    with torch.no_grad():
+        O.pidnet_forward(sd, x, taps=taps)
+    outs = {'out': got[1] if isinstance(got, (list, tuple)) else got}
+    if isinstance(got, (list, tuple)):
+        outs['out_p'], outs['out_d'] = got[0], got[2]
+    eng = {'x': x}
     rows = []
-    for nm in NAMED:
-        if nm not in taps:
-            continue
-        got = model.debug_tensor(nm)
-        ref = taps[nm]
-        if nm == 'dfm':      # engine stores relu(final_layer.bn1(dfm)) -- compare through the same map
-            continue
-        rows.append((nm, O.rel_l2(got, ref)))
+    for nm in O.stage_names(sd):
+        eng[nm] = outs[nm].detach().float().cpu() if nm in outs else model.debug_tensor(nm)
+        with torch.no_grad():
+            loc = O.run_stage(sd, nm, [eng[i] for i in O.stage_inputs(sd, nm)], x.shape[-2:])
+        rows.append((nm, O.rel_l2(eng[nm], loc), O.rel_l2(eng[nm], taps[nm])))
     return rows
 
 
@@ -69,23 +80,16 @@ def test_forward_matches_oracle(case, impl):
     name, ncls, aug, N, H, W = case
     model, sd = build(name, ncls, aug, seed=11, dev=dev, conv_impl=impl)
     x = torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(5))
-    taps = {}
     with torch.no_grad():
-        ref = O.pidnet_forward(sd, x, taps=taps)
         got = model(x.to(dev))
     torch.cuda.synchronize()
-    rows = report(model, taps)
-    msg = ' '.join(f'{n}={e:.3g}' for n, e in rows)
-    print(f'[{name} impl={impl}] intermediates rel-L2: {msg}')
-    for n, e in rows:
-        assert e < 3e-2, f'{n}: rel-L2 {e:.4g} ({msg})'
-    refs = ref if aug else [ref]
-    gots = got if aug else [got]
-    for i, (g, r) in enumerate(zip(gots, refs)):
-        assert g.shape == r.shape
-        e = O.rel_l2(g.cpu(), r)
-        print(f'  output {i}: rel-L2 {e:.4g} argmax agreement {O.argmax_agreement(g.cpu(), r):.5f}')
-        assert e < 4e-2, f'output {i}: rel-L2 {e:.4g}'
+    rows = stage_report(model, sd, x, got)
+    msg = ' '.join(f'{n}={l:.3g}/{e:.3g}' for n, l, e in rows)
+    print(f'[{name} {H}x{W} impl={impl}] stage local/end-to-end rel-L2: {msg}')
+    for n, l, e in rows:
+        assert l < LOCAL_TOL, f'{n}: local rel-L2 {l:.4g} ({msg})'
+        if n.startswith('out'):   # the three network outputs
+            assert e < E2E_TOL, f'{n}: end-to-end rel-L2 {e:.4g} ({msg})'
 
 
 def test_impls_agree_and_graph_replay():
@@ -130,4 +134,4 @@ def test_state_dict_update_is_picked_up():
         b = model(x).clone()
         ref = O.pidnet_forward(sd2, x.cpu())
     assert not torch.equal(a, b)
-    assert O.rel_l2(b.cpu(), ref) < 4e-2
+    assert O.rel_l2(b.cpu(), ref) < E2E_TOL
