@@ -73,6 +73,15 @@ int pidnet_num_launches(pidnet_engine* h);
 /* Algorithmic conv FLOPs (2*MACs, no padding waste) of one forward at the planned shape. */
 double pidnet_conv_flops(pidnet_engine* h);
 
+/* Measurement support (bench.py roofline): runs the planned ops ONE AT A TIME on `stream` with a CUDA
+ * event pair around each launch and returns the device time of every launch in ms (cap >= number of
+ * launches).  pidnet_op_info describes launch i: its layer name, kernel family label, algorithmic
+ * FLOPs (2*MACs, no padding) and algorithmic bytes (each distinct input and the output once). */
+int pidnet_profile(pidnet_engine* h, void* stream, const float* x_nchw, float* out_main, float* out_p, float* out_d,
+                   float* ms_per_op, int cap);
+int pidnet_op_info(pidnet_engine* h, int i, char* name, int name_cap, char* kernel, int kernel_cap, double* flops,
+                   double* bytes, int* lane);
+
 /* Options (set before pidnet_plan): "conv_impl" = 0 tcgen05 (default) | 1 SIMT restatement (debug
  * cross-check); "lanes" = 1 | 3 concurrent branch streams (default 3). */
 int pidnet_set_option(pidnet_engine* h, const char* name, int value);

@@ -29,6 +29,9 @@ SIGNATURES = {
     'pidnet_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
     'pidnet_num_launches': (_i, [_vp]),
     'pidnet_conv_flops': (C.c_double, [_vp]),
+    'pidnet_profile': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    'pidnet_op_info': (_i, [_vp, _i, C.c_char_p, _i, C.c_char_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                            C.POINTER(_i)]),
     'pidnet_set_option': (_i, [_vp, C.c_char_p, _i]),
     'pidnet_debug_tensor': (_i, [_vp, C.c_char_p, _vp, _i64p]),
     'pidnet_op_conv2d': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i]),

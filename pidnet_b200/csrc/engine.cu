@@ -121,6 +121,9 @@ struct RunArgs {
 
 struct Op {
   std::string name;
+  std::string kernel;   // kernel family label (profiling / roofline)
+  double flops = 0;     // algorithmic FLOPs (2*MACs, no padding waste)
+  double bytes = 0;     // algorithmic bytes: every distinct input and the output once
   int lane = 0;
   std::vector<int> deps;  // producer ops on other lanes
   bool record = false;
@@ -416,8 +419,27 @@ struct Builder {
       if (out_slot >= 0) R.out_f32 = a.out[out_slot];
       return conv_ref_launch(R, st);
     });
+    {
+      Op& op = ops[idx];
+      char lab[64];
+      if (impl == 0) std::snprintf(lab, sizeof(lab), "conv_tc<BN=%d,BK=%d>", BN, BK);
+      else std::snprintf(lab, sizeof(lab), "conv_ref");
+      op.kernel = lab;
+      for (const auto& s : srcs) {
+        op.flops += 2.0 * N * Ho * Wo * Cout * s.in.C * s.k * s.k;
+        op.bytes += 2.0 * s.in.N * s.in.H * s.in.W * s.in.C + 2.0 * Cout * s.in.C * s.k * s.k;
+      }
+      if (res) op.bytes += 2.0 * N * Ho * Wo * Cout;
+      op.bytes += (out_slot >= 0 ? 4.0 : 2.0) * N * Ho * Wo * Cout;
+    }
     out.prod = idx;
     return out;
+  }
+  static double tbytes(const T& t) { return 2.0 * t.N * t.H * t.W * t.C; }
+  void label(int idx, const char* kernel, double bytes, double flops = 0) {
+    ops[idx].kernel = kernel;
+    ops[idx].bytes = bytes;
+    ops[idx].flops = flops;
   }
 };
 
@@ -431,16 +453,22 @@ struct Engine {
   int lanes = 3;
   int conv_impl = 0;
   cudaStream_t side[2] = {nullptr, nullptr};
+  cudaStream_t cap_stream = nullptr;  // capture origin (the caller's stream may be the legacy default stream)
   std::vector<cudaEvent_t> events;  // one per op that records
   std::vector<int> ev_of_op;
   cudaEvent_t ev_start = nullptr, ev_join[2] = {nullptr, nullptr};
-  // graph cache
-  cudaGraphExec_t gexec = nullptr;
-  RunArgs gargs{};
+  // CUDA-graph cache keyed by the runtime pointers (a few entries: double-buffered callers)
+  struct GraphEntry {
+    RunArgs args;
+    cudaGraphExec_t exec;
+  };
+  std::vector<GraphEntry> graphs;
+  static constexpr size_t kMaxGraphs = 4;
 
   ~Engine() { release(); }
   void release() {
-    if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
     for (auto e : events) cudaEventDestroy(e);
     events.clear();
     if (ev_start) { cudaEventDestroy(ev_start); ev_start = nullptr; }
@@ -448,6 +476,7 @@ struct Engine {
       if (ev_join[i]) { cudaEventDestroy(ev_join[i]); ev_join[i] = nullptr; }
       if (side[i]) { cudaStreamDestroy(side[i]); side[i] = nullptr; }
     }
+    if (cap_stream) { cudaStreamDestroy(cap_stream); cap_stream = nullptr; }
     if (b.act_base) { cudaFree(b.act_base); b.act_base = nullptr; }
     if (b.wt_base) { cudaFree(b.wt_base); b.wt_base = nullptr; }
     planned = false;
@@ -562,6 +591,7 @@ struct Engine {
     out.prod = b.add_op(name, {&x}, [xv, ov, s, t](cudaStream_t st, const RunArgs&) {
       return upadd_launch(xv, View{nullptr, 0, 0, 0, 0, 0}, ov, s, t, 1, st);
     });
+    b.label(out.prod, "upadd", Builder::tbytes(x) + Builder::tbytes(out));
     return out;
   }
   // out = act(s*(a + U(blow)) + t)
@@ -574,6 +604,7 @@ struct Engine {
     out.prod = b.add_op(name, {&a, &blow}, [av, bv, ov, s, t, r](cudaStream_t st, const RunArgs&) {
       return upadd_launch(av, bv, ov, s, t, r, st);
     });
+    b.label(out.prod, "upadd", Builder::tbytes(a) + Builder::tbytes(blow) + Builder::tbytes(out));
     return out;
   }
   // segmenthead (model_utils.py:100-112): `xin` must already hold relu(bn1(x)); writes fp32 NCHW slot
@@ -645,6 +676,7 @@ struct Engine {
     out.prod = b.add_op(pg + ".fuse", {&xhi, &low}, [xv, lv, ov](cudaStream_t st, const RunArgs&) {
       return pag_fuse_launch(xv, lv, ov, 1, st);
     });
+    b.label(out.prod, "pag_fuse", Builder::tbytes(xhi) + Builder::tbytes(low) + Builder::tbytes(out));
     return out;
   }
 
@@ -659,6 +691,7 @@ struct Engine {
     out.prod = b.add_op(name, {&x}, [xv, ov, k, stride, pad, s, t](cudaStream_t st, const RunArgs&) {
       return pool_affine_launch(xv, ov, k, stride, pad, s, t, 1, st);
     });
+    b.label(out.prod, "pool_affine", Builder::tbytes(x) + Builder::tbytes(out));
     return out;
   }
   T conv_plain(const std::string& name, const T& x, const std::string& conv, const Affine* post, int k, bool relu,
@@ -764,6 +797,7 @@ struct Engine {
       x1.prod = b.add_op("conv1.0", {}, [ov, wd, bd, n_, h_, w_](cudaStream_t st, const RunArgs& a) {
         return stem_conv_launch(a.x, n_, h_, w_, ov, wd, bd, st);
       });
+      b.label(x1.prod, "stem_conv", 4.0 * N * 3 * H * W + Builder::tbytes(x1), 2.0 * N * x1.H * x1.W * Pn * 27);
     }
     T x = conv_bn("conv1.3", x1, "conv1.3", "conv1.4", 3, 2, true);
     b.named["conv1"] = x;
@@ -842,6 +876,7 @@ struct Engine {
       uv.prod = b.add_op("dfm.uv", {&xp, &sp, &xd}, [pv, iv, dv, ov](cudaStream_t st, const RunArgs&) {
         return lightbag_uv_launch(pv, iv, dv, ov, st);
       });
+      b.label(uv.prod, "lightbag_uv", Builder::tbytes(xp) + Builder::tbytes(sp) + Builder::tbytes(xd) + Builder::tbytes(uv));
       const Affine ap = bn("dfm.conv_p.1"), ai = bn("dfm.conv_i.1");
       const auto &Wp = P("dfm.conv_p.0.weight").data, &Wi = P("dfm.conv_i.0.weight").data;
       ConvSrcSpec s;
@@ -865,6 +900,7 @@ struct Engine {
       a.prod = b.add_op("dfm.blend", {&xp, &sp, &xd}, [pv, iv, dv, ov, s_, t_](cudaStream_t st, const RunArgs&) {
         return bag_blend_launch(pv, iv, dv, ov, s_, t_, st);
       });
+      b.label(a.prod, "bag_blend", Builder::tbytes(xp) + Builder::tbytes(sp) + Builder::tbytes(xd) + Builder::tbytes(a));
       f = conv_plain("dfm.conv", a, "dfm.conv.2", &a1, 3, true, nullptr);
     }
     b.named["dfm"] = f;
@@ -898,6 +934,7 @@ struct Engine {
     b.wt_host.shrink_to_fit();
     // streams / events
     for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
     ev_of_op.assign(b.ops.size(), -1);
@@ -932,6 +969,24 @@ struct Engine {
       }
   }
 
+  // one launch at a time on `stream`, CUDA events around each: per-op device time in ms
+  void profile(cudaStream_t stream, const RunArgs& a, float* ms, int cap) {
+    if (!planned) fail("pidnet_profile called before pidnet_plan");
+    const int n = static_cast<int>(b.ops.size());
+    if (cap < n) fail("profile buffer too small");
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(ev[0], stream));
+    for (int i = 0; i < n; ++i) {
+      cudaError_t e = b.ops[i].fn(stream, a);
+      if (e != cudaSuccess) fail("launch of '" + b.ops[i].name + "' failed: " + cudaGetErrorString(e));
+      CK(cudaEventRecord(ev[i + 1], stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < n; ++i) CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+
   void forward(cudaStream_t stream, const RunArgs& a, bool use_graph) {
     if (!planned) fail("pidnet_forward called before pidnet_plan");
     if (!a.x || !a.out[0]) fail("null input/output pointer");
@@ -940,24 +995,31 @@ struct Engine {
       enqueue(stream, a);
       return;
     }
-    if (!gexec || std::memcmp(&gargs, &a, sizeof(RunArgs)) != 0) {
-      if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
-      cudaGraph_t g = nullptr;
-      CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-      try {
-        enqueue(stream, a);
-      } catch (...) {
-        cudaStreamEndCapture(stream, &g);
-        if (g) cudaGraphDestroy(g);
-        throw;
+    for (auto& g : graphs)
+      if (std::memcmp(&g.args, &a, sizeof(RunArgs)) == 0) {
+        CK(cudaGraphLaunch(g.exec, stream));
+        return;
       }
-      CK(cudaStreamEndCapture(stream, &g));
-      cudaError_t e = cudaGraphInstantiate(&gexec, g, 0);
-      cudaGraphDestroy(g);
-      if (e != cudaSuccess) { gexec = nullptr; fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-      gargs = a;
+    if (graphs.size() >= kMaxGraphs) {
+      cudaGraphExecDestroy(graphs.front().exec);
+      graphs.erase(graphs.begin());
     }
-    CK(cudaGraphLaunch(gexec, stream));
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      enqueue(cap_stream, a);
+    } catch (...) {
+      cudaStreamEndCapture(cap_stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    CK(cudaStreamEndCapture(cap_stream, &g));
+    cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    graphs.push_back(GraphEntry{a, exec});
+    CK(cudaGraphLaunch(exec, stream));
   }
 };
 
@@ -1054,6 +1116,28 @@ int pidnet_forward(pidnet_engine* h, void* stream, const float* x, float* out_ma
     if (!h) fail("null handle");
     RunArgs a{x, {out_main, out_p, out_d}};
     h->e.forward(reinterpret_cast<cudaStream_t>(stream), a, use_graph != 0);
+  });
+}
+
+int pidnet_profile(pidnet_engine* h, void* stream, const float* x, float* out_main, float* out_p, float* out_d,
+                   float* ms_per_op, int cap) {
+  return guard([&] {
+    if (!h || !ms_per_op) fail("null argument");
+    RunArgs a{x, {out_main, out_p, out_d}};
+    h->e.profile(reinterpret_cast<cudaStream_t>(stream), a, ms_per_op, cap);
+  });
+}
+
+int pidnet_op_info(pidnet_engine* h, int i, char* name, int name_cap, char* kernel, int kernel_cap, double* flops,
+                   double* bytes, int* lane) {
+  return guard([&] {
+    if (!h || i < 0 || i >= static_cast<int>(h->e.b.ops.size())) fail("bad op index");
+    const Op& op = h->e.b.ops[i];
+    if (name && name_cap > 0) std::snprintf(name, name_cap, "%s", op.name.c_str());
+    if (kernel && kernel_cap > 0) std::snprintf(kernel, kernel_cap, "%s", op.kernel.c_str());
+    if (flops) *flops = op.flops;
+    if (bytes) *bytes = op.bytes;
+    if (lane) *lane = op.lane;
   });
 }
 

@@ -261,6 +261,26 @@ class PIDNet(nn.Module):
         _lib.check(lib.pidnet_debug_tensor(self._engine, name.encode(), C.c_void_p(t.data_ptr()), shape))
         return t
 
+    def profile(self, x, out, out_p=None, out_d=None):
+        """Per-launch device times: list of dicts (name, kernel, lane, flops, bytes, ms), ops serialised."""
+        lib = self._sync(x.shape[0], x.shape[2], x.shape[3], x.device)
+        n = self.num_launches()
+        ms = (C.c_float * n)()
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(lib.pidnet_profile(
+            self._engine, C.c_void_p(stream), C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+            C.c_void_p(out_p.data_ptr()) if out_p is not None else None,
+            C.c_void_p(out_d.data_ptr()) if out_d is not None else None, ms, n))
+        rows = []
+        for i in range(n):
+            name, kern = C.create_string_buffer(128), C.create_string_buffer(64)
+            fl, by, lane = C.c_double(), C.c_double(), C.c_int()
+            _lib.check(lib.pidnet_op_info(self._engine, i, name, 128, kern, 64, C.byref(fl), C.byref(by),
+                                          C.byref(lane)))
+            rows.append(dict(name=name.value.decode(), kernel=kern.value.decode(), lane=lane.value, flops=fl.value,
+                             bytes=by.value, ms=float(ms[i])))
+        return rows
+
     def num_launches(self):
         return int(_lib.load().pidnet_num_launches(self._engine))
 
