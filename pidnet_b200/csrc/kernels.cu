@@ -63,48 +63,76 @@ __device__ __forceinline__ F8 sample8(const View& b, int n, const Lerp& lh, cons
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // --------------------------------------------------------------------------- stem
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, int N, int H, int W, View out,
+// Register-tiled direct conv: one thread = 2 horizontally adjacent output pixels x 32 output channels
+// (1728 FMAs per 45 input loads + 216 broadcast LDS.128 of the weights), fp32 math on the fp32 image.
+template <int CH>  // output channels per thread (32; 8 for tiny test configs)
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, int N, int H, int W, View out,
                                                         const float* __restrict__ w, const float* __restrict__ bias) {
-  extern __shared__ float ws[];  // [27][Cout] + [Cout]
+  __shared__ __align__(16) float ws[27 * CH + CH];
   const int Cout = out.C;
-  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) ws[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) ws[27 * Cout + i] = bias[i];
+  const int c0 = blockIdx.y * CH;  // this block's channel slice
+  for (int i = threadIdx.x; i < 27 * CH; i += blockDim.x) ws[i] = w[(i / CH) * Cout + c0 + (i % CH)];
+  if (threadIdx.x < CH) ws[27 * CH + threadIdx.x] = bias[c0 + threadIdx.x];
   __syncthreads();
-  const int groups = Cout >> 3;
-  const long total = static_cast<long>(N) * out.H * out.W * groups;
+  const int Wp = (out.W + 1) >> 1;  // pixel pairs per output row
+  const long total = static_cast<long>(N) * out.H * Wp;
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int cg = static_cast<int>(idx % groups);
-  long pix = idx / groups;
-  const int ow = static_cast<int>(pix % out.W);
-  pix /= out.W;
-  const int oh = static_cast<int>(pix % out.H);
-  const int n = static_cast<int>(pix / out.H);
-  float acc[8];
+  const int pw = static_cast<int>(idx % Wp);
+  const long t1 = idx / Wp;
+  const int oh = static_cast<int>(t1 % out.H);
+  const int n = static_cast<int>(t1 / out.H);
+  const int ow = pw * 2;
+  float acc0[CH], acc1[CH];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = ws[27 * Cout + cg * 8 + e];
+  for (int e = 0; e < CH; ++e) acc0[e] = acc1[e] = ws[27 * CH + e];
   const float* xn = x + static_cast<long>(n) * 3 * H * W;
+  const int iw0 = ow * 2 - 1;
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int ih = oh * 2 - 1 + r;
+      float v[5];
+      const bool rowok = ih >= 0 && ih < H;
+      const float* row = xn + (static_cast<long>(ci) * H + (rowok ? ih : 0)) * W;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int iw = ow * 2 - 1 + s;
-        float v = 0.f;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(xn + (static_cast<long>(ci) * H + ih) * W + iw);
-        const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * 3 + r) * 3 + s) * Cout + cg * 8);
-        const float4 wa = wp[0], wb = wp[1];
-        acc[0] += v * wa.x; acc[1] += v * wa.y; acc[2] += v * wa.z; acc[3] += v * wa.w;
-        acc[4] += v * wb.x; acc[5] += v * wb.y; acc[6] += v * wb.z; acc[7] += v * wb.w;
+      for (int j = 0; j < 5; ++j) {
+        const int iw = iw0 + j;
+        v[j] = (rowok && iw >= 0 && iw < W) ? __ldg(row + iw) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * 3 + r) * 3 + q) * CH);
+        const float a0 = v[q], a1 = v[q + 2];
+#pragma unroll
+        for (int e4 = 0; e4 < CH / 4; ++e4) {
+          const float4 wv = wp[e4];
+          acc0[e4 * 4 + 0] += a0 * wv.x; acc0[e4 * 4 + 1] += a0 * wv.y;
+          acc0[e4 * 4 + 2] += a0 * wv.z; acc0[e4 * 4 + 3] += a0 * wv.w;
+          acc1[e4 * 4 + 0] += a1 * wv.x; acc1[e4 * 4 + 1] += a1 * wv.y;
+          acc1[e4 * 4 + 2] += a1 * wv.z; acc1[e4 * 4 + 3] += a1 * wv.w;
+        }
       }
     }
   }
-  F8 o;
+  bf16* o0 = out.ptr + ((static_cast<long>(n) * out.H + oh) * out.W + ow) * out.ps + c0;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) o.v[e] = fmaxf(acc[e], 0.f);
-  st8(out.ptr + ((static_cast<long>(n) * out.H + oh) * out.W + ow) * out.ps + cg * 8, o);
+  for (int g = 0; g < CH / 8; ++g) {
+    F8 f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f.v[e] = fmaxf(acc0[g * 8 + e], 0.f);
+    st8(o0 + g * 8, f);
+  }
+  if (ow + 1 < out.W) {
+#pragma unroll
+    for (int g = 0; g < CH / 8; ++g) {
+      F8 f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f.v[e] = fmaxf(acc1[g * 8 + e], 0.f);
+      st8(o0 + out.ps + g * 8, f);
+    }
+  }
 }
 
 // --------------------------------------------------------------------------- PagFM fuse
@@ -334,9 +362,15 @@ inline unsigned blocks_for(long total, int threads) { return static_cast<unsigne
 
 cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, const float* w, const float* bias,
                              cudaStream_t st) {
-  const long total = static_cast<long>(N) * out.H * out.W * (out.C / 8);
-  const size_t smem = static_cast<size_t>(28 * out.C) * sizeof(float);
-  stem_conv_kernel<<<blocks_for(total, 256), 256, smem, st>>>(x, N, H, W, out, w, bias);
+  if (out.C % 8 != 0) return cudaErrorInvalidValue;
+  const long total = static_cast<long>(N) * out.H * ((out.W + 1) / 2);
+  if (out.C % 32 == 0) {
+    dim3 grid(blocks_for(total, 128), out.C / 32, 1);
+    stem_conv_kernel<32><<<grid, 128, 0, st>>>(x, N, H, W, out, w, bias);
+  } else {
+    dim3 grid(blocks_for(total, 128), out.C / 8, 1);
+    stem_conv_kernel<8><<<grid, 128, 0, st>>>(x, N, H, W, out, w, bias);
+  }
   return cudaGetLastError();
 }
 

@@ -27,6 +27,9 @@ class _Node(nn.Module):
     def forward(self, *a, **k):  # pragma: no cover
         raise RuntimeError('pidnet_b200 container modules hold parameters only')
 
+    def __getitem__(self, idx):  # numeric children, like nn.Sequential
+        return self._modules[str(idx)]
+
 
 def _conv(cin, cout, k, bias=False, groups=1):
     return nn.Conv2d(cin, cout, k, bias=bias, groups=groups)

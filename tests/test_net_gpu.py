@@ -100,7 +100,8 @@ def test_impls_agree_and_graph_replay():
     with torch.no_grad():
         a, b = m0(x), m1(x)
         for u, v in zip(a, b):
-            assert O.rel_l2(u.cpu(), v.cpu()) < 1e-2
+            # same arithmetic, different fp32 accumulation order -> 1-ulp bf16 flips that propagate
+            assert O.rel_l2(u.cpu(), v.cpu()) < E2E_TOL
         # CUDA-graph replay and single-lane execution give bit-identical results to the eager 3-lane run
         m0.use_graph = True
         c = m0(x)
