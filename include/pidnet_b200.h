@@ -83,7 +83,8 @@ int pidnet_op_info(pidnet_engine* h, int i, char* name, int name_cap, char* kern
                    double* bytes, int* lane);
 
 /* Options (set before pidnet_plan): "conv_impl" = 0 tcgen05 (default) | 1 SIMT restatement (debug
- * cross-check); "lanes" = 1 | 3 concurrent branch streams (default 3). */
+ * cross-check); "lanes" = 1 | 3 concurrent branch streams (default 3); "use_ws" = 1 (default) | 0: use
+ * the weight-stationary halo-patch kernel for 3x3 stride-1 convs. */
 int pidnet_set_option(pidnet_engine* h, const char* name, int value);
 
 /* Debug: copy a named intermediate (e.g. "layer3", "pag3", "spp"; see engine.cu) to the host as fp32
@@ -95,7 +96,8 @@ int pidnet_debug_tensor(pidnet_engine* h, const char* name, float* host_out, int
 /* nn.Conv2d (+folded affine, +residual, +ReLU) on one NHWC bf16 tensor.  w: host fp32 [Cout][Cin/groups][k][k]
  * (already BN-folded), bias: host fp32 [Cout] or NULL, res: device NHWC bf16 [N,Ho,Wo,Cout] or NULL.
  * out_nhwc (bf16) or out_nchw_f32 (exactly one non-NULL).  k in {1,3}, pad = k/2, stride in {1,2}.
- * impl: 0 tcgen05, 1 SIMT. */
+ * impl: 0 tcgen05 (weight-stationary halo kernel where it applies, else the generic one), 1 SIMT restatement,
+ * 2 generic tcgen05 kernel only. */
 int pidnet_op_conv2d(void* stream, const void* x_nhwc, int N, int H, int W, int Cin, const float* w, const float* bias,
                      int Cout, int k, int stride, int groups, const void* res, int relu, void* out_nhwc,
                      float* out_nchw_f32, int impl);
@@ -117,6 +119,11 @@ int pidnet_op_lightbag(void* stream, const void* p, const void* i_low, const voi
 /* Bag blend + BN + ReLU: out [N,H,W,C]. */
 int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d, void* out, int N, int H, int W, int C,
                   int h, int w, const float* s, const float* t);
+
+/* Hardware probe used by tools/probe_halo.py (documents how tcgen05 reads shifted windows of a
+ * TMA-written halo patch; not on the product path). */
+int pidnet_probe_halo(void* stream, const void* x_18x10x64_bf16, const void* w_64x64_bf16, int r, int s, int mode,
+                      float* out_128x64);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,347 @@
+// conv3x3 (stride 1, pad 1) on tcgen05 -- weight-stationary, halo-patch, persistent.
+//
+// The generic kernel (conv_tc.cu) re-fetches the input once per filter tap (9x) and the whole weight
+// matrix once per 128-pixel tile; measured on B200 that makes every PIDNet 3x3 layer L2->SM-bandwidth
+// bound (~9-10 TB/s) with the tensor pipe idle.  This kernel removes both re-reads:
+//   * weights: each persistent CTA owns ONE Cout tile and keeps all 9 x Cin x BN weights resident in
+//     shared memory (loaded once by TMA);
+//   * activations: a 16x8-pixel output tile needs an 18x10-pixel halo patch; ONE TMA box load per
+//     64/32-channel chunk brings it in (zero-filled outside the image == the conv padding), and the
+//     nine taps are nine tcgen05 smem descriptors whose start address is shifted by whole pixel rows
+//     inside the patch (row stride 10 px -> SBO = 10 * row bytes).  The hardware swizzle is a function
+//     of absolute smem address bits, so TMA's SWIZZLE_128B/64B write pattern and the shifted reads
+//     agree (verified by csrc/probe.cu).
+//   * accumulators are double-buffered in TMEM: the 4 epilogue warps drain tile i (bias, residual,
+//     ReLU, bf16, swizzled smem staging, TMA store) while the MMA warp already runs tile i+1.
+//   * a dedicated store warp issues the TMA stores and signals when a staging buffer has drained, so
+//     the epilogue warps never wait on a store and the residual prefetch of tile i+2 starts early.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue, 6 = TMA store.
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace pidnet {
+
+namespace {
+
+constexpr int kWsThreads = 224;
+constexpr int kTH = 16, kTW = 8, kPH = 18, kPW = 10;
+constexpr int kMaxPatch = 8;
+
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int CK>
+struct WsGeom {
+  static constexpr int kRowBytes = CK * 2;                          // one pixel of one chunk
+  static constexpr int kPatchBytes = kPH * kPW * kRowBytes;         // 23040 / 11520
+  static constexpr int kPatchStride = (kPatchBytes + 1023) / 1024 * 1024;
+};
+
+template <int BN, int CK>
+__global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_constant__ Conv3Params p) {
+  using G = WsGeom<CK>;
+  constexpr int kSlabC = BN < 64 ? BN : 64;
+  constexpr int kSlabRowBytes = kSlabC * 2;
+  constexpr int kSlabBytes = 128 * kSlabRowBytes;
+  constexpr int kNumSlabs = BN / kSlabC;
+  constexpr int kStageBytes = 128 * BN * 2;
+  constexpr int kWTileBytes = BN * CK * 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int chunks = p.chunks;
+  const int npatch = p.npatch;
+  const uint32_t w_base = smem_base;
+  const uint32_t w_bytes = 9u * chunks * kWTileBytes;
+  const uint32_t patch_base = w_base + w_bytes;
+  const uint32_t stage_base = patch_base + npatch * G::kPatchStride;
+  uint8_t* stage_gen = smem_gen + w_bytes + npatch * G::kPatchStride;
+  const uint32_t bar_base = stage_base + 2 * kStageBytes;
+  // barriers (8 B each): w_full | patch_full[8] | patch_empty[8] | tmem_full[2] | tmem_empty[2] | res_full[2] |
+  //                      stage_free[2] | stage_ready[2]
+  const uint32_t w_full = bar_base;
+  auto patch_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto patch_empty = [&](int s) { return bar_base + 8u * (1 + kMaxPatch + s); };
+  auto tmem_full = [&](int b) { return bar_base + 8u * (1 + 2 * kMaxPatch + b); };
+  auto tmem_empty = [&](int b) { return bar_base + 8u * (3 + 2 * kMaxPatch + b); };
+  auto res_full = [&](int b) { return bar_base + 8u * (5 + 2 * kMaxPatch + b); };
+  auto stage_free = [&](int b) { return bar_base + 8u * (7 + 2 * kMaxPatch + b); };
+  auto stage_ready = [&](int b) { return bar_base + 8u * (9 + 2 * kMaxPatch + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (11 + 2 * kMaxPatch);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+      stage_gen + 2 * kStageBytes + 8 * (11 + 2 * kMaxPatch));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.y;
+  const int c_out0 = n_tile * BN;
+  const int per_img = p.tiles_w * p.tiles_h;
+  const int m_tiles = p.N * per_img;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < kMaxPatch; ++s) {
+      mbar_init(patch_full(s), 1);
+      mbar_init(patch_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full(b), 1);
+      mbar_init(tmem_empty(b), 4);
+      mbar_init(res_full(b), 1);
+      mbar_init(stage_free(b), 1);
+      mbar_init(stage_ready(b), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmA);
+      tma_prefetch_desc(&p.tmW);
+      mbar_arrive_expect_tx(w_full, w_bytes);
+      for (int t = 0; t < 9 * chunks; ++t)
+        tma_load_2d(w_base + t * kWTileBytes, &p.tmW, w_full, t * CK, c_out0);
+      int item = 0, i = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
+        const int n = tile / per_img;
+        const int rem = tile - n * per_img;
+        const int th = rem / p.tiles_w;
+        const int tw = rem - th * p.tiles_w;
+        const int w0 = tw * kTW, h0 = th * kTH;
+        for (int c = 0; c < chunks; ++c, ++item) {
+          const int slot = item % npatch;
+          const uint32_t ph = (item / npatch) & 1;
+          mbar_wait(patch_empty(slot), ph ^ 1);
+          mbar_arrive_expect_tx(patch_full(slot), G::kPatchBytes);
+          tma_load_4d(patch_base + slot * G::kPatchStride, &p.tmA, patch_full(slot), c * CK, w0 - 1, h0 - 1, n);
+        }
+        if (p.has_res) {
+          const int b = i & 1;
+          const uint32_t u = static_cast<uint32_t>(i >> 1);
+          mbar_wait(stage_free(b), (u & 1) ^ 1);
+          mbar_arrive_expect_tx(res_full(b), kStageBytes);
+          for (int sl = 0; sl < kNumSlabs; ++sl)
+            tma_load_4d(stage_base + b * kStageBytes + sl * kSlabBytes, &p.tmR, res_full(b), c_out0 + sl * kSlabC, w0,
+                        h0, n);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      constexpr uint64_t kLayout = (CK == 64) ? 2ull : 4ull;  // SWIZZLE_128B / SWIZZLE_64B
+      // A: 8-pixel tile rows are 10 patch pixels apart
+      const uint64_t a_hi = (static_cast<uint64_t>((kPW * G::kRowBytes) >> 4) << 32) | (1ull << 46) | (kLayout << 61) |
+                            (1ull << 16);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      int item = 0, i = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
+        const int ab = i & 1;
+        const uint32_t u = static_cast<uint32_t>(i >> 1);
+        mbar_wait(tmem_empty(ab), (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_acc + ab * BN;
+        for (int c = 0; c < chunks; ++c, ++item) {
+          const int slot = item % npatch;
+          const uint32_t ph = (item / npatch) & 1;
+          mbar_wait(patch_full(slot), ph);
+          tc_fence_after();
+          const uint32_t pbase = patch_base + slot * G::kPatchStride;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap % 3;
+            const uint32_t a_addr = pbase + (r * kPW + s) * G::kRowBytes;
+            const uint64_t a_desc = a_hi | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4);
+            const uint64_t b_desc = make_kmajor_desc(w_base + (tap * chunks + c) * kWTileBytes, G::kRowBytes);
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k)
+              umma_bf16(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(patch_empty(slot));
+        }
+        umma_commit(tmem_full(ab));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    // ============================== TMA store warp ==============================
+    if (lane == 0 && p.out_mode == kOutNHWCbf16) {
+      int i = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
+        const int n = tile / per_img;
+        const int rem = tile - n * per_img;
+        const int th = rem / p.tiles_w;
+        const int tw = rem - th * p.tiles_w;
+        const int b = i & 1;
+        const uint32_t u = static_cast<uint32_t>(i >> 1);
+        mbar_wait(stage_ready(b), u & 1);
+        for (int sl = 0; sl < kNumSlabs; ++sl)
+          if (c_out0 + sl * kSlabC < p.Cout)
+            tma_store_4d(&p.tmD, stage_base + b * kStageBytes + sl * kSlabBytes, c_out0 + sl * kSlabC, tw * kTW,
+                         th * kTH, n);
+        tma_store_commit();
+        tma_store_wait_read();       // smem of this buffer has been read out
+        mbar_arrive(stage_free(b));
+      }
+      tma_store_wait_all();
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue (warps 2..5) ==============================
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;        // tile row == TMEM lane
+    const uint32_t swz = (kSlabRowBytes == 128) ? (row & 7) : (kSlabRowBytes == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+    int i = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
+      const int n = tile / per_img;
+      const int rem = tile - n * per_img;
+      const int th = rem / p.tiles_w;
+      const int tw = rem - th * p.tiles_w;
+      const int w0 = tw * kTW, h0 = th * kTH;
+      const int b = i & 1;
+      const uint32_t u = static_cast<uint32_t>(i >> 1);
+      mbar_wait(tmem_full(b), u & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_acc + b * BN + (static_cast<uint32_t>(q * 32) << 16);
+      if (p.out_mode == kOutNHWCbf16) {
+        if (p.has_res) mbar_wait(res_full(b), u & 1);
+        else mbar_wait(stage_free(b), (u & 1) ^ 1);
+        uint8_t* stage = stage_gen + b * kStageBytes;
+#pragma unroll
+        for (int g = 0; g < BN / 32; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_row + g * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = g * 32 + j * 8;
+            const int slab = c / kSlabC;
+            const int chunk = (c % kSlabC) / 8;
+            uint4* ptr = reinterpret_cast<uint4*>(stage + slab * kSlabBytes + row * kSlabRowBytes + ((chunk ^ swz) << 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c_out0 + c));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c_out0 + c + 4));
+            float f[8];
+            f[0] = __uint_as_float(v[j * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[j * 8 + 1]) + b0.y;
+            f[2] = __uint_as_float(v[j * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[j * 8 + 3]) + b0.w;
+            f[4] = __uint_as_float(v[j * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[j * 8 + 5]) + b1.y;
+            f[6] = __uint_as_float(v[j * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
+            if (p.has_res) {
+              const uint4 rr = *ptr;
+              f[0] += bf16lo(rr.x); f[1] += bf16hi(rr.x); f[2] += bf16lo(rr.y); f[3] += bf16hi(rr.y);
+              f[4] += bf16lo(rr.z); f[5] += bf16hi(rr.z); f[6] += bf16lo(rr.w); f[7] += bf16hi(rr.w);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+            o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+            *ptr = o;
+          }
+        }
+        // accumulator drained -> MMA warp may reuse it; staged tile complete -> store warp may ship it
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(tmem_empty(b));
+          mbar_arrive(stage_ready(b));
+        }
+      } else {
+        const int iw = row % kTW, ih = row / kTW;
+        const int w = w0 + iw, h = h0 + ih;
+        const bool ok = (w < p.Wo) && (h < p.Ho);
+        const size_t plane = static_cast<size_t>(p.Ho) * p.Wo;
+        float* dst = p.out_f32 + (static_cast<size_t>(n) * p.Cout) * plane + static_cast<size_t>(h) * p.Wo + w;
+#pragma unroll
+        for (int g = 0; g < BN / 32; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_row + g * 32, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int c = c_out0 + g * 32 + e;
+              if (c < p.Cout) {
+                float f = __uint_as_float(v[e]) + __ldg(p.bias + c);
+                if (p.relu) f = fmaxf(f, 0.f);
+                dst[static_cast<size_t>(c) * plane] = f;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty(b));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_acc);
+}
+
+template <int BN, int CK>
+cudaError_t ws_launch_inst(const Conv3Launch& L, cudaStream_t stream) {
+  conv3_ws_kernel<BN, CK><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
+  return cudaGetLastError();
+}
+template <int BN, int CK>
+cudaError_t ws_init_inst() {
+  return cudaFuncSetAttribute(conv3_ws_kernel<BN, CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3MaxSmem);
+}
+
+}  // namespace
+
+cudaError_t conv3_ws_launch(const Conv3Launch& L, cudaStream_t stream) {
+  const int BN = L.BN, CK = L.CK;
+  if (BN == 32 && CK == 32) return ws_launch_inst<32, 32>(L, stream);
+  if (BN == 32 && CK == 64) return ws_launch_inst<32, 64>(L, stream);
+  if (BN == 64 && CK == 32) return ws_launch_inst<64, 32>(L, stream);
+  if (BN == 64 && CK == 64) return ws_launch_inst<64, 64>(L, stream);
+  if (BN == 128 && CK == 32) return ws_launch_inst<128, 32>(L, stream);
+  if (BN == 128 && CK == 64) return ws_launch_inst<128, 64>(L, stream);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t conv3_ws_init() {
+  cudaError_t e;
+  if ((e = ws_init_inst<32, 32>()) != cudaSuccess) return e;
+  if ((e = ws_init_inst<32, 64>()) != cudaSuccess) return e;
+  if ((e = ws_init_inst<64, 32>()) != cudaSuccess) return e;
+  if ((e = ws_init_inst<64, 64>()) != cudaSuccess) return e;
+  if ((e = ws_init_inst<128, 32>()) != cudaSuccess) return e;
+  if ((e = ws_init_inst<128, 64>()) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+// Shared-memory plan for (BN, CK, chunks): returns the number of patch buffers (0: does not fit) and the bytes.
+int conv3_ws_plan(int BN, int CK, int chunks, size_t* smem_bytes) {
+  const size_t w = static_cast<size_t>(9) * chunks * BN * CK * 2;
+  const size_t stage = static_cast<size_t>(2) * 128 * BN * 2;
+  const size_t patch = (static_cast<size_t>(kPH) * kPW * CK * 2 + 1023) / 1024 * 1024;
+  const size_t fixed = w + stage + 512 /*barriers*/ + 1024 /*alignment slack*/;  // see kernel smem carve-up
+  if (fixed + 2 * patch > static_cast<size_t>(kConv3MaxSmem)) return 0;
+  size_t np = (kConv3MaxSmem - fixed) / patch;
+  if (np > static_cast<size_t>(kMaxPatch)) np = kMaxPatch;
+  if (smem_bytes) *smem_bytes = fixed + np * patch;
+  return static_cast<int>(np);
+}
+
+}  // namespace pidnet

@@ -50,6 +50,34 @@ struct ConvLaunch {
   dim3 grid;
 };
 
+// ---- conv3x3 stride-1 weight-stationary / halo-patch / persistent kernel (conv3_ws.cu)
+constexpr int kConv3MaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+struct Conv3Params {
+  CUtensorMap tmA;   // input  [N,H,W,C]  box {CK, 10, 18, 1}
+  CUtensorMap tmW;   // packed weights [Cout_pad][9*chunks*CK], box {CK, BN}
+  CUtensorMap tmR;   // residual, box {min(BN,64), 8, 16, 1}
+  CUtensorMap tmD;   // output,   box {min(BN,64), 8, 16, 1}
+  int chunks;        // ceil(Cin / CK)
+  int npatch;        // halo patch ring depth
+  int tiles_w, tiles_h, N;
+  int Cout, Ho, Wo;
+  int relu, has_res, out_mode;
+  const float* bias;
+  float* out_f32;
+};
+
+struct Conv3Launch {
+  Conv3Params p;
+  int BN, CK;
+  dim3 grid;          // (persistent CTAs per Cout tile, Cout tiles)
+  size_t smem_bytes;
+};
+
+cudaError_t conv3_ws_launch(const Conv3Launch& L, cudaStream_t stream);
+cudaError_t conv3_ws_init();
+int conv3_ws_plan(int BN, int CK, int chunks, size_t* smem_bytes);
+
 // Launches the kernel instance for (BN, BK); returns cudaError_t.
 cudaError_t conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);
 // One-time: opt in to large dynamic shared memory for all instances.

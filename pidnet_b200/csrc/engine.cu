@@ -20,6 +20,15 @@
 #include "kernels.cuh"
 
 namespace pidnet {
+struct ProbeParams {
+  CUtensorMap tmA, tmB;
+  int r, s, mode;
+  float* out;
+};
+cudaError_t halo_probe_launch(const ProbeParams& p, cudaStream_t st);
+}  // namespace pidnet
+
+namespace pidnet {
 
 // ----------------------------------------------------------------------------------------- errors
 static thread_local std::string g_err;
@@ -140,6 +149,7 @@ struct ConvSrcSpec {
 struct Builder {
   bool dry = true;
   int conv_impl = 0;
+  int use_ws = 1;   // weight-stationary halo-patch kernel for 3x3 stride-1 convs
   int num_sms = 148;
   size_t act_cur = 0, wt_cur = 0;
   uint8_t* act_base = nullptr;
@@ -262,6 +272,22 @@ struct Builder {
     const int m_tiles = tiles_w * tiles_h * tiles_n;
     int BN = Cout >= 128 ? 128 : (Cout > 32 ? 64 : 32);
     while (BN > 32 && static_cast<long>(m_tiles) * cdiv(Cout, BN) < num_sms) BN >>= 1;
+    // weight-stationary halo-patch kernel: single-source 3x3 stride-1 convs whose 9*Cin*BN weights fit in smem
+    bool ws = false;
+    int ws_np = 0;
+    size_t ws_smem = 0;
+    if (conv_impl == 0 && use_ws && srcs.size() == 1 && srcs[0].k == 3 && srcs[0].stride == 1) {
+      const int chunks = cdiv(in0.C, BK);
+      for (int bn = 128; bn >= 32 && !ws; bn >>= 1) {
+        if (bn > 32 && bn / 2 >= Cout) continue;
+        const int np = conv3_ws_plan(bn, BK, chunks, &ws_smem);
+        if (np >= 2) {
+          ws = true;
+          ws_np = np;
+          BN = bn;
+        }
+      }
+    }
     const int n_tiles = cdiv(Cout, BN);
     const int Cout_pad = n_tiles * BN;
 
@@ -392,6 +418,37 @@ struct Builder {
       if (out_slot < 0) p.tmD = out_map(out);
       if (res) p.tmR = out_map(*res);
     }
+    Conv3Launch L3;
+    std::memset(&L3, 0, sizeof(L3));
+    if (ws) {
+      Conv3Params& q = L3.p;
+      L3.BN = BN; L3.CK = BK; L3.smem_bytes = ws_smem;
+      q.chunks = cdiv(in0.C, BK);
+      q.npatch = ws_np;
+      q.tiles_w = cdiv(Wo, 8); q.tiles_h = cdiv(Ho, 16); q.N = N;
+      q.Cout = Cout; q.Ho = Ho; q.Wo = Wo;
+      q.relu = p.relu; q.has_res = p.has_res; q.out_mode = p.out_mode;
+      q.bias = bdev;
+      const long mt = static_cast<long>(N) * q.tiles_w * q.tiles_h;
+      long gx = std::max<long>(1, num_sms / n_tiles);
+      if (gx > mt) gx = mt;
+      L3.grid = dim3(static_cast<unsigned>(gx), n_tiles, 1);
+      if (!dry) {
+        auto nhwc_map = [&](const T& t, int boxc, int bw, int bh) {
+          uint64_t dims4[4] = {static_cast<uint64_t>(t.C), static_cast<uint64_t>(t.W), static_cast<uint64_t>(t.H),
+                               static_cast<uint64_t>(t.N)};
+          uint64_t str[3] = {static_cast<uint64_t>(t.ps) * 2, static_cast<uint64_t>(t.W) * t.ps * 2,
+                             static_cast<uint64_t>(t.H) * t.W * t.ps * 2};
+          uint32_t box4[4] = {static_cast<uint32_t>(boxc), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1};
+          return encode_map(t.ptr, 4, dims4, str, box4, boxc * 2);
+        };
+        q.tmA = nhwc_map(in0, BK, 10, 18);
+        q.tmW = p.tmB;
+        const int SC = BN < 64 ? BN : 64;
+        if (out_slot < 0) q.tmD = nhwc_map(out, SC, 8, 16);
+        if (res) q.tmR = nhwc_map(*res, SC, 8, 16);
+      }
+    }
     // ---- SIMT restatement parameters
     for (int si = 0; si < p.nsrc; ++si) R.src[si] = p.src[si];
     R.nsrc = p.nsrc; R.BK = BK; R.wpk = wdev; R.Ktot = Ktot; R.bias = bdev;
@@ -411,7 +468,11 @@ struct Builder {
     for (const auto& s : srcs) ins.push_back(&s.in);
     if (res) ins.push_back(res);
     const int impl = conv_impl;
-    const int idx = add_op(name, ins, [L, R, impl, out_slot](cudaStream_t st, const RunArgs& a) mutable {
+    const int idx = add_op(name, ins, [L, L3, ws, R, impl, out_slot](cudaStream_t st, const RunArgs& a) mutable {
+      if (impl == 0 && ws) {
+        if (out_slot >= 0) L3.p.out_f32 = a.out[out_slot];
+        return conv3_ws_launch(L3, st);
+      }
       if (impl == 0) {
         if (out_slot >= 0) L.p.out_f32 = a.out[out_slot];
         return conv_tc_launch(L, st);
@@ -422,7 +483,8 @@ struct Builder {
     {
       Op& op = ops[idx];
       char lab[64];
-      if (impl == 0) std::snprintf(lab, sizeof(lab), "conv_tc<BN=%d,BK=%d>", BN, BK);
+      if (impl == 0 && ws) std::snprintf(lab, sizeof(lab), "conv3_ws<BN=%d,CK=%d>", BN, BK);
+      else if (impl == 0) std::snprintf(lab, sizeof(lab), "conv_tc<BN=%d,BK=%d>", BN, BK);
       else std::snprintf(lab, sizeof(lab), "conv_ref");
       op.kernel = lab;
       for (const auto& s : srcs) {
@@ -452,6 +514,7 @@ struct Engine {
   int N = 0, H = 0, W = 0;
   int lanes = 3;
   int conv_impl = 0;
+  int use_ws = 1;
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;  // capture origin (the caller's stream may be the legacy default stream)
   std::vector<cudaEvent_t> events;  // one per op that records
@@ -918,7 +981,9 @@ struct Engine {
     if (conv_impl == 0) {
       if (prop.major != 10) fail("the tcgen05 conv path needs an sm_100 GPU (found sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
       CK(conv_tc_init());
+      CK(conv3_ws_init());
     }
+    b.use_ws = use_ws;
     b.reset(true);
     build();  // dry pass: sizes only
     const size_t act_bytes = b.act_cur, wt_bytes = b.wt_cur;
@@ -1096,6 +1161,7 @@ int pidnet_set_option(pidnet_engine* h, const char* name, int value) {
     const std::string k = name;
     if (k == "conv_impl") h->e.conv_impl = value;
     else if (k == "lanes") h->e.lanes = value == 3 ? 3 : 1;
+    else if (k == "use_ws") h->e.use_ws = value ? 1 : 0;
     else fail("unknown option '" + k + "'");
     h->e.planned = false;
   });
@@ -1174,7 +1240,10 @@ int pidnet_op_conv2d(void* stream, const void* x, int N, int H, int W, int Cin, 
     if (groups < 1 || Cin % groups || Cout % groups) fail("bad groups");
     if (groups > 1 && out_nchw_f32) fail("grouped conv with NCHW output is not supported");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (impl == 0) CK(conv_tc_init());
+    if (impl != 1) {
+      CK(conv_tc_init());
+      CK(conv3_ws_init());
+    }
     const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
     const int cig = Cin / groups, cog = Cout / groups;
     Builder b;
@@ -1183,7 +1252,8 @@ int pidnet_op_conv2d(void* stream, const void* x, int N, int H, int W, int Cin, 
     CK(cudaGetDevice(&dev));
     CK(cudaGetDeviceProperties(&prop, dev));
     b.num_sms = prop.multiProcessorCount;
-    b.conv_impl = impl;
+    b.conv_impl = impl == 1 ? 1 : 0;
+    b.use_ws = impl == 2 ? 0 : 1;
     T xin = ext_tensor(x, N, H, W, Cin);
     T rt, ot;
     if (res) rt = ext_tensor(res, N, Ho, Wo, Cout);
@@ -1289,6 +1359,24 @@ int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d,
     CK(bag_blend_launch(ext_tensor(p, N, H, W, C).view(), ext_tensor(i_low, N, h, w, C).view(),
                         ext_tensor(d, N, H, W, C).view(), ext_tensor(out, N, H, W, C).view(), s, t,
                         reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
+
+
+// hardware probe (see probe.cu): x [18][10][64] bf16, w [64][64] bf16 (device), out [128][64] fp32 (device)
+int pidnet_probe_halo(void* stream, const void* x, const void* w, int r, int s, int mode, float* out) {
+  return guard([&] {
+    ProbeParams p;
+    std::memset(&p, 0, sizeof(p));
+    uint64_t dims[4] = {64, 10, 18, 1}, str[3] = {128, 1280, 23040};
+    uint32_t box[4] = {64, 10, 18, 1};
+    p.tmA = encode_map(x, 4, dims, str, box, 128);
+    uint64_t d2[2] = {64, 64}, s2[1] = {128};
+    uint32_t b2[2] = {64, 64};
+    p.tmB = encode_map(w, 2, d2, s2, b2, 128);
+    p.r = r; p.s = s; p.mode = mode; p.out = out;
+    CK(halo_probe_launch(p, reinterpret_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
   });
 }
 

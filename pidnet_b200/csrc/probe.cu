@@ -1,0 +1,82 @@
+// Hardware probe (kept as a documented experiment, not on the product path): does tcgen05.mma read a
+// K-major SWIZZLE_128B operand correctly when the descriptor start address is shifted by whole
+// 128-byte rows inside a TMA-written halo patch and the 8-row groups are SBO = 1280 B apart
+// (10-pixel patch rows), i.e. is the swizzle XOR a function of absolute smem address bits?
+// If yes, one (TH+2)x(TW+2) patch load can feed all nine 3x3 taps.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "ptx.cuh"
+
+namespace pidnet {
+
+struct ProbeParams {
+  CUtensorMap tmA;  // [1,18,10,64] bf16 NHWC, box {64,10,18,1}, SWIZZLE_128B
+  CUtensorMap tmB;  // [64][64] bf16, box {64,64}, SWIZZLE_128B
+  int r, s, mode;   // mode 1: also program base_offset = (start >> 7) & 7
+  float* out;       // [128][64]
+};
+
+__global__ void __launch_bounds__(128) halo_probe_kernel(const __grid_constant__ ProbeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t patch = base;            // 180 rows x 128 B = 23040 B
+  const uint32_t wts = base + 23552;      // 1024-aligned
+  const uint32_t bar = wts + 8192;
+  const uint32_t bar2 = bar + 8;
+  const uint32_t slot = bar + 16;
+  volatile uint32_t* slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 23552 + 8192 + 16);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<64>(slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_gen;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, 23040 + 8192);
+    tma_load_4d(patch, &p.tmA, bar, 0, 0, 0, 0);
+    tma_load_2d(wts, &p.tmB, bar, 0, 0);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+    const uint32_t a_start = patch + (p.r * 10 + p.s) * 128;
+    uint64_t a_desc = 0;
+    a_desc |= static_cast<uint64_t>((a_start & 0x3FFFF) >> 4);
+    a_desc |= static_cast<uint64_t>(1) << 16;
+    a_desc |= static_cast<uint64_t>(1280 >> 4) << 32;  // SBO: one tile row (8 px) per 10-px patch row
+    a_desc |= static_cast<uint64_t>(1) << 46;
+    if (p.mode == 1) a_desc |= static_cast<uint64_t>((a_start >> 7) & 7) << 49;
+    a_desc |= static_cast<uint64_t>(2) << 61;
+    const uint64_t b_desc = make_kmajor_desc(wts, 128);
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0);
+    umma_commit(bar2);
+  }
+  __syncwarp();
+  mbar_wait(bar2, 0);
+  tc_fence_after();
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int g = 0; g < 2; ++g) {
+    uint32_t v[32];
+    tmem_ld32(t_row + g * 32, v);
+    tmem_ld_wait();
+    for (int e = 0; e < 32; ++e) p.out[threadIdx.x * 64 + g * 32 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<64>(tmem);
+}
+
+cudaError_t halo_probe_launch(const ProbeParams& p, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(halo_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
+  if (e != cudaSuccess) return e;
+  halo_probe_kernel<<<1, 128, 40960, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace pidnet

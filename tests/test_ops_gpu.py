@@ -42,10 +42,19 @@ CONV_CASES = [
     (1, 16, 32, 256, 256, 3, 2, 1, False, True, False),   # layer5.0.conv2-like
     (3, 1, 1, 512, 96, 1, 1, 1, False, False, False),     # global-pool branch: 1x1 maps
     (1, 128, 256, 64, 1, 1, 1, 1, False, False, True),    # seghead_d: single output channel
+    # 3x3 stride-1 single-source: the weight-stationary halo-patch kernel (impl 0)
+    (2, 64, 128, 128, 128, 3, 1, 1, True, True, False),   # C=128: 2 chunks, BN=64 x 2 Cout tiles
+    (1, 90, 120, 128, 128, 3, 1, 1, True, False, False),  # CamVid 1/8: ragged 16x8 tiles
+    (2, 64, 64, 32, 32, 3, 1, 1, True, True, False),      # layer1: CK=32 (SWIZZLE_64B patches)
+    (1, 32, 64, 256, 256, 3, 1, 1, False, True, False),   # layer4: 4 chunks, BN=32 x 8 Cout tiles
+    (1, 64, 128, 128, 32, 3, 1, 1, False, False, False),  # diff3
+    (1, 128, 256, 128, 128, 3, 1, 1, False, True, False), # final_layer.conv1 (many tiles per CTA)
+    (4, 16, 32, 112, 112, 3, 1, 1, False, False, False),  # DAPPM process conv (K tail 112 = 64 + 48)
+    (1, 40, 24, 64, 19, 3, 1, 1, False, False, True),     # 3x3 with fp32 NCHW output
 ]
 
 
-@pytest.mark.parametrize('impl', [1, 0], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('impl', [1, 2, 0], ids=['simt', 'tcgen05-generic', 'tcgen05-default'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: 'x'.join(map(str, c)))
 def test_conv2d(case, impl):
     dev = _dev()
@@ -78,8 +87,10 @@ def test_conv2d_impls_agree_large():
     b = torch.randn(64, generator=g)
     xn = U.to_nhwc_bf16(x)
     a = U.op_conv2d(xn, w, b, 1, 1, xn, True, False, 0)
+    g2 = U.op_conv2d(xn, w, b, 1, 1, xn, True, False, 2)
     c = U.op_conv2d(xn, w, b, 1, 1, xn, True, False, 1)
-    _check(a.float(), c.float(), 1e-2, 'tc vs simt')
+    _check(a.float(), c.float(), 1e-2, 'ws vs simt')
+    _check(g2.float(), c.float(), 1e-2, 'generic vs simt')
 
 
 def test_stem():
