@@ -249,7 +249,7 @@ def run_ours(a):
         dom = top[0]
         tf = dom['flops'] / (dom['ms'] * 1e-3) / 1e12
         gbs = dom['bytes'] / (dom['ms'] * 1e-3) / 1e9
-        tensor_bound = dom['kernel'].startswith('conv_tc')
+        tensor_bound = dom['kernel'].startswith('conv')
         line['roofline'] = {
             'kernel': dom['kernel'], 'bound': 'tensor' if tensor_bound else 'hbm',
             'achieved': tf if tensor_bound else gbs, 'peak': peaks['tc_sustained'] if tensor_bound else peaks['hbm'],

@@ -16,6 +16,10 @@
 //   * a dedicated store warp issues the TMA stores and signals when a staging buffer has drained, so
 //     the epilogue warps never wait on a store and the residual prefetch of tile i+2 starts early.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue, 6 = TMA store.
+//
+// MODE 1 is the same persistent, weight-stationary pipeline for 1x1 stride-1 convs over the flattened
+// pixel dimension (tile = 128 consecutive pixels, one tap, up to two K-concatenated sources): these
+// layers have K of only 64..512, so they are pure streaming and live or die by the per-tile overhead.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 
@@ -34,16 +38,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int CK>
+template <int CK, int MODE>
 struct WsGeom {
   static constexpr int kRowBytes = CK * 2;                          // one pixel of one chunk
-  static constexpr int kPatchBytes = kPH * kPW * kRowBytes;         // 23040 / 11520
+  static constexpr int kPatchRows = MODE == 0 ? kPH * kPW : 128;    // halo patch | plain 128-pixel tile
+  static constexpr int kPatchBytes = kPatchRows * kRowBytes;
   static constexpr int kPatchStride = (kPatchBytes + 1023) / 1024 * 1024;
+  static constexpr int kTaps = MODE == 0 ? 9 : 1;
+  static constexpr int kSboBytes = MODE == 0 ? kPW * kRowBytes : 8 * kRowBytes;
 };
 
-template <int BN, int CK>
+template <int BN, int CK, int MODE>
 __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_constant__ Conv3Params p) {
-  using G = WsGeom<CK>;
+  using G = WsGeom<CK, MODE>;
   constexpr int kSlabC = BN < 64 ? BN : 64;
   constexpr int kSlabRowBytes = kSlabC * 2;
   constexpr int kSlabBytes = 128 * kSlabRowBytes;
@@ -58,7 +65,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   const int chunks = p.chunks;
   const int npatch = p.npatch;
   const uint32_t w_base = smem_base;
-  const uint32_t w_bytes = 9u * chunks * kWTileBytes;
+  const uint32_t w_bytes = static_cast<uint32_t>(G::kTaps) * chunks * kWTileBytes;
   const uint32_t patch_base = w_base + w_bytes;
   const uint32_t stage_base = patch_base + npatch * G::kPatchStride;
   uint8_t* stage_gen = smem_gen + w_bytes + npatch * G::kPatchStride;
@@ -82,7 +89,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   const int n_tile = blockIdx.y;
   const int c_out0 = n_tile * BN;
   const int per_img = p.tiles_w * p.tiles_h;
-  const int m_tiles = p.N * per_img;
+  const int m_tiles = MODE == 0 ? p.N * per_img : p.tiles_w;   // MODE 1: tiles_w = ceil(rows / 128)
+  // tile -> TMA coordinates (w, h, n) of its first output pixel
+  auto tile_coord = [&](int tile, int& w0, int& h0, int& n) {
+    if (MODE == 0) {
+      n = tile / per_img;
+      const int rem = tile - n * per_img;
+      const int th = rem / p.tiles_w;
+      w0 = (rem - th * p.tiles_w) * kTW;
+      h0 = th * kTH;
+    } else {
+      w0 = tile * 128; h0 = 0; n = 0;
+    }
+  };
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
@@ -111,21 +130,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
       tma_prefetch_desc(&p.tmA);
       tma_prefetch_desc(&p.tmW);
       mbar_arrive_expect_tx(w_full, w_bytes);
-      for (int t = 0; t < 9 * chunks; ++t)
+      for (int t = 0; t < G::kTaps * chunks; ++t)
         tma_load_2d(w_base + t * kWTileBytes, &p.tmW, w_full, t * CK, c_out0);
       int item = 0, i = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
-        const int n = tile / per_img;
-        const int rem = tile - n * per_img;
-        const int th = rem / p.tiles_w;
-        const int tw = rem - th * p.tiles_w;
-        const int w0 = tw * kTW, h0 = th * kTH;
+        int w0, h0, n;
+        tile_coord(tile, w0, h0, n);
         for (int c = 0; c < chunks; ++c, ++item) {
           const int slot = item % npatch;
           const uint32_t ph = (item / npatch) & 1;
           mbar_wait(patch_empty(slot), ph ^ 1);
           mbar_arrive_expect_tx(patch_full(slot), G::kPatchBytes);
-          tma_load_4d(patch_base + slot * G::kPatchStride, &p.tmA, patch_full(slot), c * CK, w0 - 1, h0 - 1, n);
+          if (MODE == 0) {
+            tma_load_4d(patch_base + slot * G::kPatchStride, &p.tmA, patch_full(slot), c * CK, w0 - 1, h0 - 1, n);
+          } else {
+            const bool first = c < p.chunks0;
+            tma_load_4d(patch_base + slot * G::kPatchStride, first ? &p.tmA : &p.tmA2, patch_full(slot),
+                        (first ? c : c - p.chunks0) * CK, w0, 0, 0);
+          }
         }
         if (p.has_res) {
           const int b = i & 1;
@@ -145,7 +167,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
       constexpr uint32_t idesc = make_idesc_bf16(128, BN);
       constexpr uint64_t kLayout = (CK == 64) ? 2ull : 4ull;  // SWIZZLE_128B / SWIZZLE_64B
       // A: 8-pixel tile rows are 10 patch pixels apart
-      const uint64_t a_hi = (static_cast<uint64_t>((kPW * G::kRowBytes) >> 4) << 32) | (1ull << 46) | (kLayout << 61) |
+      const uint64_t a_hi = (static_cast<uint64_t>(G::kSboBytes >> 4) << 32) | (1ull << 46) | (kLayout << 61) |
                             (1ull << 16);
       mbar_wait(w_full, 0);
       tc_fence_after();
@@ -163,7 +185,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
           tc_fence_after();
           const uint32_t pbase = patch_base + slot * G::kPatchStride;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < G::kTaps; ++tap) {
             const int r = tap / 3, s = tap % 3;
             const uint32_t a_addr = pbase + (r * kPW + s) * G::kRowBytes;
             const uint64_t a_desc = a_hi | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4);
@@ -183,17 +205,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
     if (lane == 0 && p.out_mode == kOutNHWCbf16) {
       int i = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
-        const int n = tile / per_img;
-        const int rem = tile - n * per_img;
-        const int th = rem / p.tiles_w;
-        const int tw = rem - th * p.tiles_w;
+        int w0, h0, n;
+        tile_coord(tile, w0, h0, n);
         const int b = i & 1;
         const uint32_t u = static_cast<uint32_t>(i >> 1);
         mbar_wait(stage_ready(b), u & 1);
         for (int sl = 0; sl < kNumSlabs; ++sl)
           if (c_out0 + sl * kSlabC < p.Cout)
-            tma_store_4d(&p.tmD, stage_base + b * kStageBytes + sl * kSlabBytes, c_out0 + sl * kSlabC, tw * kTW,
-                         th * kTH, n);
+            tma_store_4d(&p.tmD, stage_base + b * kStageBytes + sl * kSlabBytes, c_out0 + sl * kSlabC, w0, h0, n);
         tma_store_commit();
         tma_store_wait_read();       // smem of this buffer has been read out
         mbar_arrive(stage_free(b));
@@ -208,11 +227,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
     const uint32_t swz = (kSlabRowBytes == 128) ? (row & 7) : (kSlabRowBytes == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
     int i = 0;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
-      const int n = tile / per_img;
-      const int rem = tile - n * per_img;
-      const int th = rem / p.tiles_w;
-      const int tw = rem - th * p.tiles_w;
-      const int w0 = tw * kTW, h0 = th * kTH;
+      int w0, h0, n;
+      tile_coord(tile, w0, h0, n);
       const int b = i & 1;
       const uint32_t u = static_cast<uint32_t>(i >> 1);
       mbar_wait(tmem_full(b), u & 1);
@@ -264,10 +280,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
           mbar_arrive(stage_ready(b));
         }
       } else {
-        const int iw = row % kTW, ih = row / kTW;
-        const int w = w0 + iw, h = h0 + ih;
-        const bool ok = (w < p.Wo) && (h < p.Ho);
+        int w, h;
+        bool ok;
         const size_t plane = static_cast<size_t>(p.Ho) * p.Wo;
+        if (MODE == 0) {
+          w = w0 + row % kTW; h = h0 + row / kTW;
+          ok = (w < p.Wo) && (h < p.Ho);
+        } else {
+          const long pix = static_cast<long>(w0) + row;          // flat pixel index over (n, h, w)
+          ok = pix < static_cast<long>(p.N) * static_cast<long>(plane);
+          n = static_cast<int>(pix / static_cast<long>(plane));
+          const int rem = static_cast<int>(pix - static_cast<long>(n) * static_cast<long>(plane));
+          h = rem / p.Wo; w = rem - h * p.Wo;
+        }
         float* dst = p.out_f32 + (static_cast<size_t>(n) * p.Cout) * plane + static_cast<size_t>(h) * p.Wo + w;
 #pragma unroll
         for (int g = 0; g < BN / 32; ++g) {
@@ -299,12 +324,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
 
 template <int BN, int CK>
 cudaError_t ws_launch_inst(const Conv3Launch& L, cudaStream_t stream) {
-  conv3_ws_kernel<BN, CK><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
+  if (L.mode == 0) conv3_ws_kernel<BN, CK, 0><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
+  else conv3_ws_kernel<BN, CK, 1><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
   return cudaGetLastError();
 }
 template <int BN, int CK>
 cudaError_t ws_init_inst() {
-  return cudaFuncSetAttribute(conv3_ws_kernel<BN, CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3MaxSmem);
+  cudaError_t e = cudaFuncSetAttribute(conv3_ws_kernel<BN, CK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kConv3MaxSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv3_ws_kernel<BN, CK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3MaxSmem);
 }
 
 }  // namespace
@@ -332,10 +361,10 @@ cudaError_t conv3_ws_init() {
 }
 
 // Shared-memory plan for (BN, CK, chunks): returns the number of patch buffers (0: does not fit) and the bytes.
-int conv3_ws_plan(int BN, int CK, int chunks, size_t* smem_bytes) {
-  const size_t w = static_cast<size_t>(9) * chunks * BN * CK * 2;
+int conv3_ws_plan(int mode, int BN, int CK, int chunks, size_t* smem_bytes) {
+  const size_t w = static_cast<size_t>(mode == 0 ? 9 : 1) * chunks * BN * CK * 2;
   const size_t stage = static_cast<size_t>(2) * 128 * BN * 2;
-  const size_t patch = (static_cast<size_t>(kPH) * kPW * CK * 2 + 1023) / 1024 * 1024;
+  const size_t patch = (static_cast<size_t>(mode == 0 ? kPH * kPW : 128) * CK * 2 + 1023) / 1024 * 1024;
   const size_t fixed = w + stage + 512 /*barriers*/ + 1024 /*alignment slack*/;  // see kernel smem carve-up
   if (fixed + 2 * patch > static_cast<size_t>(kConv3MaxSmem)) return 0;
   size_t np = (kConv3MaxSmem - fixed) / patch;

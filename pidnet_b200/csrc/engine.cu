@@ -272,19 +272,29 @@ struct Builder {
     const int m_tiles = tiles_w * tiles_h * tiles_n;
     int BN = Cout >= 128 ? 128 : (Cout > 32 ? 64 : 32);
     while (BN > 32 && static_cast<long>(m_tiles) * cdiv(Cout, BN) < num_sms) BN >>= 1;
-    // weight-stationary halo-patch kernel: single-source 3x3 stride-1 convs whose 9*Cin*BN weights fit in smem
+    // persistent weight-stationary kernels (conv3_ws.cu): mode 0 = single-source 3x3 stride-1 (halo patch),
+    // mode 1 = 1x1 stride-1 (<= 2 sources) over flattened pixels; used when the Cout tile's weights fit in smem
     bool ws = false;
-    int ws_np = 0;
+    int ws_mode = 0, ws_np = 0, ws_chunks = 0;
     size_t ws_smem = 0;
-    if (conv_impl == 0 && use_ws && srcs.size() == 1 && srcs[0].k == 3 && srcs[0].stride == 1) {
-      const int chunks = cdiv(in0.C, BK);
-      for (int bn = 128; bn >= 32 && !ws; bn >>= 1) {
-        if (bn > 32 && bn / 2 >= Cout) continue;
-        const int np = conv3_ws_plan(bn, BK, chunks, &ws_smem);
-        if (np >= 2) {
-          ws = true;
-          ws_np = np;
-          BN = bn;
+    if (conv_impl == 0 && use_ws) {
+      bool all1x1 = true;
+      for (const auto& sp : srcs) {
+        ws_chunks += cdiv(sp.in.C, BK);
+        if (sp.k != 1 || sp.stride != 1) all1x1 = false;
+      }
+      const bool m0 = srcs.size() == 1 && srcs[0].k == 3 && srcs[0].stride == 1;
+      if (m0 || all1x1) {
+        ws_mode = m0 ? 0 : 1;
+        for (int bn = 128; bn >= 32 && !ws; bn >>= 1) {
+          if (bn > 32 && bn / 2 >= Cout) continue;      // tile wider than needed
+          if (m0 && bn == 32 && Cout > 32) continue;    // N=32 MMAs re-reading the patch per Cout tile lose to the generic kernel
+          const int np = conv3_ws_plan(ws_mode, bn, BK, ws_chunks, &ws_smem);
+          if (np >= (m0 ? 2 : 3)) {
+            ws = true;
+            ws_np = np;
+            BN = bn;
+          }
         }
       }
     }
@@ -422,14 +432,22 @@ struct Builder {
     std::memset(&L3, 0, sizeof(L3));
     if (ws) {
       Conv3Params& q = L3.p;
-      L3.BN = BN; L3.CK = BK; L3.smem_bytes = ws_smem;
-      q.chunks = cdiv(in0.C, BK);
+      L3.BN = BN; L3.CK = BK; L3.mode = ws_mode; L3.smem_bytes = ws_smem;
+      q.chunks = ws_chunks;
+      q.chunks0 = cdiv(in0.C, BK);
       q.npatch = ws_np;
-      q.tiles_w = cdiv(Wo, 8); q.tiles_h = cdiv(Ho, 16); q.N = N;
-      q.Cout = Cout; q.Ho = Ho; q.Wo = Wo;
+      q.N = N; q.Cout = Cout; q.Ho = Ho; q.Wo = Wo;
       q.relu = p.relu; q.has_res = p.has_res; q.out_mode = p.out_mode;
       q.bias = bdev;
-      const long mt = static_cast<long>(N) * q.tiles_w * q.tiles_h;
+      const long rows = static_cast<long>(N) * Ho * Wo;
+      long mt;
+      if (ws_mode == 0) {
+        q.tiles_w = cdiv(Wo, 8); q.tiles_h = cdiv(Ho, 16);
+        mt = static_cast<long>(N) * q.tiles_w * q.tiles_h;
+      } else {
+        mt = (rows + 127) / 128;
+        q.tiles_w = static_cast<int>(mt); q.tiles_h = 1;
+      }
       long gx = std::max<long>(1, num_sms / n_tiles);
       if (gx > mt) gx = mt;
       L3.grid = dim3(static_cast<unsigned>(gx), n_tiles, 1);
@@ -442,11 +460,25 @@ struct Builder {
           uint32_t box4[4] = {static_cast<uint32_t>(boxc), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1};
           return encode_map(t.ptr, 4, dims4, str, box4, boxc * 2);
         };
-        q.tmA = nhwc_map(in0, BK, 10, 18);
-        q.tmW = p.tmB;
+        auto flat_map = [&](const T& t, int boxc) {
+          const uint64_t r = static_cast<uint64_t>(t.N) * t.H * t.W;
+          uint64_t dims4[4] = {static_cast<uint64_t>(t.C), r, 1, 1};
+          uint64_t str[3] = {static_cast<uint64_t>(t.ps) * 2, r * t.ps * 2, r * t.ps * 2};
+          uint32_t box4[4] = {static_cast<uint32_t>(boxc), 128, 1, 1};
+          return encode_map(t.ptr, 4, dims4, str, box4, boxc * 2);
+        };
         const int SC = BN < 64 ? BN : 64;
-        if (out_slot < 0) q.tmD = nhwc_map(out, SC, 8, 16);
-        if (res) q.tmR = nhwc_map(*res, SC, 8, 16);
+        q.tmW = p.tmB;
+        if (ws_mode == 0) {
+          q.tmA = nhwc_map(in0, BK, 10, 18);
+          if (out_slot < 0) q.tmD = nhwc_map(out, SC, 8, 16);
+          if (res) q.tmR = nhwc_map(*res, SC, 8, 16);
+        } else {
+          q.tmA = flat_map(in0, BK);
+          if (srcs.size() > 1) q.tmA2 = flat_map(srcs[1].in, BK);
+          if (out_slot < 0) q.tmD = flat_map(out, SC);
+          if (res) q.tmR = flat_map(*res, SC);
+        }
       }
     }
     // ---- SIMT restatement parameters
@@ -483,7 +515,7 @@ struct Builder {
     {
       Op& op = ops[idx];
       char lab[64];
-      if (impl == 0 && ws) std::snprintf(lab, sizeof(lab), "conv3_ws<BN=%d,CK=%d>", BN, BK);
+      if (impl == 0 && ws) std::snprintf(lab, sizeof(lab), "%s<BN=%d,CK=%d>", ws_mode == 0 ? "conv3_ws" : "conv1_ws", BN, BK);
       else if (impl == 0) std::snprintf(lab, sizeof(lab), "conv_tc<BN=%d,BK=%d>", BN, BK);
       else std::snprintf(lab, sizeof(lab), "conv_ref");
       op.kernel = lab;
