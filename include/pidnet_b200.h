@@ -125,6 +125,8 @@ int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d,
 int pidnet_probe_halo(void* stream, const void* x_18x10x64_bf16, const void* w_64x64_bf16, int r, int s, int mode,
                       float* out_128x64);
 
+int pidnet_probe_mma_rate(void* stream, int N, int iters, int distinct, int blocks, long long* out_cycles_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,7 @@ SIGNATURES = {
     'pidnet_op_upadd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i]),
     'pidnet_op_pool': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i]),
     'pidnet_op_lightbag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
+    'pidnet_probe_mma_rate': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'pidnet_probe_halo': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'pidnet_op_bag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }

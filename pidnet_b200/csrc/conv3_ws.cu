@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   auto stage_free = [&](int b) { return bar_base + 8u * (7 + 2 * kMaxPatch + b); };
   auto stage_ready = [&](int b) { return bar_base + 8u * (9 + 2 * kMaxPatch + b); };
   const uint32_t tmem_slot = bar_base + 8u * (11 + 2 * kMaxPatch);
+  float* bias_s = reinterpret_cast<float*>(stage_gen + 2 * kStageBytes + 256);   // BN floats after the barriers
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
       stage_gen + 2 * kStageBytes + 8 * (11 + 2 * kMaxPatch));
 
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) bias_s[threadIdx.x - 64] = p.bias[c_out0 + threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&p.tmA);
       tma_prefetch_desc(&p.tmW);
       mbar_arrive_expect_tx(w_full, w_bytes);
@@ -163,12 +165,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
     __syncwarp();
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // The whole warp runs the loop converged (waits included); one ELECTED lane issues tcgen05.mma / commit
+    // (elect.sync lets ptxas keep descriptors in uniform registers without per-MMA uniformisation loops).
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN);
       constexpr uint64_t kLayout = (CK == 64) ? 2ull : 4ull;  // SWIZZLE_128B / SWIZZLE_64B
-      // A: 8-pixel tile rows are 10 patch pixels apart
-      const uint64_t a_hi = (static_cast<uint64_t>(G::kSboBytes >> 4) << 32) | (1ull << 46) | (kLayout << 61) |
-                            (1ull << 16);
+      // descriptor high words are constant: SBO (A: tile rows are kPW patch pixels apart), version, layout
+      constexpr uint64_t a_hi = (static_cast<uint64_t>(G::kSboBytes >> 4) << 32) | (1ull << 46) | (kLayout << 61) |
+                                (1ull << 16);
+      constexpr uint64_t b_hi = (static_cast<uint64_t>((8 * G::kRowBytes) >> 4) << 32) | (1ull << 46) |
+                                (kLayout << 61) | (1ull << 16);
       mbar_wait(w_full, 0);
       tc_fence_after();
       int item = 0, i = 0;
@@ -184,25 +190,30 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
           mbar_wait(patch_full(slot), ph);
           tc_fence_after();
           const uint32_t pbase = patch_base + slot * G::kPatchStride;
+          const uint32_t wbase = w_base + c * kWTileBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int tap = 0; tap < G::kTaps; ++tap) {
-            const int r = tap / 3, s = tap % 3;
-            const uint32_t a_addr = pbase + (r * kPW + s) * G::kRowBytes;
-            const uint64_t a_desc = a_hi | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4);
-            const uint64_t b_desc = make_kmajor_desc(w_base + (tap * chunks + c) * kWTileBytes, G::kRowBytes);
+            for (int tap = 0; tap < G::kTaps; ++tap) {
+              const int r = tap / 3, s = tap % 3;
+              const uint64_t a_desc =
+                  a_hi | static_cast<uint64_t>(((pbase + (r * kPW + s) * G::kRowBytes) & 0x3FFFF) >> 4);
+              const uint64_t b_desc =
+                  b_hi | static_cast<uint64_t>(((wbase + tap * chunks * kWTileBytes) & 0x3FFFF) >> 4);
 #pragma unroll
-            for (int k = 0; k < CK / 16; ++k)
-              umma_bf16(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < CK / 16; ++k)
+                umma_bf16(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(patch_empty(slot));
+            if (c == chunks - 1) umma_commit(tmem_full(ab));
           }
-          umma_commit(patch_empty(slot));
+          __syncwarp();
         }
-        umma_commit(tmem_full(ab));
       }
     }
     __syncwarp();
   } else if (warp == 6) {
     // ============================== TMA store warp ==============================
-    if (lane == 0 && p.out_mode == kOutNHWCbf16) {
+    if (p.out_mode == kOutNHWCbf16 && elect_one()) {
       int i = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
         int w0, h0, n;
@@ -239,36 +250,44 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
         else mbar_wait(stage_free(b), (u & 1) ^ 1);
         uint8_t* stage = stage_gen + b * kStageBytes;
 #pragma unroll
-        for (int g = 0; g < BN / 32; ++g) {
-          uint32_t v[32];
-          tmem_ld32(t_row + g * 32, v);
+        for (int g2 = 0; g2 < BN / 32; g2 += 2) {
+          // two 32-column TMEM loads in flight, one wait
+          uint32_t v[2][32];
+          tmem_ld32(t_row + g2 * 32, v[0]);
+          if (g2 + 1 < BN / 32) tmem_ld32(t_row + (g2 + 1) * 32, v[1]);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = g * 32 + j * 8;
-            const int slab = c / kSlabC;
-            const int chunk = (c % kSlabC) / 8;
-            uint4* ptr = reinterpret_cast<uint4*>(stage + slab * kSlabBytes + row * kSlabRowBytes + ((chunk ^ swz) << 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c_out0 + c));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c_out0 + c + 4));
-            float f[8];
-            f[0] = __uint_as_float(v[j * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[j * 8 + 1]) + b0.y;
-            f[2] = __uint_as_float(v[j * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[j * 8 + 3]) + b0.w;
-            f[4] = __uint_as_float(v[j * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[j * 8 + 5]) + b1.y;
-            f[6] = __uint_as_float(v[j * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
-            if (p.has_res) {
-              const uint4 rr = *ptr;
-              f[0] += bf16lo(rr.x); f[1] += bf16hi(rr.x); f[2] += bf16lo(rr.y); f[3] += bf16hi(rr.y);
-              f[4] += bf16lo(rr.z); f[5] += bf16hi(rr.z); f[6] += bf16lo(rr.w); f[7] += bf16hi(rr.w);
-            }
-            if (p.relu) {
+          for (int gg = 0; gg < 2; ++gg) {
+            const int g = g2 + gg;
+            if (g >= BN / 32) break;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            for (int j = 0; j < 4; ++j) {
+              const int c = g * 32 + j * 8;
+              const int slab = c / kSlabC;
+              const int chunk = (c % kSlabC) / 8;
+              uint4* ptr =
+                  reinterpret_cast<uint4*>(stage + slab * kSlabBytes + row * kSlabRowBytes + ((chunk ^ swz) << 4));
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c + 4);
+              float f[8];
+              f[0] = __uint_as_float(v[gg][j * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[gg][j * 8 + 1]) + b0.y;
+              f[2] = __uint_as_float(v[gg][j * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[gg][j * 8 + 3]) + b0.w;
+              f[4] = __uint_as_float(v[gg][j * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[gg][j * 8 + 5]) + b1.y;
+              f[6] = __uint_as_float(v[gg][j * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[gg][j * 8 + 7]) + b1.w;
+              if (p.has_res) {
+                const uint4 rr = *ptr;
+                f[0] += bf16lo(rr.x); f[1] += bf16hi(rr.x); f[2] += bf16lo(rr.y); f[3] += bf16hi(rr.y);
+                f[4] += bf16lo(rr.z); f[5] += bf16hi(rr.z); f[6] += bf16lo(rr.w); f[7] += bf16hi(rr.w);
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              }
+              uint4 o;
+              o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+              o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+              *ptr = o;
             }
-            uint4 o;
-            o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-            o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-            *ptr = o;
           }
         }
         // accumulator drained -> MMA warp may reuse it; staged tile complete -> store warp may ship it
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
             for (int e = 0; e < 32; ++e) {
               const int c = c_out0 + g * 32 + e;
               if (c < p.Cout) {
-                float f = __uint_as_float(v[e]) + __ldg(p.bias + c);
+                float f = __uint_as_float(v[e]) + bias_s[g * 32 + e];
                 if (p.relu) f = fmaxf(f, 0.f);
                 dst[static_cast<size_t>(c) * plane] = f;
               }
@@ -365,7 +384,7 @@ int conv3_ws_plan(int mode, int BN, int CK, int chunks, size_t* smem_bytes) {
   const size_t w = static_cast<size_t>(mode == 0 ? 9 : 1) * chunks * BN * CK * 2;
   const size_t stage = static_cast<size_t>(2) * 128 * BN * 2;
   const size_t patch = (static_cast<size_t>(mode == 0 ? kPH * kPW : 128) * CK * 2 + 1023) / 1024 * 1024;
-  const size_t fixed = w + stage + 512 /*barriers*/ + 1024 /*alignment slack*/;  // see kernel smem carve-up
+  const size_t fixed = w + stage + 1024 /*barriers + bias*/ + 1024 /*alignment slack*/;  // see kernel smem carve-up
   if (fixed + 2 * patch > static_cast<size_t>(kConv3MaxSmem)) return 0;
   size_t np = (kConv3MaxSmem - fixed) / patch;
   if (np > static_cast<size_t>(kMaxPatch)) np = kMaxPatch;

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&p.tmB);
       if (p.has_res) {
         mbar_arrive_expect_tx(res_bar, C::kOutBytes);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN);
       for (int ks = 0; ks < num_k; ++ks) {
         const int st = ks % C::kStages;

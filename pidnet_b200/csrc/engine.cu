@@ -26,6 +26,7 @@ struct ProbeParams {
   float* out;
 };
 cudaError_t halo_probe_launch(const ProbeParams& p, cudaStream_t st);
+cudaError_t mma_rate_launch(int N, int iters, int distinct, int blocks, long long* out, cudaStream_t st);
 }  // namespace pidnet
 
 namespace pidnet {
@@ -889,10 +890,38 @@ struct Engine {
       View ov = x1.view();
       const int n_ = N, h_ = H, w_ = W;
       b.flops += 2.0 * N * x1.H * x1.W * Pn * 27;
-      x1.prod = b.add_op("conv1.0", {}, [ov, wd, bd, n_, h_, w_](cudaStream_t st, const RunArgs& a) {
+      const bool stem_tc = conv_impl == 0 && (Pn == 32 || Pn == 64);
+      // tcgen05 stem: weights [Cout][32] bf16 K-major, pre-swizzled the way a SWIZZLE_64B tile sits in smem
+      std::vector<uint16_t> wsw(static_cast<size_t>(Pn) * 32, 0);
+      for (int co = 0; co < Pn; ++co)
+        for (int k = 0; k < 27; ++k) {
+          const int chunk = k / 8, within = k % 8;
+          const int pos = co * 32 + ((chunk ^ ((co >> 1) & 3)) * 8) + within;
+          wsw[pos] = f2bf(w[static_cast<size_t>(co) * 27 + k]);
+        }
+      const uint8_t* wswd = reinterpret_cast<const uint8_t*>(b.alloc_wt(wsw.data(), wsw.size() * 2));
+      StemParams sp;
+      std::memset(&sp, 0, sizeof(sp));
+      sp.w_swz = wswd; sp.bias = bd; sp.H = H; sp.W = W; sp.Ho = x1.H; sp.Wo = x1.W;
+      sp.rows = static_cast<long>(N) * x1.H * x1.W;
+      sp.tiles = (sp.rows + 127) / 128;
+      if (stem_tc && !b.dry) {
+        uint64_t dims4[4] = {static_cast<uint64_t>(Pn), static_cast<uint64_t>(sp.rows), 1, 1};
+        uint64_t str[3] = {static_cast<uint64_t>(Pn) * 2, static_cast<uint64_t>(sp.rows) * Pn * 2,
+                           static_cast<uint64_t>(sp.rows) * Pn * 2};
+        uint32_t box4[4] = {static_cast<uint32_t>(Pn), 128, 1, 1};
+        sp.tmD = encode_map(x1.ptr, 4, dims4, str, box4, Pn * 2);
+      }
+      const int sms = b.num_sms;
+      x1.prod = b.add_op("conv1.0", {}, [ov, wd, bd, n_, h_, w_, sp, stem_tc, Pn, sms](cudaStream_t st, const RunArgs& a) mutable {
+        if (stem_tc) {
+          sp.x = a.x;
+          return stem_tc_launch(sp, Pn, sms, st);
+        }
         return stem_conv_launch(a.x, n_, h_, w_, ov, wd, bd, st);
       });
-      b.label(x1.prod, "stem_conv", 4.0 * N * 3 * H * W + Builder::tbytes(x1), 2.0 * N * x1.H * x1.W * Pn * 27);
+      b.label(x1.prod, stem_tc ? "stem_tc" : "stem_conv", 4.0 * N * 3 * H * W + Builder::tbytes(x1),
+              2.0 * N * x1.H * x1.W * Pn * 27);
     }
     T x = conv_bn("conv1.3", x1, "conv1.3", "conv1.4", 3, 2, true);
     b.named["conv1"] = x;
@@ -1394,6 +1423,14 @@ int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d,
   });
 }
 
+
+// hardware probe: cycles for `iters` x 4 back-to-back M128 x N x K16 SS MMAs on `blocks` CTAs (out: device int64[blocks])
+int pidnet_probe_mma_rate(void* stream, int N, int iters, int distinct, int blocks, long long* out) {
+  return guard([&] {
+    CK(mma_rate_launch(N, iters, distinct, blocks, out, reinterpret_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
 
 // hardware probe (see probe.cu): x [18][10][64] bf16, w [64][64] bf16 (device), out [128][64] fp32 (device)
 int pidnet_probe_halo(void* stream, const void* x, const void* w, int r, int s, int mode, float* out) {

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cuda.h>
 #include "conv_tc.cuh"
 
 namespace pidnet {
@@ -22,6 +23,17 @@ struct View {
 // w: [27][Cout] fp32 with k = (ci*3 + r)*3 + s ; bias: [Cout]
 cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, const float* w, const float* bias,
                              cudaStream_t st);
+
+// ---- the same stem on tcgen05 (software im2col A-producer; stem_tc.cu). Cout in {32, 64}.
+struct StemParams {
+  CUtensorMap tmD;      // output as flat [rows = N*Ho*Wo][Cout] bf16, box {Cout, 128, 1, 1}, swizzle = Cout*2 bytes
+  const float* x;       // fp32 NCHW image
+  const uint8_t* w_swz; // [Cout][32] bf16 K-major (k = (ci*3+r)*3+s, zero padded), pre-swizzled SWIZZLE_64B
+  const float* bias;    // [Cout]
+  int H, W, Ho, Wo;
+  long rows, tiles;     // N*Ho*Wo, ceil(rows / 128)
+};
+cudaError_t stem_tc_launch(const StemParams& p, int Cout, int num_sms, cudaStream_t st);
 
 // ---- PagFM fuse (model_utils.py:292-312 after the low-res algebra of DESIGN.md):
 //   low = [y | z | t | pad] at (h,w);  s = <x, U(z)> + U(t);  g = sigmoid(s);  out = relu((1-g) x + g U(y))

@@ -79,4 +79,61 @@ cudaError_t halo_probe_launch(const ProbeParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+
+// ---- MMA rate probe: one CTA per SM issues `iters` back-to-back tcgen05.mma (M=128, N, K=16, SS operands in
+// SWIZZLE_128B smem, garbage data) and reports cycles per MMA (clock64 around issue + final commit wait).
+template <int N>
+__global__ void __launch_bounds__(128) mma_rate_kernel(int iters, int distinct, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_base = base;                 // 9 x 16 KB "taps"
+  const uint32_t b_base = base + 9 * 16384;     // 9 x N*128 B
+  const uint32_t bar = b_base + 9 * N * 128;
+  const uint32_t slot = bar + 8;
+  volatile uint32_t* slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 9 * 16384 + 9 * N * 128 + 8);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc<(N < 32 ? 32 : N)>(slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_gen;
+  if (warp == 0) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, N);
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        const int t = distinct ? (i % 9) : 0;
+        const uint64_t a_desc = make_kmajor_desc(a_base + t * 16384, 128);
+        const uint64_t b_desc = make_kmajor_desc(b_base + t * N * 128, 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
+      }
+      umma_commit(bar);
+      mbar_wait(bar, 0);
+      const long long t1 = clock64();
+      out[blockIdx.x] = t1 - t0;
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<(N < 32 ? 32 : N)>(tmem);
+}
+
+cudaError_t mma_rate_launch(int N, int iters, int distinct, int blocks, long long* out, cudaStream_t st) {
+  const int smem = 9 * 16384 + 9 * N * 128 + 64 + 1024;
+#define PIDNET_RATE(NN)                                                                                       \
+  if (N == NN) {                                                                                              \
+    cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    if (e != cudaSuccess) return e;                                                                           \
+    mma_rate_kernel<NN><<<blocks, 128, smem, st>>>(iters, distinct, out);                                     \
+    return cudaGetLastError();                                                                                \
+  }
+  PIDNET_RATE(32) PIDNET_RATE(64) PIDNET_RATE(128) PIDNET_RATE(256)
+#undef PIDNET_RATE
+  return cudaErrorInvalidValue;
+}
+
 }  // namespace pidnet
