@@ -25,6 +25,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# keep stdout to the single JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
+if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+    os.environ['NCCL_DEBUG'] = 'WARN'
+
 import torch  # noqa: E402
 
 METRIC = 'pidnet_s_1024x2048_images_per_sec'
