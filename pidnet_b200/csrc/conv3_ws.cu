@@ -15,7 +15,12 @@
 //     ReLU, bf16, swizzled smem staging, TMA store) while the MMA warp already runs tile i+1.
 //   * a dedicated store warp issues the TMA stores and signals when a staging buffer has drained, so
 //     the epilogue warps never wait on a store and the residual prefetch of tile i+2 starts early.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue, 6 = TMA store.
+//   * even and odd tiles run on two independent lanes: each lane has its own MMA-issuing warp, TMEM
+//     accumulator, 4-warp epilogue group and staging buffer, so one lane's per-tile barrier/commit
+//     overhead and its ~2000-cycle epilogue hide behind the other lane's MMAs (ncu: with one lane both
+//     the issuing warp and the epilogue group sat on the critical path).
+// Warp roles: 0 = TMA producer, 1 and 10 = MMA issuers (lane 0 / 1; warp 1 also owns the TMEM allocation),
+// 2..5 and 6..9 = epilogue groups (lane 0 / 1), 11 = TMA store.
 //
 // MODE 1 is the same persistent, weight-stationary pipeline for 1x1 stride-1 convs over the flattened
 // pixel dimension (tile = 128 consecutive pixels, one tap, up to two K-concatenated sources): these
@@ -27,7 +32,7 @@ namespace pidnet {
 
 namespace {
 
-constexpr int kWsThreads = 224;
+constexpr int kWsThreads = 384;
 constexpr int kTH = 16, kTW = 8, kPH = 18, kPW = 10;
 constexpr int kMaxPatch = 8;
 
@@ -70,20 +75,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   const uint32_t stage_base = patch_base + npatch * G::kPatchStride;
   uint8_t* stage_gen = smem_gen + w_bytes + npatch * G::kPatchStride;
   const uint32_t bar_base = stage_base + 2 * kStageBytes;
-  // barriers (8 B each): w_full | patch_full[8] | patch_empty[8] | tmem_full[2] | tmem_empty[2] | res_full[2] |
+  // barriers (8 B each): w_full | patch_full[8] | patch_empty[8] | tmem_full[4] | tmem_empty[4] | res_full[2] |
   //                      stage_free[2] | stage_ready[2]
   const uint32_t w_full = bar_base;
   auto patch_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto patch_empty = [&](int s) { return bar_base + 8u * (1 + kMaxPatch + s); };
   auto tmem_full = [&](int b) { return bar_base + 8u * (1 + 2 * kMaxPatch + b); };
-  auto tmem_empty = [&](int b) { return bar_base + 8u * (3 + 2 * kMaxPatch + b); };
-  auto res_full = [&](int b) { return bar_base + 8u * (5 + 2 * kMaxPatch + b); };
-  auto stage_free = [&](int b) { return bar_base + 8u * (7 + 2 * kMaxPatch + b); };
-  auto stage_ready = [&](int b) { return bar_base + 8u * (9 + 2 * kMaxPatch + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (11 + 2 * kMaxPatch);
+  auto tmem_empty = [&](int b) { return bar_base + 8u * (5 + 2 * kMaxPatch + b); };
+  auto res_full = [&](int b) { return bar_base + 8u * (9 + 2 * kMaxPatch + b); };
+  auto stage_free = [&](int b) { return bar_base + 8u * (11 + 2 * kMaxPatch + b); };
+  auto stage_ready = [&](int b) { return bar_base + 8u * (13 + 2 * kMaxPatch + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (15 + 2 * kMaxPatch);
   float* bias_s = reinterpret_cast<float*>(stage_gen + 2 * kStageBytes + 256);   // BN floats after the barriers
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-      stage_gen + 2 * kStageBytes + 8 * (11 + 2 * kMaxPatch));
+      stage_gen + 2 * kStageBytes + 8 * (15 + 2 * kMaxPatch));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,16 +115,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
       mbar_init(patch_full(s), 1);
       mbar_init(patch_empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(tmem_full(b), 1);
       mbar_init(tmem_empty(b), 4);
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(res_full(b), 1);
       mbar_init(stage_free(b), 1);
       mbar_init(stage_ready(b), 4);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<4 * BN>(tmem_slot);   // four accumulators: two per tile-parity lane
   if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) bias_s[threadIdx.x - 64] = p.bias[c_out0 + threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
@@ -134,13 +141,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
       mbar_arrive_expect_tx(w_full, w_bytes);
       for (int t = 0; t < G::kTaps * chunks; ++t)
         tma_load_2d(w_base + t * kWTileBytes, &p.tmW, w_full, t * CK, c_out0);
-      int item = 0, i = 0;
+      // The patch ring is partitioned per lane (even slots: even tiles, odd slots: odd tiles) so that every
+      // waiter observes EVERY phase of the barriers it uses (a shared ring would alias mbarrier parities).
+      const int np_lane = npatch >> 1;
+      int i = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
         int w0, h0, n;
         tile_coord(tile, w0, h0, n);
-        for (int c = 0; c < chunks; ++c, ++item) {
-          const int slot = item % npatch;
-          const uint32_t ph = (item / npatch) & 1;
+        const int ln = i & 1;
+        int j = (i >> 1) * chunks;   // lane-local item index
+        for (int c = 0; c < chunks; ++c, ++j) {
+          const int slot = ln + 2 * (j % np_lane);
+          const uint32_t ph = (j / np_lane) & 1;
           mbar_wait(patch_empty(slot), ph ^ 1);
           mbar_arrive_expect_tx(patch_full(slot), G::kPatchBytes);
           if (MODE == 0) {
@@ -163,8 +175,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
+  } else if (warp == 1 || warp == 10) {
+    // ============================== MMA issuers (one per tile parity) ==============================
     // The whole warp runs the loop converged (waits included); one ELECTED lane issues tcgen05.mma / commit
     // (elect.sync lets ptxas keep descriptors in uniform registers without per-MMA uniformisation loops).
     {
@@ -177,16 +189,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
                                 (kLayout << 61) | (1ull << 16);
       mbar_wait(w_full, 0);
       tc_fence_after();
-      int item = 0, i = 0;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
-        const int ab = i & 1;
-        const uint32_t u = static_cast<uint32_t>(i >> 1);
-        mbar_wait(tmem_empty(ab), (u & 1) ^ 1);
+      const int ab = warp == 1 ? 0 : 1;   // this warp's tile parity (lane); each lane alternates two accumulators
+      for (int i = ab;; i += 2) {
+        const long tile = static_cast<long>(blockIdx.x) + static_cast<long>(i) * gridDim.x;
+        if (tile >= m_tiles) break;
+        const uint32_t u = static_cast<uint32_t>(i >> 1);      // lane-local tile counter
+        const int ai = ab + 2 * static_cast<int>(u & 1);       // accumulator index 0..3
+        const uint32_t acc = tmem_acc + ai * BN;
+        mbar_wait(tmem_empty(ai), ((u >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem_acc + ab * BN;
-        for (int c = 0; c < chunks; ++c, ++item) {
-          const int slot = item % npatch;
-          const uint32_t ph = (item / npatch) & 1;
+        const int np_lane = npatch >> 1;
+        int j = (i >> 1) * chunks;   // lane-local item index (see the producer)
+        for (int c = 0; c < chunks; ++c, ++j) {
+          const int slot = ab + 2 * (j % np_lane);
+          const uint32_t ph = (j / np_lane) & 1;
           mbar_wait(patch_full(slot), ph);
           tc_fence_after();
           const uint32_t pbase = patch_base + slot * G::kPatchStride;
@@ -204,14 +220,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
                 umma_bf16(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
             }
             umma_commit(patch_empty(slot));
-            if (c == chunks - 1) umma_commit(tmem_full(ab));
+            if (c == chunks - 1) umma_commit(tmem_full(ai));
           }
           __syncwarp();
         }
       }
     }
     __syncwarp();
-  } else if (warp == 6) {
+  } else if (warp == 11) {
     // ============================== TMA store warp ==============================
     if (p.out_mode == kOutNHWCbf16 && elect_one()) {
       int i = 0;
@@ -232,19 +248,22 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
     }
     __syncwarp();
   } else {
-    // ============================== epilogue (warps 2..5) ==============================
+    // ============================== epilogue groups (warps 2..5: even tiles, 6..9: odd tiles) ==============================
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;        // tile row == TMEM lane
     const uint32_t swz = (kSlabRowBytes == 128) ? (row & 7) : (kSlabRowBytes == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
-    int i = 0;
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
+    const int b = warp >= 6 ? 1 : 0;   // lane == tile parity == accumulator == staging buffer
+    for (int i = b;; i += 2) {
+      const long tile_l = static_cast<long>(blockIdx.x) + static_cast<long>(i) * gridDim.x;
+      if (tile_l >= m_tiles) break;
+      const int tile = static_cast<int>(tile_l);
       int w0, h0, n;
       tile_coord(tile, w0, h0, n);
-      const int b = i & 1;
-      const uint32_t u = static_cast<uint32_t>(i >> 1);
-      mbar_wait(tmem_full(b), u & 1);
+      const uint32_t u = static_cast<uint32_t>(i >> 1);      // lane-local tile counter == staging-buffer use count
+      const int ai = b + 2 * static_cast<int>(u & 1);        // accumulator index 0..3
+      mbar_wait(tmem_full(ai), (u >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_row = tmem_acc + b * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t t_row = tmem_acc + ai * BN + (static_cast<uint32_t>(q * 32) << 16);
       if (p.out_mode == kOutNHWCbf16) {
         if (p.has_res) mbar_wait(res_full(b), u & 1);
         else mbar_wait(stage_free(b), (u & 1) ^ 1);
@@ -295,7 +314,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(tmem_empty(b));
+          mbar_arrive(tmem_empty(ai));
           mbar_arrive(stage_ready(b));
         }
       } else {
@@ -332,13 +351,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty(b));
+        if (lane == 0) mbar_arrive(tmem_empty(ai));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<2 * BN>(tmem_acc);
+  if (warp == 1) tmem_dealloc<4 * BN>(tmem_acc);
 }
 
 template <int BN, int CK>
@@ -388,6 +407,7 @@ int conv3_ws_plan(int mode, int BN, int CK, int chunks, size_t* smem_bytes) {
   if (fixed + 2 * patch > static_cast<size_t>(kConv3MaxSmem)) return 0;
   size_t np = (kConv3MaxSmem - fixed) / patch;
   if (np > static_cast<size_t>(kMaxPatch)) np = kMaxPatch;
+  np &= ~static_cast<size_t>(1);   // even: the ring is split between the two tile-parity lanes
   if (smem_bytes) *smem_bytes = fixed + np * patch;
   return static_cast<int>(np);
 }

@@ -291,7 +291,7 @@ struct Builder {
           if (bn > 32 && bn / 2 >= Cout) continue;      // tile wider than needed
           if (m0 && bn == 32 && Cout > 32) continue;    // N=32 MMAs re-reading the patch per Cout tile lose to the generic kernel
           const int np = conv3_ws_plan(ws_mode, bn, BK, ws_chunks, &ws_smem);
-          if (np >= (m0 ? 2 : 3)) {
+          if (np >= (m0 ? 2 : 4)) {
             ws = true;
             ws_np = np;
             BN = bn;
