@@ -120,6 +120,34 @@ int pidnet_op_lightbag(void* stream, const void* p, const void* i_low, const voi
 int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d, void* out, int N, int H, int W, int C,
                   int h, int w, const float* s, const float* t);
 
+/* ---- criterion: replaces FullModel.forward after `outputs = self.model(inputs)` (utils/utils.py:41-57) with
+ * OhemCrossEntropy (utils/criterion.py:43-99; thres / min_kept / class weights / ignore label) and BondaryLoss
+ * (utils/criterion.py:102-132).  The global yacs values the reference reads (LOSS.BALANCE_WEIGHTS, LOSS.SB_WEIGHTS,
+ * MODEL.ALIGN_CORNERS=True, TRAIN.IGNORE_LABEL) are passed explicitly.
+ *   x_p, x_m, x_d : device fp32 NCHW low-res logits [N,C,h,w], [N,C,h,w], [N,1,h,w] (the three PIDNet outputs)
+ *   labels        : device int64 [N,H,W];  bd_gt: device fp32 [N,H,W] (0/1)
+ *   out12 (device fp32[12]): loss (== losses.mean()), loss_s (== loss_list[0].mean()), loss_b, pixel acc,
+ *                   ohem(x_,labels), ohem(x_,bd_label), the two OHEM thresholds, the two valid counts, |K1|, |K2|
+ *   grad_*        : optional device fp32 buffers shaped like the logits; receive d(loss.mean())/d(logits)
+ * No host synchronisation; `workspace` needs pidnet_criterion_workspace_bytes(N,H,W) device bytes. */
+typedef struct pidnet_criterion_cfg {
+  int64_t ignore_label;        /* TRAIN.IGNORE_LABEL (255) */
+  int64_t ohem_keep;           /* LOSS.OHEMKEEP (131072) */
+  float ohem_thres;            /* LOSS.OHEMTHRES (0.9) */
+  float bd_threshold;          /* 0.8, utils/utils.py:52 */
+  float balance_weight_aux;    /* LOSS.BALANCE_WEIGHTS[0] (0.4) */
+  float balance_weight_main;   /* LOSS.BALANCE_WEIGHTS[1] (1.0) */
+  float sb_weight;             /* LOSS.SB_WEIGHTS (1.0) */
+  float coeff_bce;             /* BondaryLoss(coeff_bce=20.0) */
+} pidnet_criterion_cfg;
+size_t pidnet_criterion_workspace_bytes(int N, int H, int W);
+int pidnet_criterion(void* stream, const float* x_p, const float* x_m, const float* x_d, int N, int C, int h, int w,
+                     const int64_t* labels, const float* bd_gt, int H, int W, const float* class_weights,
+                     const pidnet_criterion_cfg* cfg, void* workspace, size_t workspace_bytes, float* out12,
+                     float* grad_p, float* grad_m, float* grad_d);
+/* F.interpolate(x, size=(H,W), mode='bilinear', align_corners=True) on fp32 NCHW (utils/utils.py:44-46) */
+int pidnet_upsample_align_corners(void* stream, const float* x, int NC, int h, int w, float* out, int H, int W);
+
 /* Hardware probe used by tools/probe_halo.py (documents how tcgen05 reads shifted windows of a
  * TMA-written halo patch; not on the product path). */
 int pidnet_probe_halo(void* stream, const void* x_18x10x64_bf16, const void* w_64x64_bf16, int r, int s, int mode,

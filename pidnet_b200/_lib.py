@@ -16,6 +16,12 @@ class Cfg(C.Structure):
                 ('ppm_planes', C.c_int), ('head_planes', C.c_int), ('augment', C.c_int)]
 
 
+class CriterionCfg(C.Structure):
+    _fields_ = [('ignore_label', C.c_int64), ('ohem_keep', C.c_int64), ('ohem_thres', C.c_float),
+                ('bd_threshold', C.c_float), ('balance_weight_aux', C.c_float), ('balance_weight_main', C.c_float),
+                ('sb_weight', C.c_float), ('coeff_bce', C.c_float)]
+
+
 _vp, _fp, _i, _i64p = C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int64)
 
 # name -> (restype, argtypes); mirrors include/pidnet_b200.h one to one (tests check the list)
@@ -40,6 +46,10 @@ SIGNATURES = {
     'pidnet_op_upadd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i]),
     'pidnet_op_pool': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i]),
     'pidnet_op_lightbag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
+    'pidnet_criterion_workspace_bytes': (C.c_size_t, [_i, _i, _i]),
+    'pidnet_criterion': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, C.POINTER(CriterionCfg), _vp,
+                              C.c_size_t, _vp, _vp, _vp, _vp]),
+    'pidnet_upsample_align_corners': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i]),
     'pidnet_probe_mma_rate': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'pidnet_probe_halo': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'pidnet_op_bag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

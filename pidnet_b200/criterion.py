@@ -1,0 +1,124 @@
+"""Drop-in for the reference's criterion on the PIDNet path: `OhemCrossEntropy`, `BondaryLoss`
+(utils/criterion.py:43-132) and `FullModel` (utils/utils.py:21-57), executed by ONE fused CUDA pass
+(csrc/criterion.cu) instead of materialising three full-resolution logit tensors.
+
+Differences to the reference's surface, both deliberate:
+  * the values the reference reads from the global yacs config (LOSS.BALANCE_WEIGHTS, LOSS.SB_WEIGHTS,
+    MODEL.ALIGN_CORNERS, TRAIN.IGNORE_LABEL) are constructor arguments whose defaults are the values of
+    the shipped YAMLs;
+  * `FullModel.forward` returns `loss` / `loss_s` as 1-element tensors whose `.mean()` equals the
+    reference's `losses.mean()` / `loss_list[0].mean()` -- the only way every reference caller consumes
+    them (utils/function.py:44,56-59,118) -- rather than `[1,N,H,W]` / `[N,H,W]` maps.
+Gradients w.r.t. the three logit maps are produced by the same kernel family (`FusedCriterion.backward`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class OhemCrossEntropy(nn.Module):
+    """Parameter holder with the reference signature (utils/criterion.py:43-54)."""
+
+    def __init__(self, ignore_label=-1, thres=0.7, min_kept=100000, weight=None):
+        super().__init__()
+        self.thresh = thres
+        self.min_kept = max(1, min_kept)
+        self.ignore_label = ignore_label
+        # same registration as nn.CrossEntropyLoss(weight=...) -> state_dict key 'criterion.weight'
+        self.criterion = nn.CrossEntropyLoss(weight=weight, ignore_index=ignore_label, reduction='none')
+
+    def forward(self, *a, **k):
+        raise RuntimeError('pidnet_b200.OhemCrossEntropy is evaluated inside FullModel (fused criterion kernel)')
+
+
+class BondaryLoss(nn.Module):
+    def __init__(self, coeff_bce=20.0):
+        super().__init__()
+        self.coeff_bce = coeff_bce
+
+    def forward(self, *a, **k):
+        raise RuntimeError('pidnet_b200.BondaryLoss is evaluated inside FullModel (fused criterion kernel)')
+
+
+class FusedCriterion:
+    """loss / acc (and logit gradients) of FullModel.forward from the three low-res logit maps."""
+
+    def __init__(self, sem_loss: OhemCrossEntropy, bd_loss: BondaryLoss, balance_weights=(0.4, 1.0), sb_weights=1.0,
+                 bd_threshold=0.8):
+        if len(balance_weights) != 2:
+            raise ValueError('lengths of prediction and target are not identical!')   # criterion.py:99
+        self.cfg = _lib.CriterionCfg(ignore_label=sem_loss.ignore_label, ohem_keep=sem_loss.min_kept,
+                                     ohem_thres=sem_loss.thresh, bd_threshold=bd_threshold,
+                                     balance_weight_aux=balance_weights[0], balance_weight_main=balance_weights[1],
+                                     sb_weight=sb_weights, coeff_bce=bd_loss.coeff_bce)
+        self.sem_loss = sem_loss
+        self._ws = None
+
+    def __call__(self, outputs, labels, bd_gt, need_grads=False):
+        lib = _lib.load()
+        x_p, x_m, x_d = [o.contiguous().float() for o in outputs]
+        if not x_m.is_cuda:
+            raise RuntimeError('pidnet_b200 criterion runs on CUDA tensors only; there is no CPU fallback')
+        N, Cc, h, w = x_m.shape
+        labels = labels.contiguous().long()
+        bd_gt = bd_gt.contiguous().float()
+        H, W = labels.shape[1], labels.shape[2]
+        need = lib.pidnet_criterion_workspace_bytes(N, H, W)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != x_m.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x_m.device)
+        wt = self.sem_loss.criterion.weight
+        wt = wt.to(x_m.device, torch.float32).contiguous() if wt is not None else None
+        out = torch.empty(12, dtype=torch.float32, device=x_m.device)
+        grads = [torch.empty_like(t) for t in (x_p, x_m, x_d)] if need_grads else [None, None, None]
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        stream = torch.cuda.current_stream(x_m.device).cuda_stream
+        with torch.cuda.device(x_m.device):
+            _lib.check(lib.pidnet_criterion(C.c_void_p(stream), p(x_p), p(x_m), p(x_d), N, Cc, h, w, p(labels), p(bd_gt),
+                                            H, W, p(wt), C.byref(self.cfg), p(self._ws), self._ws.numel(), p(out),
+                                            p(grads[0]), p(grads[1]), p(grads[2])))
+        return out, grads
+
+
+def upsample_align_corners(x, size):
+    """F.interpolate(x, size, mode='bilinear', align_corners=True) (utils/utils.py:44-46) on fp32 NCHW CUDA."""
+    lib = _lib.load()
+    x = x.contiguous().float()
+    N, Cc, h, w = x.shape
+    out = torch.empty((N, Cc, size[0], size[1]), dtype=torch.float32, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pidnet_upsample_align_corners(C.c_void_p(stream), C.c_void_p(x.data_ptr()), N * Cc, h, w,
+                                                     C.c_void_p(out.data_ptr()), size[0], size[1]))
+    return out
+
+
+class FullModel(nn.Module):
+    """reference utils/utils.py:21-57: wraps model + losses; forward(inputs, labels, bd_gt) ->
+    (loss, [up(x_extra_p), up(x_)], acc, [loss_s, loss_b])."""
+
+    def __init__(self, model, sem_loss, bd_loss, balance_weights=(0.4, 1.0), sb_weights=1.0, return_outputs=True):
+        super().__init__()
+        self.model = model
+        self.sem_loss = sem_loss
+        self.bd_loss = bd_loss
+        self.return_outputs = return_outputs
+        self._crit = FusedCriterion(sem_loss, bd_loss, balance_weights, sb_weights)
+
+    def forward(self, inputs, labels, bd_gt, *args, **kwargs):
+        outputs = self.model(inputs, *args, **kwargs)
+        out, _ = self._crit(outputs, labels, bd_gt)
+        h, w = labels.size(1), labels.size(2)
+        ups = []
+        if self.return_outputs:
+            ups = [o if (o.size(2) == h and o.size(3) == w) else upsample_align_corners(o, (h, w)) for o in outputs[:-1]]
+        return out[0:1], ups, out[3], [out[1], out[2]]
+
+    def check_valid(self, out):
+        """The reference raises IndexError when an OHEM set has no valid pixel (criterion.py:73)."""
+        if float(out[8]) == 0 or float(out[9]) == 0:
+            raise IndexError('index -1 is out of bounds for dimension 0 with size 0')

@@ -1,0 +1,432 @@
+// Fused training/validation criterion of the PIDNet path (reference: FullModel.forward utils/utils.py:37-57,
+// OhemCrossEntropy utils/criterion.py:43-99, BondaryLoss :102-132; scalar restatement: SURVEY.md Appendix G).
+//
+// The reference upsamples the three low-res logit maps x8 (bilinear, align_corners=True) to label size,
+// materialising ~2 GB per step at batch 12, then runs softmax / gather / a full sort twice.  Here one pass
+// over the label pixels interpolates the 19+19+1 logits on the fly and emits, per pixel, only the target
+// probability p, the weighted CE and two validity bits (9 B/pixel); the OHEM k-th order statistic is an
+// exact 3-pass radix select on the bit pattern of p (skipped when #{p < thres} > k); a second pass forms
+// the selected-pixel means; the backward pass recomputes the softmaxes and scatters the gradients through
+// the transposed interpolation into shared-memory tiles before touching global memory.
+// Everything stays on the device (no host sync); sums are accumulated in fp64.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cfloat>
+#include "criterion.cuh"
+
+namespace pidnet {
+namespace {
+
+constexpr int kMaxC = 32;
+
+// accumulator slots (double)
+enum { A_CE_P = 0, A_ACC, A_BCE_POS, A_BCE_NEG, A_NPOS, A_NNEG, A_NV1, A_NV2, A_NLT1, A_NLT2, A_S1, A_S2, A_K1, A_K2,
+       A_COUNT };
+// select state (per OHEM set s): u32 [need, prefix, rank, thr_bits]
+struct SelState {
+  unsigned need[2], prefix[2], rank[2];
+  float thr[2];
+};
+
+struct Lerp {
+  int i0, i1;
+  float l;
+};
+// torch upsample_bilinear2d, align_corners=True: src = dst * (in-1)/(out-1)
+__device__ __forceinline__ Lerp lerp_ac(int dst, int in, int out) {
+  const float scale = out > 1 ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
+  const float src = scale * static_cast<float>(dst);
+  Lerp r;
+  r.i0 = static_cast<int>(src);
+  if (r.i0 > in - 1) r.i0 = in - 1;
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.l = src - static_cast<float>(r.i0);
+  return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct PixelCtx {
+  int n, y, x;
+  Lerp ly, lx;
+  float w00, w01, w10, w11;
+};
+__device__ __forceinline__ PixelCtx make_ctx(long pix, int H, int W, int h, int w) {
+  PixelCtx c;
+  c.x = static_cast<int>(pix % W);
+  const long t = pix / W;
+  c.y = static_cast<int>(t % H);
+  c.n = static_cast<int>(t / H);
+  c.ly = lerp_ac(c.y, h, H);
+  c.lx = lerp_ac(c.x, w, W);
+  c.w00 = (1.f - c.ly.l) * (1.f - c.lx.l);
+  c.w01 = (1.f - c.ly.l) * c.lx.l;
+  c.w10 = c.ly.l * (1.f - c.lx.l);
+  c.w11 = c.ly.l * c.lx.l;
+  return c;
+}
+// interpolated value of plane `p` ([h][w]) -- torch's evaluation order: rows first, then columns
+__device__ __forceinline__ float interp(const float* __restrict__ p, const PixelCtx& c, int w) {
+  const float a = __ldg(p + c.ly.i0 * w + c.lx.i0), b = __ldg(p + c.ly.i0 * w + c.lx.i1);
+  const float d = __ldg(p + c.ly.i1 * w + c.lx.i0), e = __ldg(p + c.ly.i1 * w + c.lx.i1);
+  return (1.f - c.ly.l) * ((1.f - c.lx.l) * a + c.lx.l * b) + c.ly.l * ((1.f - c.lx.l) * d + c.lx.l * e);
+}
+
+// --------------------------------------------------------------------------------------- pass 1
+__global__ void __launch_bounds__(256) crit_pixel_kernel(CritParams p) {
+  __shared__ double red[A_NLT2 + 1][8];
+  const long npix = static_cast<long>(p.N) * p.H * p.W;
+  const long pix = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  double acc[A_NLT2 + 1];
+#pragma unroll
+  for (int i = 0; i <= A_NLT2; ++i) acc[i] = 0.0;
+  if (pix < npix) {
+    const PixelCtx c = make_ctx(pix, p.H, p.W, p.h, p.w);
+    const long t64 = p.labels[pix];
+    const bool valid1 = t64 != p.ignore_label;
+    const int t = valid1 ? static_cast<int>(t64) : 0;
+    const size_t plane = static_cast<size_t>(p.h) * p.w;
+    const float* xm = p.x_m + static_cast<size_t>(c.n) * p.C * plane;
+    const float* xp = p.x_p + static_cast<size_t>(c.n) * p.C * plane;
+    // main head: softmax prob of the target, weighted CE, argmax
+    float vm[kMaxC];
+    float mx = -FLT_MAX;
+    int amax = 0;
+    for (int k = 0; k < p.C; ++k) {
+      vm[k] = interp(xm + k * plane, c, p.w);
+      if (vm[k] > mx) { mx = vm[k]; amax = k; }
+    }
+    float se = 0.f;
+    for (int k = 0; k < p.C; ++k) se += expf(vm[k] - mx);
+    const float lse = mx + logf(se);
+    const float wt = (valid1 && p.class_w) ? __ldg(p.class_w + t) : 1.f;
+    const float pm = expf(vm[t] - lse);
+    const float cem = wt * (lse - vm[t]);
+    acc[A_ACC] = (static_cast<long>(amax) == t64) ? 1.0 : 0.0;   // pixel_acc counts every pixel (label >= 0), utils.py:31
+    // aux head: plain weighted CE, reduction none (ignored pixels contribute 0)
+    if (valid1) {
+      float mp = -FLT_MAX, vt = 0.f, sp = 0.f;
+      float vp[kMaxC];
+      for (int k = 0; k < p.C; ++k) {
+        vp[k] = interp(xp + k * plane, c, p.w);
+        mp = fmaxf(mp, vp[k]);
+      }
+      for (int k = 0; k < p.C; ++k) sp += expf(vp[k] - mp);
+      vt = vp[t];
+      acc[A_CE_P] = wt * (mp + logf(sp) - vt);
+    }
+    // boundary head
+    const float xd = interp(p.x_d + static_cast<size_t>(c.n) * plane, c, p.w);
+    const float z = p.bd_gt[pix];
+    const float bce = fmaxf(xd, 0.f) - xd * z + log1pf(expf(-fabsf(xd)));
+    if (z == 1.f) { acc[A_BCE_POS] = bce; acc[A_NPOS] = 1.0; }
+    else if (z == 0.f) { acc[A_BCE_NEG] = bce; acc[A_NNEG] = 1.0; }
+    const float sg = 1.f / (1.f + expf(-xd));
+    const bool valid2 = valid1 && sg > p.bd_threshold;
+    if (valid1) { acc[A_NV1] = 1.0; if (pm < p.ohem_thres) acc[A_NLT1] = 1.0; }
+    if (valid2) { acc[A_NV2] = 1.0; if (pm < p.ohem_thres) acc[A_NLT2] = 1.0; }
+    p.ws_p[pix] = pm;
+    p.ws_ce[pix] = cem;
+    p.ws_flags[pix] = static_cast<unsigned char>((valid1 ? 1 : 0) | (valid2 ? 2 : 0));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i <= A_NLT2; ++i) {
+    const double v = warp_sum(acc[i]);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= A_NLT2) {
+    double v = 0.0;
+    for (int q = 0; q < 8; ++q) v += red[threadIdx.x][q];
+    if (v != 0.0) atomicAdd(p.accum + threadIdx.x, v);
+  }
+}
+
+// --------------------------------------------------------------------------------------- OHEM threshold
+__global__ void crit_select_init_kernel(CritParams p, SelState* st) {
+  if (threadIdx.x < 2) {
+    const int s = threadIdx.x;
+    const double n = p.accum[A_NV1 + s], nlt = p.accum[A_NLT1 + s];
+    const double k = fmin(static_cast<double>(p.min_kept), n - 1.0);   // index of min_value in the sorted list
+    st->thr[s] = p.ohem_thres;
+    st->prefix[s] = 0;
+    st->rank[s] = k > 0 ? static_cast<unsigned>(k) : 0u;
+    // p_sorted[k] < thres  <=>  at least k+1 valid pixels have p < thres  => threshold stays at thres
+    st->need[s] = (n >= 1.0 && !(nlt >= k + 1.0)) ? 1u : 0u;
+  }
+}
+// histogram of the next digit of p's bit pattern among candidates that match the prefix so far
+__global__ void __launch_bounds__(256) crit_hist_kernel(CritParams p, const SelState* st, unsigned* hist, int shift,
+                                                        int bits, int prefix_bits) {
+  if (!st->need[0] && !st->need[1]) return;
+  __shared__ unsigned sh[2][4096];
+  const int nb = 1 << bits;
+  for (int i = threadIdx.x; i < 2 * 4096; i += blockDim.x) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  const long npix = static_cast<long>(p.N) * p.H * p.W;
+  const unsigned need0 = st->need[0], need1 = st->need[1], pre0 = st->prefix[0], pre1 = st->prefix[1];
+  for (long pix = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
+       pix += static_cast<long>(gridDim.x) * blockDim.x) {
+    const unsigned f = p.ws_flags[pix];
+    if (!f) continue;
+    const unsigned u = __float_as_uint(p.ws_p[pix]);
+    const unsigned hi = prefix_bits ? (u >> (32 - prefix_bits)) : 0u;
+    const unsigned d = (u >> shift) & (nb - 1);
+    if (need0 && (f & 1) && hi == pre0) atomicAdd(&sh[0][d], 1u);
+    if (need1 && (f & 2) && hi == pre1) atomicAdd(&sh[1][d], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    if (sh[0][i]) atomicAdd(hist + i, sh[0][i]);
+    if (sh[1][i]) atomicAdd(hist + 4096 + i, sh[1][i]);
+  }
+}
+__global__ void crit_pick_kernel(SelState* st, unsigned* hist, int bits, int last, float thres) {
+  const int s = threadIdx.x;
+  if (s < 2 && st->need[s]) {
+    const int nb = 1 << bits;
+    unsigned r = st->rank[s], cum = 0;
+    int d = 0;
+    for (; d < nb; ++d) {
+      const unsigned hcnt = hist[s * 4096 + d];
+      if (cum + hcnt > r) break;
+      cum += hcnt;
+    }
+    if (d >= nb) d = nb - 1;
+    st->rank[s] = r - cum;
+    st->prefix[s] = (st->prefix[s] << bits) | static_cast<unsigned>(d);
+    if (last) st->thr[s] = fmaxf(__uint_as_float(st->prefix[s]), thres);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 4096; i += blockDim.x) hist[i] = 0;
+}
+
+// --------------------------------------------------------------------------------------- pass 2
+__global__ void __launch_bounds__(256) crit_sum_kernel(CritParams p, const SelState* st) {
+  __shared__ double red[4][8];
+  const long npix = static_cast<long>(p.N) * p.H * p.W;
+  const float thr1 = st->thr[0], thr2 = st->thr[1];
+  double a[4] = {0, 0, 0, 0};
+  for (long pix = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
+       pix += static_cast<long>(gridDim.x) * blockDim.x) {
+    const unsigned f = p.ws_flags[pix];
+    if (!f) continue;
+    const float pm = p.ws_p[pix], ce = p.ws_ce[pix];
+    if ((f & 1) && pm < thr1) { a[0] += ce; a[2] += 1.0; }
+    if ((f & 2) && pm < thr2) { a[1] += ce; a[3] += 1.0; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double v = warp_sum(a[i]);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int q = 0; q < 8; ++q) v += red[threadIdx.x][q];
+    if (v != 0.0) atomicAdd(p.accum + A_S1 + threadIdx.x, v);
+  }
+}
+
+__global__ void crit_final_kernel(CritParams p, const SelState* st) {
+  if (threadIdx.x != 0) return;
+  const double nhw = static_cast<double>(p.N) * p.H * p.W;
+  const double* a = p.accum;
+  const double aux = p.bw0 * a[A_CE_P] / nhw;
+  const double ohem1 = a[A_S1] / a[A_K1];   // 0/0 -> NaN like torch's mean of an empty selection
+  const double ohem2 = a[A_S2] / a[A_K2];
+  const double nb = a[A_NPOS] + a[A_NNEG];
+  const double bce = nb > 0 ? ((a[A_NNEG] / nb) * a[A_BCE_POS] + (a[A_NPOS] / nb) * a[A_BCE_NEG]) / nhw : 0.0;
+  const double loss_b = p.coeff_bce * bce;
+  const double loss_s = aux + p.bw1 * ohem1;
+  float* o = p.out;
+  o[0] = static_cast<float>(loss_s + loss_b + p.sb * ohem2);   // == losses.mean() of the reference
+  o[1] = static_cast<float>(loss_s);                           // == loss_list[0].mean()
+  o[2] = static_cast<float>(loss_b);
+  o[3] = static_cast<float>(a[A_ACC] / (nhw + 1e-10));
+  o[4] = static_cast<float>(ohem1);
+  o[5] = static_cast<float>(ohem2);
+  o[6] = st->thr[0];
+  o[7] = st->thr[1];
+  o[8] = static_cast<float>(a[A_NV1]);
+  o[9] = static_cast<float>(a[A_NV2]);
+  o[10] = static_cast<float>(a[A_K1]);
+  o[11] = static_cast<float>(a[A_K2]);
+}
+
+// --------------------------------------------------------------------------------------- backward
+// Block = 32 x 8 label pixels; gradients are first accumulated into a shared tile of the low-res maps
+// (<= 6 x 3 low-res pixels x (2C+1) channels for the x8 case), then flushed with one global atomic each.
+constexpr int kTileW = 32, kTileH = 8, kLW = 8, kLH = 4;
+__global__ void __launch_bounds__(256) crit_backward_kernel(CritParams p, const SelState* st) {
+  extern __shared__ float tile[];   // [(2C+1)][kLH][kLW]
+  const int CH = 2 * p.C + 1;
+  for (int i = threadIdx.x; i < CH * kLH * kLW; i += blockDim.x) tile[i] = 0.f;
+  __syncthreads();
+  const int tiles_x = (p.W + kTileW - 1) / kTileW, tiles_y = (p.H + kTileH - 1) / kTileH;
+  const int n = blockIdx.x / (tiles_x * tiles_y);
+  const int rem = blockIdx.x - n * tiles_x * tiles_y;
+  const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+  const int x = tx * kTileW + (threadIdx.x & 31), y = ty * kTileH + (threadIdx.x >> 5);
+  // low-res origin of this tile
+  const int ly0 = lerp_ac(ty * kTileH, p.h, p.H).i0, lx0 = lerp_ac(tx * kTileW, p.w, p.W).i0;
+  const double nhw = static_cast<double>(p.N) * p.H * p.W;
+  if (x < p.W && y < p.H) {
+    const long pix = (static_cast<long>(n) * p.H + y) * p.W + x;
+    const PixelCtx c = make_ctx(pix, p.H, p.W, p.h, p.w);
+    const unsigned f = p.ws_flags[pix];
+    const long t64 = p.labels[pix];
+    const int t = (f & 1) ? static_cast<int>(t64) : 0;
+    const size_t plane = static_cast<size_t>(p.h) * p.w;
+    const int a00 = (c.ly.i0 - ly0) * kLW + (c.lx.i0 - lx0), a01 = (c.ly.i0 - ly0) * kLW + (c.lx.i1 - lx0);
+    const int a10 = (c.ly.i1 - ly0) * kLW + (c.lx.i0 - lx0), a11 = (c.ly.i1 - ly0) * kLW + (c.lx.i1 - lx0);
+    const size_t lplane = static_cast<size_t>(p.h) * p.w;
+    auto scatter = [&](int ch, float g) {
+      if (p.direct_scatter) {
+        float* dst = ch < p.C ? p.g_p + (static_cast<size_t>(n) * p.C + ch) * lplane
+                              : (ch < 2 * p.C ? p.g_m + (static_cast<size_t>(n) * p.C + (ch - p.C)) * lplane
+                                              : p.g_d + static_cast<size_t>(n) * lplane);
+        atomicAdd(dst + c.ly.i0 * p.w + c.lx.i0, g * c.w00);
+        atomicAdd(dst + c.ly.i0 * p.w + c.lx.i1, g * c.w01);
+        atomicAdd(dst + c.ly.i1 * p.w + c.lx.i0, g * c.w10);
+        atomicAdd(dst + c.ly.i1 * p.w + c.lx.i1, g * c.w11);
+        return;
+      }
+      float* tb = tile + ch * kLH * kLW;
+      atomicAdd(tb + a00, g * c.w00);
+      atomicAdd(tb + a01, g * c.w01);
+      atomicAdd(tb + a10, g * c.w10);
+      atomicAdd(tb + a11, g * c.w11);
+    };
+    const float wt = ((f & 1) && p.class_w) ? __ldg(p.class_w + t) : 1.f;
+    if (f & 1) {
+      // main head: coefficient from both OHEM selections
+      const float pm = p.ws_p[pix];
+      float coef = 0.f;
+      if (pm < st->thr[0]) coef += static_cast<float>(p.bw1 / p.accum[A_K1]);
+      if ((f & 2) && pm < st->thr[1]) coef += static_cast<float>(p.sb / p.accum[A_K2]);
+      if (coef != 0.f) {
+        const float* xm = p.x_m + static_cast<size_t>(n) * p.C * plane;
+        float vm[kMaxC], mx = -FLT_MAX, se = 0.f;
+        for (int k = 0; k < p.C; ++k) { vm[k] = interp(xm + k * plane, c, p.w); mx = fmaxf(mx, vm[k]); }
+        for (int k = 0; k < p.C; ++k) { vm[k] = __expf(vm[k] - mx); se += vm[k]; }
+        const float inv = 1.f / se;
+        for (int k = 0; k < p.C; ++k) scatter(p.C + k, coef * wt * (vm[k] * inv - (k == t ? 1.f : 0.f)));
+      }
+      // aux head
+      {
+        const float* xp = p.x_p + static_cast<size_t>(n) * p.C * plane;
+        float vp[kMaxC], mx = -FLT_MAX, se = 0.f;
+        for (int k = 0; k < p.C; ++k) { vp[k] = interp(xp + k * plane, c, p.w); mx = fmaxf(mx, vp[k]); }
+        for (int k = 0; k < p.C; ++k) { vp[k] = __expf(vp[k] - mx); se += vp[k]; }
+        const float inv = 1.f / se, cf = static_cast<float>(p.bw0 / nhw) * wt;
+        for (int k = 0; k < p.C; ++k) scatter(k, cf * (vp[k] * inv - (k == t ? 1.f : 0.f)));
+      }
+    }
+    // boundary head
+    {
+      const float xd = interp(p.x_d + static_cast<size_t>(n) * plane, c, p.w);
+      const float z = p.bd_gt[pix];
+      const double nb = p.accum[A_NPOS] + p.accum[A_NNEG];
+      float om = 0.f;
+      if (z == 1.f) om = static_cast<float>(p.accum[A_NNEG] / nb);
+      else if (z == 0.f) om = static_cast<float>(p.accum[A_NPOS] / nb);
+      const float sg = 1.f / (1.f + __expf(-xd));
+      scatter(2 * p.C, static_cast<float>(p.coeff_bce / nhw) * om * (sg - z));
+    }
+  }
+  __syncthreads();
+  if (p.direct_scatter) return;
+  const size_t plane = static_cast<size_t>(p.h) * p.w;
+  for (int i = threadIdx.x; i < CH * kLH * kLW; i += blockDim.x) {
+    const float g = tile[i];
+    if (g == 0.f) continue;
+    const int ch = i / (kLH * kLW), r = i % (kLH * kLW);
+    const int ly = ly0 + r / kLW, lx = lx0 + r % kLW;
+    if (ly >= p.h || lx >= p.w) continue;
+    float* dst = ch < p.C ? p.g_p + (static_cast<size_t>(n) * p.C + ch) * plane
+                          : (ch < 2 * p.C ? p.g_m + (static_cast<size_t>(n) * p.C + (ch - p.C)) * plane
+                                          : p.g_d + static_cast<size_t>(n) * plane);
+    atomicAdd(dst + static_cast<size_t>(ly) * p.w + lx, g);
+  }
+}
+
+// --------------------------------------------------------------------------------------- x8 upsample (returned outputs)
+__global__ void __launch_bounds__(256) upsample_ac_kernel(const float* __restrict__ x, int NC, int h, int w,
+                                                          float* __restrict__ out, int H, int W) {
+  const long total = static_cast<long>(NC) * H * W;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int X = static_cast<int>(idx % W);
+  const long t = idx / W;
+  const int Y = static_cast<int>(t % H);
+  const long nc = t / H;
+  const Lerp ly = lerp_ac(Y, h, H), lx = lerp_ac(X, w, W);
+  const float* p = x + nc * h * w;
+  const float a = __ldg(p + ly.i0 * w + lx.i0), b = __ldg(p + ly.i0 * w + lx.i1);
+  const float d = __ldg(p + ly.i1 * w + lx.i0), e = __ldg(p + ly.i1 * w + lx.i1);
+  out[idx] = (1.f - ly.l) * ((1.f - lx.l) * a + lx.l * b) + ly.l * ((1.f - lx.l) * d + lx.l * e);
+}
+
+}  // namespace
+
+size_t criterion_workspace_bytes(int N, int H, int W) {
+  const size_t npix = static_cast<size_t>(N) * H * W;
+  return npix * 9 + 4096 /*alignment*/ + A_COUNT * sizeof(double) + sizeof(SelState) + 2 * 4096 * sizeof(unsigned) + 1024;
+}
+
+cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaStream_t st) {
+  if (p.C > kMaxC) return cudaErrorInvalidValue;
+  const size_t npix = static_cast<size_t>(p.N) * p.H * p.W;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t off = 0;
+  p.ws_p = reinterpret_cast<float*>(ws + off); off = al(off + npix * 4);
+  p.ws_ce = reinterpret_cast<float*>(ws + off); off = al(off + npix * 4);
+  p.ws_flags = ws + off; off = al(off + npix);
+  p.accum = reinterpret_cast<double*>(ws + off); off = al(off + A_COUNT * sizeof(double));
+  SelState* sel = reinterpret_cast<SelState*>(ws + off); off = al(off + sizeof(SelState));
+  unsigned* hist = reinterpret_cast<unsigned*>(ws + off);
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(p.accum, 0, A_COUNT * sizeof(double) + 512 + 2 * 4096 * sizeof(unsigned) + 256, st)) != cudaSuccess) return e;
+  const unsigned blocks = static_cast<unsigned>((npix + 255) / 256);
+  crit_pixel_kernel<<<blocks, 256, 0, st>>>(p);
+  crit_select_init_kernel<<<1, 32, 0, st>>>(p, sel);
+  const unsigned hb = blocks < 1184 ? blocks : 1184;
+  // exact k-th order statistic of p: radix select over the 32-bit pattern (12 + 12 + 8 bits)
+  crit_hist_kernel<<<hb, 256, 0, st>>>(p, sel, hist, 20, 12, 0);
+  crit_pick_kernel<<<1, 256, 0, st>>>(sel, hist, 12, 0, p.ohem_thres);
+  crit_hist_kernel<<<hb, 256, 0, st>>>(p, sel, hist, 8, 12, 12);
+  crit_pick_kernel<<<1, 256, 0, st>>>(sel, hist, 12, 0, p.ohem_thres);
+  crit_hist_kernel<<<hb, 256, 0, st>>>(p, sel, hist, 0, 8, 24);
+  crit_pick_kernel<<<1, 256, 0, st>>>(sel, hist, 8, 1, p.ohem_thres);
+  crit_sum_kernel<<<hb, 256, 0, st>>>(p, sel);
+  crit_final_kernel<<<1, 32, 0, st>>>(p, sel);
+  if (backward) {
+    const size_t lowres = static_cast<size_t>(p.N) * p.h * p.w;
+    if ((e = cudaMemsetAsync(p.g_p, 0, lowres * p.C * 4, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(p.g_m, 0, lowres * p.C * 4, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(p.g_d, 0, lowres * 4, st)) != cudaSuccess) return e;
+    const int tiles = ((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
+    // low-res footprint of a 32 x 8 label tile (+1 for the i1 neighbour, +1 for the fractional start)
+    auto span = [](int t, int in, int out) { return out > 1 ? (static_cast<long>(t - 1) * (in - 1)) / (out - 1) + 3 : 1; };
+    p.direct_scatter = (span(kTileW, p.w, p.W) > kLW || span(kTileH, p.h, p.H) > kLH) ? 1 : 0;
+    const size_t smem = static_cast<size_t>(2 * p.C + 1) * kLH * kLW * sizeof(float);
+    crit_backward_kernel<<<p.N * tiles, 256, smem, st>>>(p, sel);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t upsample_ac_launch(const float* x, int NC, int h, int w, float* out, int H, int W, cudaStream_t st) {
+  const long total = static_cast<long>(NC) * H * W;
+  upsample_ac_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, NC, h, w, out, H, W);
+  return cudaGetLastError();
+}
+
+}  // namespace pidnet

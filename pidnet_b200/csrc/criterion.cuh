@@ -1,0 +1,35 @@
+// Fused criterion (OhemCrossEntropy + BondaryLoss + FullModel composition) -- see criterion.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace pidnet {
+
+struct CritParams {
+  const float* x_p;   // x_extra_p logits, fp32 NCHW [N,C,h,w]
+  const float* x_m;   // x_ logits
+  const float* x_d;   // x_extra_d logits [N,1,h,w]
+  const int64_t* labels;  // [N,H,W], ignore_label marks ignored pixels
+  const float* bd_gt;     // [N,H,W] 0/1
+  const float* class_w;   // [C] or nullptr
+  int N, C, h, w, H, W;
+  long ignore_label;
+  float ohem_thres, bd_threshold;
+  long min_kept;
+  double bw0, bw1, sb, coeff_bce;
+  float* out;             // device float[12]
+  float *g_p, *g_m, *g_d; // low-res gradients of loss.mean() (backward only)
+  int direct_scatter;     // backward: 1 = global atomics (footprint does not fit the smem tile)
+  // workspace (filled by criterion_launch)
+  float* ws_p;
+  float* ws_ce;
+  unsigned char* ws_flags;
+  double* accum;
+};
+
+size_t criterion_workspace_bytes(int N, int H, int W);
+cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaStream_t st);
+cudaError_t upsample_ac_launch(const float* x, int NC, int h, int w, float* out, int H, int W, cudaStream_t st);
+
+}  // namespace pidnet

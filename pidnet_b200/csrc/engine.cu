@@ -18,6 +18,7 @@
 #include "../../include/pidnet_b200.h"
 #include "conv_tc.cuh"
 #include "kernels.cuh"
+#include "criterion.cuh"
 
 namespace pidnet {
 struct ProbeParams {
@@ -1423,6 +1424,37 @@ int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d,
   });
 }
 
+
+// ---- criterion (FullModel / OhemCrossEntropy / BondaryLoss), see criterion.cu
+size_t pidnet_criterion_workspace_bytes(int N, int H, int W) { return criterion_workspace_bytes(N, H, W); }
+
+int pidnet_criterion(void* stream, const float* x_p, const float* x_m, const float* x_d, int N, int C, int h, int w,
+                     const int64_t* labels, const float* bd_gt, int H, int W, const float* class_weights,
+                     const pidnet_criterion_cfg* cfg, void* workspace, size_t workspace_bytes, float* out12,
+                     float* grad_p, float* grad_m, float* grad_d) {
+  return guard([&] {
+    if (!x_p || !x_m || !x_d || !labels || !bd_gt || !cfg || !workspace || !out12) fail("null argument");
+    if (workspace_bytes < criterion_workspace_bytes(N, H, W)) fail("criterion workspace too small");
+    if (C < 1 || C > 32) fail("criterion supports 1..32 classes");
+    const bool bwd = grad_p || grad_m || grad_d;
+    if (bwd && !(grad_p && grad_m && grad_d)) fail("pass all three gradient buffers or none");
+    CritParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.x_p = x_p; p.x_m = x_m; p.x_d = x_d; p.labels = labels; p.bd_gt = bd_gt; p.class_w = class_weights;
+    p.N = N; p.C = C; p.h = h; p.w = w; p.H = H; p.W = W;
+    p.ignore_label = cfg->ignore_label;
+    p.ohem_thres = cfg->ohem_thres; p.bd_threshold = cfg->bd_threshold;
+    p.min_kept = cfg->ohem_keep < 1 ? 1 : cfg->ohem_keep;
+    p.bw0 = cfg->balance_weight_aux; p.bw1 = cfg->balance_weight_main; p.sb = cfg->sb_weight;
+    p.coeff_bce = cfg->coeff_bce;
+    p.out = out12; p.g_p = grad_p; p.g_m = grad_m; p.g_d = grad_d;
+    CK(criterion_launch(p, workspace, bwd, reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
+
+int pidnet_upsample_align_corners(void* stream, const float* x, int NC, int h, int w, float* out, int H, int W) {
+  return guard([&] { CK(upsample_ac_launch(x, NC, h, w, out, H, W, reinterpret_cast<cudaStream_t>(stream))); });
+}
 
 // hardware probe: cycles for `iters` x 4 back-to-back M128 x N x K16 SS MMAs on `blocks` CTAs (out: device int64[blocks])
 int pidnet_probe_mma_rate(void* stream, int N, int iters, int distinct, int blocks, long long* out) {
