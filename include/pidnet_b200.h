@@ -148,11 +148,32 @@ int pidnet_criterion(void* stream, const float* x_p, const float* x_m, const flo
 /* F.interpolate(x, size=(H,W), mode='bilinear', align_corners=True) on fp32 NCHW (utils/utils.py:44-46) */
 int pidnet_upsample_align_corners(void* stream, const float* x, int NC, int h, int w, float* out, int H, int W);
 
+/* ---- training step: replaces, for one per-GPU batch shard, the reference's
+ *   losses, _, acc, loss_list = model(images, labels, bd_gts); loss = losses.mean(); loss.backward()
+ * (utils/function.py:43-48 with FullModel utils/utils.py:37-57 in train mode): train-mode forward (BatchNorm batch
+ * statistics + running-stat update, momentum 0.1), fused criterion, and the backward pass of every op into the
+ * caller's fp32 gradient buffers.  Parameters are BOUND, not copied: `dev_param` / `dev_grad` point at the storage of
+ * the torch parameters (and of the running_mean / running_var buffers, dev_grad = NULL), keys are the reference
+ * state_dict keys.  Gradients of different ranks are summed by the caller (NCCL all-reduce of the flat buffer).
+ * S/M topologies (m == 2), augment = 1. */
+typedef struct pidnet_trainer pidnet_trainer;
+int pidnet_train_create(const pidnet_cfg* cfg, pidnet_trainer** out);
+int pidnet_train_destroy(pidnet_trainer* h);
+int pidnet_train_bind(pidnet_trainer* h, const char* key, float* dev_param, float* dev_grad, const int64_t* shape, int ndim);
+int pidnet_train_plan(pidnet_trainer* h, int N, int H, int W, size_t* arena_bytes);
+/* out12: device fp32[12] as in pidnet_criterion; out_main/out_p/out_d: optional device copies of the low-res logits */
+int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x_nchw, const int64_t* labels, const float* bd_gt,
+                      const float* class_weights, const pidnet_criterion_cfg* cfg, int backward, float* out12,
+                      float* out_main, float* out_p, float* out_d);
+int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd);
+int pidnet_train_debug_tensor(pidnet_trainer* h, const char* name, int grad, float* host_out, int64_t* shape4);
+
 /* Hardware probe used by tools/probe_halo.py (documents how tcgen05 reads shifted windows of a
  * TMA-written halo patch; not on the product path). */
 int pidnet_probe_halo(void* stream, const void* x_18x10x64_bf16, const void* w_64x64_bf16, int r, int s, int mode,
                       float* out_128x64);
 
+int pidnet_probe_mn(void* stream, const void* a_64x128_bf16, const void* b_64x64_bf16, int lbo, int sbo, float* out_128x64);
 int pidnet_probe_mma_rate(void* stream, int N, int iters, int distinct, int blocks, long long* out_cycles_dev);
 
 #ifdef __cplusplus

@@ -110,6 +110,8 @@ class FullModel(nn.Module):
         self._crit = FusedCriterion(sem_loss, bd_loss, balance_weights, sb_weights)
 
     def forward(self, inputs, labels, bd_gt, *args, **kwargs):
+        if self.training and torch.is_grad_enabled():
+            return self._train_forward(inputs, labels, bd_gt)
         outputs = self.model(inputs, *args, **kwargs)
         out, _ = self._crit(outputs, labels, bd_gt)
         h, w = labels.size(1), labels.size(2)
@@ -117,6 +119,21 @@ class FullModel(nn.Module):
         if self.return_outputs:
             ups = [o if (o.size(2) == h and o.size(3) == w) else upsample_align_corners(o, (h, w)) for o in outputs[:-1]]
         return out[0:1], ups, out[3], [out[1], out[2]]
+
+    def _train_forward(self, inputs, labels, bd_gt):
+        """Train mode: one engine call does forward (BN batch statistics), criterion and backward; the returned
+        loss is attached to autograd so `loss.mean().backward()` delivers the parameter gradients."""
+        from .train import EngineTrainer, _TrainStepFn
+        if getattr(self, '_trainer', None) is None:
+            self._trainer = EngineTrainer(self.model)
+        names = [k for k, _ in self.model.named_parameters()]
+        params = [p for _, p in self.model.named_parameters()]
+        wt = self.sem_loss.criterion.weight
+        res = _TrainStepFn.apply(self._trainer, inputs, labels, bd_gt, wt, self._crit.cfg, names, *params)
+        loss, out12, x_p, x_m, x_d = res
+        h, w = labels.size(1), labels.size(2)
+        ups = [upsample_align_corners(o, (h, w)) for o in (x_p, x_m)] if self.return_outputs else []
+        return loss, ups, out12[3], [out12[1], out12[2]]
 
     def check_valid(self, out):
         """The reference raises IndexError when an OHEM set has no valid pixel (criterion.py:73)."""

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <map>
 #include <stdexcept>
@@ -19,6 +20,7 @@
 #include "conv_tc.cuh"
 #include "kernels.cuh"
 #include "criterion.cuh"
+#include "train_kernels.cuh"
 
 namespace pidnet {
 struct ProbeParams {
@@ -28,6 +30,12 @@ struct ProbeParams {
 };
 cudaError_t halo_probe_launch(const ProbeParams& p, cudaStream_t st);
 cudaError_t mma_rate_launch(int N, int iters, int distinct, int blocks, long long* out, cudaStream_t st);
+struct MnProbeParams {
+  CUtensorMap tmA, tmB;
+  int lbo_a, sbo, variant;
+  float* out;
+};
+cudaError_t mn_probe_launch(const MnProbeParams& p, cudaStream_t st);
 }  // namespace pidnet
 
 namespace pidnet {
@@ -122,7 +130,11 @@ struct T {  // NHWC bf16 view
   int N = 0, H = 0, W = 0, C = 0;
   long ps = 0;    // pixel stride (elements)
   int prod = -1;  // index of the producing op (-1: external)
+  long sH = 0, sN = 0;  // explicit row / image strides in elements (0: dense, derived from W and H); sW == ps
   View view() const { return View{ptr, N, H, W, C, ps}; }
+  long row_stride() const { return sH ? sH : static_cast<long>(W) * ps; }
+  long img_stride() const { return sN ? sN : static_cast<long>(H) * W * ps; }
+  bool dense() const { return sH == 0 && sN == 0; }
 };
 
 struct RunArgs {
@@ -141,10 +153,20 @@ struct Op {
   std::function<cudaError_t(cudaStream_t, const RunArgs&)> fn;
 };
 
+struct TapSpec {
+  int dh, dw;  // input offset (in pixels of `in`) relative to the output pixel
+  int r, s;    // which tap of the weight tensor multiplies it
+};
 struct ConvSrcSpec {
   T in;
-  std::vector<float> w;  // [Cout][Cin][k][k] fp32, BN-folded
+  std::vector<float> w;  // [Cout][Cin][k][k] fp32, BN-folded (eval); empty when dev_w is set
   int k = 1, stride = 1;
+  // training: weights live on the device as fp32 [Co][Cin_total][k][k] and are re-packed every step
+  const float* dev_w = nullptr;
+  int dev_cin_total = 0, dev_ci_off = 0;
+  int dev_cin = 0;               // valid channels of `in` for packing (0: in.C); e.g. 3 of the 8-channel padded image
+  bool dgrad = false;            // pack transposed (rows = ci, channels = co): this conv computes an input gradient
+  std::vector<TapSpec> xtaps;    // explicit tap list (stride-2 dgrad parities); stride must be 1
 };
 
 // ----------------------------------------------------------------------------------------- builder
@@ -161,8 +183,11 @@ struct Builder {
   int lane = 0;
   double flops = 0;
   std::map<std::string, T> named;
+  const float* dev_bias_override = nullptr;   // training: conv bias read straight from the fp32 parameter
+  std::vector<PackJob> pack_jobs;   // training: device-side weight packing, run at the start of every step
 
   void reset(bool dry_) {
+    pack_jobs.clear();
     dry = dry_;
     act_cur = wt_cur = 0;
     ops.clear();
@@ -243,16 +268,19 @@ struct Builder {
     if (srcs.empty() || srcs.size() > 2) fail(name + ": 1 or 2 sources supported");
     const T& in0 = srcs[0].in;
     const int N = in0.N;
-    const int Ho = cdiv(in0.H, srcs[0].stride), Wo = cdiv(in0.W, srcs[0].stride);
-    bool flat = out_slot < 0;
+    const bool xt = !srcs[0].xtaps.empty();
+    if (xt && (!out_view || srcs.size() != 1)) fail(name + ": explicit taps need one source and an output view");
+    const int Ho = xt ? out_view->H : cdiv(in0.H, srcs[0].stride), Wo = xt ? out_view->W : cdiv(in0.W, srcs[0].stride);
+    bool flat = out_slot < 0 && !xt && (!out_view || out_view->dense()) && (!res || res->dense());
     int BK = 32;
     for (const auto& s : srcs) {
       if (s.k != 1 && s.k != 3) fail(name + ": kernel size must be 1 or 3");
       if (s.stride != 1 && s.stride != 2) fail(name + ": stride must be 1 or 2");
-      if (cdiv(s.in.H, s.stride) != Ho || cdiv(s.in.W, s.stride) != Wo || s.in.N != N)
+      if (!xt && (cdiv(s.in.H, s.stride) != Ho || cdiv(s.in.W, s.stride) != Wo || s.in.N != N))
         fail(name + ": source geometry mismatch");
-      if (static_cast<long>(s.w.size()) != static_cast<long>(Cout) * s.in.C * s.k * s.k)
+      if (!s.dev_w && static_cast<long>(s.w.size()) != static_cast<long>(Cout) * s.in.C * s.k * s.k)
         fail(name + ": weight size mismatch");
+      if (!s.in.dense()) fail(name + ": conv sources must be dense NHWC views");
       if (s.k != 1 || s.stride != 1) flat = false;
       if (s.in.C > 32) BK = 64;
       flops += 2.0 * N * Ho * Wo * Cout * s.in.C * s.k * s.k;
@@ -285,7 +313,9 @@ struct Builder {
         ws_chunks += cdiv(sp.in.C, BK);
         if (sp.k != 1 || sp.stride != 1) all1x1 = false;
       }
-      const bool m0 = srcs.size() == 1 && srcs[0].k == 3 && srcs[0].stride == 1;
+      const bool strided_io = xt || (out_view && !out_view->dense()) || (res && !res->dense());
+      const bool m0 = !strided_io && srcs.size() == 1 && srcs[0].k == 3 && srcs[0].stride == 1;
+      if (strided_io) all1x1 = false;
       if (m0 || all1x1) {
         ws_mode = m0 ? 0 : 1;
         for (int bn = 128; bn >= 32 && !ws; bn >>= 1) {
@@ -329,13 +359,25 @@ struct Builder {
       cs.chunks = cdiv(in.C, BK);
       cs.ntaps = 0;
       int map_of[2][2] = {{-1, -1}, {-1, -1}};
-      for (int r = 0; r < s.k; ++r)
-        for (int q = 0; q < s.k; ++q) {
-          int hp = 0, wp = 0, dh = 0, dw = 0;
-          if (s.k == 3) {
-            if (s.stride == 1) { dh = r - 1; dw = q - 1; }
-            else { hp = (r == 1) ? 0 : 1; dh = (r == 0) ? -1 : 0; wp = (q == 1) ? 0 : 1; dw = (q == 0) ? -1 : 0; }
+      struct Cand { int hp, wp, dh, dw, r, q; };
+      std::vector<Cand> cands;
+      if (!s.xtaps.empty()) {
+        if (s.stride != 1) fail(name + ": explicit taps require stride 1");
+        for (const TapSpec& t : s.xtaps) cands.push_back(Cand{0, 0, t.dh, t.dw, t.r, t.s});
+      } else {
+        for (int r = 0; r < s.k; ++r)
+          for (int q = 0; q < s.k; ++q) {
+            Cand c{0, 0, 0, 0, r, q};
+            if (s.k == 3) {
+              if (s.stride == 1) { c.dh = r - 1; c.dw = q - 1; }
+              else { c.hp = (r == 1) ? 0 : 1; c.dh = (r == 0) ? -1 : 0; c.wp = (q == 1) ? 0 : 1; c.dw = (q == 0) ? -1 : 0; }
+            }
+            cands.push_back(c);
           }
+      }
+      for (const Cand& cd : cands) {
+        {
+          const int hp = cd.hp, wp = cd.wp, dh = cd.dh, dw = cd.dw, r = cd.r, q = cd.q;
           // geometry of the (sub-)lattice this tap reads
           const int st = s.stride;
           const int LW = (in.W - wp + st - 1) / st, LH = (in.H - hp + st - 1) / st;
@@ -373,6 +415,7 @@ struct Builder {
                                 (static_cast<uint32_t>(dw + 8) << 16);
           kept[si].push_back(TapW{r, q});
         }
+      }
       if (cs.ntaps == 0) fail(name + ": source has no taps");
     }
 
@@ -386,6 +429,10 @@ struct Builder {
       for (size_t si = 0; si < srcs.size(); ++si) {
         const ConvSrcSpec& s = srcs[si];
         const int Cin = s.in.C, kk = s.k * s.k, chunks = p.src[si].chunks;
+        if (s.dev_w) {   // packed on the device every step (see pack_jobs below)
+          kofs += static_cast<long>(kept[si].size()) * chunks * BK;
+          continue;
+        }
         for (size_t ti = 0; ti < kept[si].size(); ++ti) {
           const int r = kept[si][ti].r, q = kept[si][ti].s;
           for (int co = 0; co < Cout; ++co) {
@@ -399,9 +446,36 @@ struct Builder {
     }
     const bf16* wdev =
         reinterpret_cast<const bf16*>(alloc_wt(wpk.data(), static_cast<size_t>(Cout_pad) * Ktot * 2));
+    {
+      long kofs = 0;
+      for (size_t si = 0; si < srcs.size(); ++si) {
+        const ConvSrcSpec& s = srcs[si];
+        const int chunks = p.src[si].chunks;
+        if (s.dev_w) {
+          PackJob j;
+          std::memset(&j, 0, sizeof(j));
+          j.src = s.dev_w;
+          j.dst = const_cast<bf16*>(wdev);
+          j.Ktot = Ktot; j.kofs = kofs; j.rows_pad = Cout_pad;
+          j.k = s.k; j.BK = BK; j.chunks = chunks; j.ntaps = static_cast<int>(kept[si].size());
+          j.dgrad = s.dgrad ? 1 : 0;
+          j.Cin_total = s.dev_cin_total; j.ci_off = s.dev_ci_off;
+          const int src_ch = s.dev_cin ? s.dev_cin : s.in.C;   // valid channels of the source tensor
+          j.Cout = s.dgrad ? src_ch : Cout;   // ORIGINAL conv's Cout / Cin (dgrad swaps the GEMM roles)
+          j.Cin = s.dgrad ? Cout : src_ch;
+          for (size_t ti = 0; ti < kept[si].size(); ++ti) {
+            int r = kept[si][ti].r, q = kept[si][ti].s;
+            if (s.dgrad && s.xtaps.empty()) { r = s.k - 1 - r; q = s.k - 1 - q; }   // mirrored filter
+            j.taps[ti] = static_cast<unsigned char>((r << 4) | q);
+          }
+          if (!dry) pack_jobs.push_back(j);
+        }
+        kofs += static_cast<long>(kept[si].size()) * chunks * BK;
+      }
+    }
     std::vector<float> bpad(Cout_pad, 0.f);
     for (int c = 0; c < Cout && c < static_cast<int>(bias.size()); ++c) bpad[c] = bias[c];
-    const float* bdev = upload_f32(bpad);
+    const float* bdev = dev_bias_override ? dev_bias_override : upload_f32(bpad);
     p.bias = bdev;
 
     if (!dry) {
@@ -420,8 +494,8 @@ struct Builder {
         } else {
           dims4[1] = Wo; dims4[2] = Ho; dims4[3] = N;
           str[0] = static_cast<uint64_t>(t.ps) * 2;
-          str[1] = static_cast<uint64_t>(Wo) * t.ps * 2;
-          str[2] = static_cast<uint64_t>(Ho) * Wo * t.ps * 2;
+          str[1] = static_cast<uint64_t>(t.row_stride()) * 2;
+          str[2] = static_cast<uint64_t>(t.img_stride()) * 2;
         }
         uint32_t box4[4] = {static_cast<uint32_t>(SC), static_cast<uint32_t>(TW), static_cast<uint32_t>(TH),
                             static_cast<uint32_t>(TN)};
@@ -489,13 +563,13 @@ struct Builder {
     R.N = gN; R.Ho = gH; R.Wo = gW; R.Cout = Cout; R.relu = p.relu; R.out_mode = p.out_mode;
     if (res) {
       R.res.ptr = res->ptr;
-      R.res.sW = res->ps; R.res.sH = flat ? 0 : static_cast<long>(Wo) * res->ps;
-      R.res.sN = flat ? 0 : static_cast<long>(Ho) * Wo * res->ps;
+      R.res.sW = res->ps; R.res.sH = flat ? 0 : res->row_stride();
+      R.res.sN = flat ? 0 : res->img_stride();
     }
     if (out_slot < 0) {
       R.out = out.ptr;
-      R.o_sW = out.ps; R.o_sH = flat ? 0 : static_cast<long>(Wo) * out.ps;
-      R.o_sN = flat ? 0 : static_cast<long>(Ho) * Wo * out.ps;
+      R.o_sW = out.ps; R.o_sH = flat ? 0 : out.row_stride();
+      R.o_sN = flat ? 0 : out.img_stride();
     }
 
     std::vector<const T*> ins;
@@ -1172,6 +1246,8 @@ static T ext_tensor(const void* ptr, int N, int H, int W, int C) {
   return t;
 }
 
+#include "train.inc"
+
 }  // namespace pidnet
 
 using namespace pidnet;
@@ -1425,6 +1501,85 @@ int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d,
 }
 
 
+// ---- training (train.inc)
+struct pidnet_trainer_ { TrainNet t; };
+
+int pidnet_train_create(const pidnet_cfg* cfg, pidnet_trainer** out) {
+  return guard([&] {
+    if (!cfg || !out) fail("null argument");
+    pidnet_trainer_* h = new pidnet_trainer_();
+    h->t.cfg = *cfg;
+    *out = reinterpret_cast<pidnet_trainer*>(h);
+  });
+}
+int pidnet_train_destroy(pidnet_trainer* h) {
+  return guard([&] { delete reinterpret_cast<pidnet_trainer_*>(h); });
+}
+int pidnet_train_bind(pidnet_trainer* h, const char* key, float* dev_param, float* dev_grad, const int64_t* shape, int ndim) {
+  return guard([&] {
+    if (!h || !key || !dev_param) fail("null argument");
+    TrainParam p;
+    p.w = dev_param; p.g = dev_grad;
+    for (int i = 0; i < ndim; ++i) p.shape.push_back(shape[i]);
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    t.P[key] = p;
+    t.planned = false;
+  });
+}
+int pidnet_train_plan(pidnet_trainer* h, int N, int H, int W, size_t* arena_bytes) {
+  return guard([&] {
+    if (!h) fail("null handle");
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    t.plan(N, H, W);
+    if (arena_bytes) *arena_bytes = t.b.act_cur + t.b.wt_cur;
+  });
+}
+int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x, const int64_t* labels, const float* bd_gt,
+                      const float* class_weights, const pidnet_criterion_cfg* cfg, int backward, float* out12,
+                      float* out_main, float* out_p, float* out_d) {
+  return guard([&] {
+    if (!h || !x || !labels || !bd_gt || !cfg) fail("null argument");
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    t.step(st, x, labels, bd_gt, class_weights, *cfg, backward != 0);
+    const size_t lp = static_cast<size_t>(t.N) * t.h8 * t.w8;
+    if (out12) CK(cudaMemcpyAsync(out12, t.out12, 12 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out_main) CK(cudaMemcpyAsync(out_main, t.logits[0], lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
+    if (out_p) CK(cudaMemcpyAsync(out_p, t.logits[1], lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
+    if (out_d) CK(cudaMemcpyAsync(out_d, t.logits[2], lp * 4, cudaMemcpyDeviceToDevice, st));
+  });
+}
+static void dump_nhwc(const T& t, float* host_out, int64_t* shape4) {
+  if (shape4) { shape4[0] = t.N; shape4[1] = t.C; shape4[2] = t.H; shape4[3] = t.W; }
+  if (!host_out) return;
+  CK(cudaDeviceSynchronize());
+  const size_t npix = static_cast<size_t>(t.N) * t.H * t.W;
+  std::vector<uint16_t> tmp(npix * t.ps);
+  CK(cudaMemcpy(tmp.data(), t.ptr, (npix - 1) * t.ps * 2 + static_cast<size_t>(t.C) * 2, cudaMemcpyDeviceToHost));
+  for (int n = 0; n < t.N; ++n)
+    for (int c = 0; c < t.C; ++c)
+      for (int y = 0; y < t.H; ++y)
+        for (int x = 0; x < t.W; ++x)
+          host_out[((static_cast<size_t>(n) * t.C + c) * t.H + y) * t.W + x] =
+              bf2f(tmp[((static_cast<size_t>(n) * t.H + y) * t.W + x) * t.ps + c]);
+}
+/* debug: named stage tensor (grad != 0: its gradient) of the last training step as fp32 NCHW on the host */
+int pidnet_train_debug_tensor(pidnet_trainer* h, const char* name, int grad, float* host_out, int64_t* shape4) {
+  return guard([&] {
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    auto it = t.named.find(name);
+    if (it == t.named.end()) fail(std::string("no training tensor named '") + name + "'");
+    dump_nhwc(grad ? t.tt[it->second].g : t.tt[it->second].v, host_out, shape4);
+  });
+}
+int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd) {
+  return guard([&] {
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    if (fwd) *fwd = static_cast<int>(t.b.ops.size() + t.b.pack_jobs.size());
+    if (bwd) *bwd = static_cast<int>(t.bops.size());
+  });
+}
+
 // ---- criterion (FullModel / OhemCrossEntropy / BondaryLoss), see criterion.cu
 size_t pidnet_criterion_workspace_bytes(int N, int H, int W) { return criterion_workspace_bytes(N, H, W); }
 
@@ -1454,6 +1609,22 @@ int pidnet_criterion(void* stream, const float* x_p, const float* x_m, const flo
 
 int pidnet_upsample_align_corners(void* stream, const float* x, int NC, int h, int w, float* out, int H, int W) {
   return guard([&] { CK(upsample_ac_launch(x, NC, h, w, out, H, W, reinterpret_cast<cudaStream_t>(stream))); });
+}
+
+// hardware probe: MN-major operands. a: [64][128] bf16, b: [64][64] bf16 (device), out [128][64] fp32
+int pidnet_probe_mn(void* stream, const void* a, const void* b, int lbo, int sbo, float* out) {
+  return guard([&] {
+    MnProbeParams p;
+    std::memset(&p, 0, sizeof(p));
+    uint64_t da[2] = {128, 64}, sa[1] = {256};
+    uint64_t db[2] = {64, 64}, sb[1] = {128};
+    uint32_t box[2] = {64, 64};
+    p.tmA = encode_map(a, 2, da, sa, box, 128);
+    p.tmB = encode_map(b, 2, db, sb, box, 128);
+    p.lbo_a = lbo; p.sbo = sbo; p.out = out;
+    CK(mn_probe_launch(p, reinterpret_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  });
 }
 
 // hardware probe: cycles for `iters` x 4 back-to-back M128 x N x K16 SS MMAs on `blocks` CTAs (out: device int64[blocks])

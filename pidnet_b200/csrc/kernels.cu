@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View ou
 }
 
 // --------------------------------------------------------------------------- upadd / affine
-__global__ void __launch_bounds__(256) upadd_kernel(View a, View b, View out, const float* __restrict__ s,
+__global__ void __launch_bounds__(256) upadd_kernel(View a, View b, View r, View out, const float* __restrict__ s,
                                                     const float* __restrict__ t, int relu) {
   const int groups = out.C >> 3;
   const long total = static_cast<long>(out.N) * out.H * out.W * groups;
@@ -201,6 +201,11 @@ __global__ void __launch_bounds__(256) upadd_kernel(View a, View b, View out, co
   if (s) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v.v[e] = v.v[e] * __ldg(s + cg * 8 + e) + __ldg(t + cg * 8 + e);
+  }
+  if (r.ptr) {   // residual added after the affine map (BatchNorm -> + identity -> ReLU)
+    const F8 rv = ld8(r.ptr + pix * r.ps + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v.v[e] += rv.v[e];
   }
   if (relu) {
 #pragma unroll
@@ -391,8 +396,12 @@ cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t s
 }
 
 cudaError_t upadd_launch(View a, View b, View out, const float* s, const float* t, int relu, cudaStream_t st) {
+  return upadd_res_launch(a, b, View{nullptr, 0, 0, 0, 0, 0}, out, s, t, relu, st);
+}
+
+cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, const float* t, int relu, cudaStream_t st) {
   const long total = static_cast<long>(out.N) * out.H * out.W * (out.C / 8);
-  upadd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, b, out, s, t, relu);
+  upadd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, b, r, out, s, t, relu);
   return cudaGetLastError();
 }
 

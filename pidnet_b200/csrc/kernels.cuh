@@ -41,6 +41,8 @@ cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t s
 
 // ---- generic elementwise: out = act(s * (a + U(b)) + t)   (a, b, s/t optional; U = bilinear, align_corners=False)
 cudaError_t upadd_launch(View a, View b, View out, const float* s, const float* t, int relu, cudaStream_t st);
+// same with a residual added AFTER the affine map: out = act(s * (a + U(b)) + t + r)
+cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, const float* t, int relu, cudaStream_t st);
 
 // ---- average pool (count_include_pad) + affine + ReLU; k == 0 means global average pool
 cudaError_t pool_affine_launch(View x, View out, int k, int stride, int pad, const float* s, const float* t, int relu,

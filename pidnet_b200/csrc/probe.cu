@@ -122,6 +122,75 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int iters, int distinct, 
   if (warp == 1) tmem_dealloc<(N < 32 ? 32 : N)>(tmem);
 }
 
+// ---- MN-major operand probe (wgrad shape): D[co, ci] = sum_p A[p][co] * B[p][ci], both operands loaded by TMA
+// from row-major [pixels][channels] matrices (channel-contiguous == "MN-major"), SWIZZLE_128B.
+struct MnProbeParams {
+  CUtensorMap tmA;  // [64 pixels][128 co] bf16, box {64 ch, 64 px}
+  CUtensorMap tmB;  // [64 pixels][64 ci]  bf16, box {64 ch, 64 px}
+  int lbo_a, sbo, variant;
+  float* out;       // [128][64]
+};
+__global__ void __launch_bounds__(128) mn_probe_kernel(const __grid_constant__ MnProbeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a0 = base, a1 = base + 8192, b0 = base + 16384;   // three 64 x 128 B tiles
+  const uint32_t bar = base + 24576, bar2 = bar + 8, slot = bar + 16;
+  volatile uint32_t* slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 24576 + 16);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc<64>(slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_gen;
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar, 3 * 8192);
+      tma_load_2d(a0, &p.tmA, bar, 0, 0);
+      tma_load_2d(a1, &p.tmA, bar, 64, 0);
+      tma_load_2d(b0, &p.tmB, bar, 0, 0);
+      mbar_wait(bar, 0);
+      tc_fence_after();
+      // idesc: f32 accum, bf16 x bf16, A and B MN-major (bits 15, 16)
+      const uint32_t idesc = make_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+      auto mk = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) {
+        uint64_t d = 0;
+        d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+        d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+        d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+        d |= 1ull << 46;
+        d |= 2ull << 61;   // SWIZZLE_128B
+        return d;
+      };
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t koff = k * 2048;   // 16 pixel rows x 128 B
+        umma_bf16(tmem, mk(a0 + koff, p.lbo_a, p.sbo), mk(b0 + koff, p.lbo_a, p.sbo), idesc, k != 0);
+      }
+      umma_commit(bar2);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar2, 0);
+  tc_fence_after();
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int g = 0; g < 2; ++g) {
+    uint32_t v[32];
+    tmem_ld32(t_row + g * 32, v);
+    tmem_ld_wait();
+    for (int e = 0; e < 32; ++e) p.out[threadIdx.x * 64 + g * 32 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<64>(tmem);
+}
+cudaError_t mn_probe_launch(const MnProbeParams& p, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(mn_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+  if (e != cudaSuccess) return e;
+  mn_probe_kernel<<<1, 128, 32768, st>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t mma_rate_launch(int N, int iters, int distinct, int blocks, long long* out, cudaStream_t st) {
   const int smem = 9 * 16384 + 9 * N * 128 + 64 + 1024;
 #define PIDNET_RATE(NN)                                                                                       \

@@ -1,0 +1,603 @@
+// Training-mode kernels of the PIDNet path: BatchNorm with batch statistics (forward statistics, finalize +
+// running-stat update, backward reduce/apply), device-side weight packing (fp32 master weights -> the bf16
+// K-major layouts of the conv kernels, forward and dgrad orientation), layout converters and the transposes
+// of the bilinear-upsample / average-pool operators.  Reference semantics: nn.BatchNorm2d(momentum=0.1,
+// eps=1e-5) in train mode (models/model_utils.py:8-9), SURVEY.md Appendix H.
+#include "train_kernels.cuh"
+
+namespace pidnet {
+namespace {
+
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ld8(const bf16* p) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  F8 r;
+  r.v[0] = __uint_as_float(u.x << 16); r.v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  r.v[2] = __uint_as_float(u.y << 16); r.v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  r.v[4] = __uint_as_float(u.z << 16); r.v[5] = __uint_as_float(u.z & 0xFFFF0000u);
+  r.v[6] = __uint_as_float(u.w << 16); r.v[7] = __uint_as_float(u.w & 0xFFFF0000u);
+  return r;
+}
+__device__ __forceinline__ uint32_t pk(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st8(bf16* p, const F8& f) {
+  uint4 o;
+  o.x = pk(f.v[0], f.v[1]); o.y = pk(f.v[2], f.v[3]); o.z = pk(f.v[4], f.v[5]); o.w = pk(f.v[6], f.v[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+inline unsigned blocks_for(long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+// ----------------------------------------------------------------------------- per-channel reductions
+// grid.x = pixel chunks, block = 256 threads = (C/8 channel groups) x (pixel lanes); each thread strides over
+// pixels of its chunk; fp32 partials per block, fp64 atomics across blocks.
+// MODE 0: sum x, sum x^2 (forward statistics)
+// MODE 1: sum dz', sum dz' * xhat with dz' = dz * [z > 0 if relu]   (BN backward)
+template <int MODE>
+__global__ void __launch_bounds__(256) chan_reduce_kernel(View x, View dz, View z, const float* __restrict__ mean,
+                                                          const float* __restrict__ invstd, int relu, long pix_per_block,
+                                                          double* __restrict__ out /*[2][C]*/) {
+  extern __shared__ float red[];  // [lanes][groups*16]
+  const int groups = x.C >> 3;
+  const int lanes = blockDim.x / groups;
+  const int cg = threadIdx.x % groups, ln = threadIdx.x / groups;
+  const long npix = static_cast<long>(x.N) * x.H * x.W;
+  const long p0 = static_cast<long>(blockIdx.x) * pix_per_block;
+  const long p1 = min(p0 + pix_per_block, npix);
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+  float mu[8], is[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = invstd[cg * 8 + e]; }
+  }
+  if (ln < lanes) {
+    for (long p = p0 + ln; p < p1; p += lanes) {
+      const F8 xv = ld8(x.ptr + p * x.ps + cg * 8);
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] += xv.v[e]; b[e] += xv.v[e] * xv.v[e]; }
+      } else {
+        F8 g = ld8(dz.ptr + p * dz.ps + cg * 8);
+        if (relu) {
+          const F8 zv = ld8(z.ptr + p * z.ps + cg * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] += g.v[e]; b[e] += g.v[e] * (xv.v[e] - mu[e]) * is[e]; }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { red[(ln * groups + cg) * 16 + e] = a[e]; red[(ln * groups + cg) * 16 + 8 + e] = b[e]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 16; i += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < lanes; ++q) s += red[q * groups * 16 + i];
+    const int g = i / 16, e = i % 16;
+    atomicAdd(out + (e >= 8 ? x.C : 0) + g * 8 + (e & 7), static_cast<double>(s));
+  }
+}
+
+// ----------------------------------------------------------------------------- BN finalize (forward)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps,
+                                   float momentum, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ run_mean,
+                                   float* __restrict__ run_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] / count;
+  double var = sums[C + c] / count - m * m;
+  if (var < 0) var = 0;
+  const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma[c];
+  mean_out[c] = static_cast<float>(m);
+  invstd_out[c] = is;
+  scale[c] = g * is;
+  shift[c] = beta[c] - static_cast<float>(m) * g * is;
+  if (run_mean) {
+    // the conv bias (stem convs) cancels in the normalisation but is part of the batch mean the reference tracks
+    const float bm = static_cast<float>(m) + (conv_bias ? conv_bias[c] : 0.f);
+    const double unbiased = count > 1 ? var * count / (count - 1.0) : var;
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * bm;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// ----------------------------------------------------------------------------- BN backward apply
+//   dz' = dz * [z > 0]        (relu)
+//   dx  = gamma*invstd * (dz' - sum(dz')/M - xhat * sum(dz' xhat)/M)      (+= if accumulate)
+//   dres (+)= dz'             (residual added before the ReLU)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View x, View dz, View z, View dx, View dres,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const double* __restrict__ sums,
+                                                           double count, int relu, int acc_dx, int acc_dres,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int groups = x.C >> 3;
+  const long total = static_cast<long>(x.N) * x.H * x.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
+      dbeta[c] += static_cast<float>(sums[c]);
+      dgamma[c] += static_cast<float>(sums[x.C + c]);
+    }
+  }
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long p = idx / groups;
+  F8 g = ld8(dz.ptr + p * dz.ps + cg * 8);
+  if (relu) {
+    const F8 zv = ld8(z.ptr + p * z.ps + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
+  }
+  if (dres.ptr) {
+    F8 r = g;
+    if (acc_dres) {
+      const F8 o = ld8(dres.ptr + p * dres.ps + cg * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r.v[e] += o.v[e];
+    }
+    st8(dres.ptr + p * dres.ps + cg * 8, r);
+  }
+  if (dx.ptr) {
+    const F8 xv = ld8(x.ptr + p * x.ps + cg * 8);
+    F8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      const float is = invstd[c];
+      const float xh = (xv.v[e] - mean[c]) * is;
+      const float sb = static_cast<float>(sums[c] / count), sg = static_cast<float>(sums[x.C + c] / count);
+      o.v[e] = gamma[c] * is * (g.v[e] - sb - xh * sg);
+    }
+    if (acc_dx) {
+      const F8 old = ld8(dx.ptr + p * dx.ps + cg * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o.v[e] += old.v[e];
+    }
+    st8(dx.ptr + p * dx.ps + cg * 8, o);
+  }
+}
+
+// ----------------------------------------------------------------------------- weight packing
+// dst[row][kofs + (tap_i*chunks + cc)*BK + j] (bf16); forward: row = co, channel = ci; dgrad: row = ci, channel = co
+// and the tap is mirrored.  One thread per destination element of this source's K range.
+__global__ void __launch_bounds__(256) pack_weights_kernel(PackJob j) {
+  const long per_row = static_cast<long>(j.ntaps) * j.chunks * j.BK;
+  const long total = static_cast<long>(j.rows_pad) * per_row;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int row = static_cast<int>(idx / per_row);
+  const long k = idx % per_row;
+  const int ti = static_cast<int>(k / (static_cast<long>(j.chunks) * j.BK));
+  const int ch = static_cast<int>(k % (static_cast<long>(j.chunks) * j.BK));
+  float v = 0.f;
+  const int nrow = j.dgrad ? j.Cin : j.Cout, nch = j.dgrad ? j.Cout : j.Cin;
+  if (row < nrow && ch < nch) {
+    int r = (j.taps[ti] >> 4) & 0xF, s = j.taps[ti] & 0xF;
+    const int co = j.dgrad ? ch : row, ci = j.dgrad ? row : ch;
+    v = j.src[((static_cast<long>(co) * j.Cin_total + j.ci_off + ci) * j.k + r) * j.k + s];
+  }
+  j.dst[static_cast<long>(row) * j.Ktot + j.kofs + k] = __float2bfloat16_rn(v);
+}
+
+// ----------------------------------------------------------------------------- layout converters
+// fp32 NCHW image -> bf16 NHWC with C padded to Cp (zeros)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, int H, int W, View out) {
+  const long total = static_cast<long>(N) * H * W;
+  const long p = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const long hw = static_cast<long>(H) * W;
+  const int n = static_cast<int>(p / hw);
+  const long r = p % hw;
+  for (int c0 = 0; c0 < out.C; c0 += 8) {
+    F8 f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f.v[e] = (c0 + e < C) ? __ldg(x + (static_cast<long>(n) * C + c0 + e) * hw + r) : 0.f;
+    st8(out.ptr + p * out.ps + c0, f);
+  }
+}
+
+// ----------------------------------------------------------------------------- transposed operators
+// dlow (+)= U^T dhi for bilinear align_corners=False (gather over the hi-res support of each low-res pixel)
+__device__ __forceinline__ void lerp_af(int dst, int in, int out, int& i0, int& i1, float& l) {
+  const float scale = static_cast<float>(in) / static_cast<float>(out);
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l = src - static_cast<float>(i0);
+}
+__global__ void __launch_bounds__(256) upsample_transpose_kernel(View dhi, View dlow, int accumulate) {
+  const int groups = dlow.C >> 3;
+  const long total = static_cast<long>(dlow.N) * dlow.H * dlow.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long p = idx / groups;
+  const int lx = static_cast<int>(p % dlow.W);
+  const long t = p / dlow.W;
+  const int ly = static_cast<int>(t % dlow.H);
+  const int n = static_cast<int>(t / dlow.H);
+  // hi-res rows/cols whose 2-tap footprint can include (ly, lx): conservative window from the inverse map
+  const float sy = static_cast<float>(dhi.H) / dlow.H, sx = static_cast<float>(dhi.W) / dlow.W;
+  const int y0 = max(0, static_cast<int>(floorf((ly - 1) * sy)) - 1), y1 = min(dhi.H - 1, static_cast<int>(ceilf((ly + 2) * sy)) + 1);
+  const int x0 = max(0, static_cast<int>(floorf((lx - 1) * sx)) - 1), x1 = min(dhi.W - 1, static_cast<int>(ceilf((lx + 2) * sx)) + 1);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int y = y0; y <= y1; ++y) {
+    int a0, a1; float la;
+    lerp_af(y, dlow.H, dhi.H, a0, a1, la);
+    float wy = 0.f;
+    if (a0 == ly) wy += 1.f - la;
+    if (a1 == ly) wy += la;
+    if (wy == 0.f) continue;
+    for (int x = x0; x <= x1; ++x) {
+      int b0, b1; float lb;
+      lerp_af(x, dlow.W, dhi.W, b0, b1, lb);
+      float wx = 0.f;
+      if (b0 == lx) wx += 1.f - lb;
+      if (b1 == lx) wx += lb;
+      if (wx == 0.f) continue;
+      const F8 g = ld8(dhi.ptr + ((static_cast<long>(n) * dhi.H + y) * dhi.W + x) * dhi.ps + cg * 8);
+      const float w = wy * wx;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += w * g.v[e];
+    }
+  }
+  F8 o;
+  bf16* dst = dlow.ptr + p * dlow.ps + cg * 8;
+  if (accumulate) {
+    const F8 old = ld8(dst);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += old.v[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = acc[e];
+  st8(dst, o);
+}
+
+// dx (+)= P^T dy for AvgPool(k,s,p) with count_include_pad (k == 0: global average pool)
+__global__ void __launch_bounds__(256) pool_transpose_kernel(View dy, View dx, int k, int stride, int pad, int accumulate) {
+  const int groups = dx.C >> 3;
+  const long total = static_cast<long>(dx.N) * dx.H * dx.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long p = idx / groups;
+  const int x = static_cast<int>(p % dx.W);
+  const long t = p / dx.W;
+  const int y = static_cast<int>(t % dx.H);
+  const int n = static_cast<int>(t / dx.H);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (k == 0) {
+    const F8 g = ld8(dy.ptr + static_cast<long>(n) * dy.ps + cg * 8);
+    const float inv = 1.f / static_cast<float>(dx.H * dx.W);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = g.v[e] * inv;
+  } else {
+    const float inv = 1.f / static_cast<float>(k * k);
+    for (int oy = 0; oy < dy.H; ++oy) {
+      const int h0 = oy * stride - pad;
+      if (y < h0 || y >= h0 + k) continue;
+      for (int ox = 0; ox < dy.W; ++ox) {
+        const int w0 = ox * stride - pad;
+        if (x < w0 || x >= w0 + k) continue;
+        const F8 g = ld8(dy.ptr + ((static_cast<long>(n) * dy.H + oy) * dy.W + ox) * dy.ps + cg * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += g.v[e] * inv;
+      }
+    }
+  }
+  bf16* dst = dx.ptr + p * dx.ps + cg * 8;
+  if (accumulate) {
+    const F8 old = ld8(dst);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += old.v[e];
+  }
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = acc[e];
+  st8(dst, o);
+}
+
+// generic elementwise: out (+)= a * [mask > 0]   (ReLU backward / plain copy / accumulate)
+__global__ void __launch_bounds__(256) masked_add_kernel(View a, View mask, View out, int accumulate) {
+  const int groups = out.C >> 3;
+  const long total = static_cast<long>(out.N) * out.H * out.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long p = idx / groups;
+  F8 g = ld8(a.ptr + p * a.ps + cg * 8);
+  if (mask.ptr) {
+    const F8 m = ld8(mask.ptr + p * mask.ps + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if (!(m.v[e] > 0.f)) g.v[e] = 0.f;
+  }
+  bf16* dst = out.ptr + p * out.ps + cg * 8;
+  if (accumulate) {
+    const F8 old = ld8(dst);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g.v[e] += old.v[e];
+  }
+  st8(dst, g);
+}
+
+
+// bilinear sample (align_corners=False) of 8 channels of a low-res view at hi-res pixel (y, x)
+__device__ __forceinline__ F8 sample8(const View& b, int n, int y, int x, int H, int W, int c) {
+  int y0, y1, x0, x1; float ly, lx;
+  lerp_af(y, b.H, H, y0, y1, ly);
+  lerp_af(x, b.W, W, x0, x1, lx);
+  const bf16* base = b.ptr + static_cast<long>(n) * b.H * b.W * b.ps + c;
+  const F8 v00 = ld8(base + (static_cast<long>(y0) * b.W + x0) * b.ps), v01 = ld8(base + (static_cast<long>(y0) * b.W + x1) * b.ps);
+  const F8 v10 = ld8(base + (static_cast<long>(y1) * b.W + x0) * b.ps), v11 = ld8(base + (static_cast<long>(y1) * b.W + x1) * b.ps);
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  F8 r;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) r.v[e] = w00 * v00.v[e] + w01 * v01.v[e] + w10 * v10.v[e] + w11 * v11.v[e];
+  return r;
+}
+
+// ---- PagFM (model_utils.py:292-312), unfused training form.  Forward: g = sigmoid(sum_c xk_c * U(yq)_c) (saved),
+// out = relu((1-g) x + g U(y)).  Threads: LPX lanes per pixel over C = 8*LPX channels of x; xk/yq have Cm channels.
+template <int LPX>
+__global__ void __launch_bounds__(256) pag_train_fwd_kernel(View x, View xk, View yq, View y, View out, float* gate) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long npix = static_cast<long>(x.N) * x.H * x.W;
+  long pix = gid / LPX;
+  const int cg = static_cast<int>(gid % LPX);
+  const bool valid = pix < npix;
+  if (!valid) pix = npix - 1;
+  const int w = static_cast<int>(pix % x.W);
+  const long t1 = pix / x.W;
+  const int h = static_cast<int>(t1 % x.H);
+  const int n = static_cast<int>(t1 / x.H);
+  float dot = 0.f;
+  if (cg * 8 < xk.C) {
+    const F8 a = ld8(xk.ptr + pix * xk.ps + cg * 8);
+    const F8 b = sample8(yq, n, h, w, x.H, x.W, cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dot += a.v[e] * b.v[e];
+  }
+#pragma unroll
+  for (int o = LPX / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  const float g = 1.f / (1.f + __expf(-dot));
+  const F8 xv = ld8(x.ptr + pix * x.ps + cg * 8);
+  const F8 yv = sample8(y, n, h, w, x.H, x.W, cg * 8);
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = fmaxf((1.f - g) * xv.v[e] + g * yv.v[e], 0.f);
+  if (valid) {
+    st8(out.ptr + pix * out.ps + cg * 8, o);
+    if (cg == 0) gate[pix] = g;
+  }
+}
+// Backward: dz' = dout*[out>0]; dg = sum_c dz'_c (U(y)_c - x_c); ds = dg g (1-g);
+//   dx (+)= (1-g) dz';  dxk = ds U(yq);  t1 = ds xk  (-> U^T -> dyq);  t2 = g dz'  (-> U^T -> dy)
+template <int LPX>
+__global__ void __launch_bounds__(256) pag_train_bwd_kernel(View x, View xk, View yq, View y, View out, View dout,
+                                                            const float* __restrict__ gate, View dx, int acc_dx, View dxk,
+                                                            View t1, View t2) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long npix = static_cast<long>(x.N) * x.H * x.W;
+  long pix = gid / LPX;
+  const int cg = static_cast<int>(gid % LPX);
+  const bool valid = pix < npix;
+  if (!valid) pix = npix - 1;
+  const int w = static_cast<int>(pix % x.W);
+  const long tq = pix / x.W;
+  const int h = static_cast<int>(tq % x.H);
+  const int n = static_cast<int>(tq / x.H);
+  const float g = gate[pix];
+  F8 dz = ld8(dout.ptr + pix * dout.ps + cg * 8);
+  const F8 ov = ld8(out.ptr + pix * out.ps + cg * 8);
+  const F8 xv = ld8(x.ptr + pix * x.ps + cg * 8);
+  const F8 yv = sample8(y, n, h, w, x.H, x.W, cg * 8);
+  float dg = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (!(ov.v[e] > 0.f)) dz.v[e] = 0.f;
+    dg += dz.v[e] * (yv.v[e] - xv.v[e]);
+  }
+#pragma unroll
+  for (int o = LPX / 2; o > 0; o >>= 1) dg += __shfl_xor_sync(0xffffffffu, dg, o);
+  const float ds = dg * g * (1.f - g);
+  if (!valid) return;
+  F8 a, b;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a.v[e] = (1.f - g) * dz.v[e]; b.v[e] = g * dz.v[e]; }
+  if (acc_dx) {
+    const F8 old = ld8(dx.ptr + pix * dx.ps + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a.v[e] += old.v[e];
+  }
+  st8(dx.ptr + pix * dx.ps + cg * 8, a);
+  st8(t2.ptr + pix * t2.ps + cg * 8, b);
+  if (cg * 8 < xk.C) {
+    const F8 kv = ld8(xk.ptr + pix * xk.ps + cg * 8);
+    const F8 qv = sample8(yq, n, h, w, x.H, x.W, cg * 8);
+    F8 c, d;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { c.v[e] = ds * qv.v[e]; d.v[e] = ds * kv.v[e]; }
+    st8(dxk.ptr + pix * dxk.ps + cg * 8, c);
+    st8(t1.ptr + pix * t1.ps + cg * 8, d);
+  }
+}
+
+// ---- Light_Bag backward: e = sigmoid(d); u = (1-e) i + p; v = i + e p
+//   dp (+)= du + e dv;  dd (+)= (dv p - du i) e (1-e);  ti = (1-e) du + dv  (-> U^T -> di_low)
+__global__ void __launch_bounds__(256) lightbag_bwd_kernel(View p, View il, View d, View duv, View dp, int acc_dp, View dd,
+                                                           int acc_dd, View ti) {
+  const int groups = p.C >> 3;
+  const long total = static_cast<long>(p.N) * p.H * p.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long pix = idx / groups;
+  const int w = static_cast<int>(pix % p.W);
+  const long t1 = pix / p.W;
+  const int h = static_cast<int>(t1 % p.H);
+  const int n = static_cast<int>(t1 / p.H);
+  const F8 iv = sample8(il, n, h, w, p.H, p.W, cg * 8);
+  const F8 pv = ld8(p.ptr + pix * p.ps + cg * 8);
+  const F8 dv_ = ld8(d.ptr + pix * d.ps + cg * 8);
+  const F8 du = ld8(duv.ptr + pix * duv.ps + cg * 8);
+  const F8 dv = ld8(duv.ptr + pix * duv.ps + p.C + cg * 8);
+  F8 op, od, ot;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float g = 1.f / (1.f + __expf(-dv_.v[e]));
+    op.v[e] = du.v[e] + g * dv.v[e];
+    od.v[e] = (dv.v[e] * pv.v[e] - du.v[e] * iv.v[e]) * g * (1.f - g);
+    ot.v[e] = (1.f - g) * du.v[e] + dv.v[e];
+  }
+  if (acc_dp) {
+    const F8 o = ld8(dp.ptr + pix * dp.ps + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) op.v[e] += o.v[e];
+  }
+  if (acc_dd) {
+    const F8 o = ld8(dd.ptr + pix * dd.ps + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) od.v[e] += o.v[e];
+  }
+  st8(dp.ptr + pix * dp.ps + cg * 8, op);
+  st8(dd.ptr + pix * dd.ps + cg * 8, od);
+  st8(ti.ptr + pix * ti.ps + cg * 8, ot);
+}
+
+__global__ void add_sums_kernel(const double* __restrict__ sums, float* __restrict__ dst, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) dst[c] += static_cast<float>(sums[c]);
+}
+
+}  // namespace
+
+static int reduce_geometry(const View& x, long& pix_per_block, int& threads, size_t& smem, unsigned& blocks) {
+  const int groups = x.C / 8;
+  if (groups < 1 || groups > 256) return -1;
+  const int lanes = 256 / groups;
+  threads = lanes * groups;
+  const long npix = static_cast<long>(x.N) * x.H * x.W;
+  pix_per_block = 2048;
+  blocks = static_cast<unsigned>((npix + pix_per_block - 1) / pix_per_block);
+  smem = static_cast<size_t>(threads) * 16 * sizeof(float);
+  return 0;
+}
+
+cudaError_t bn_stats_launch(View x, double* sums, cudaStream_t st) {
+  long ppb; int threads; size_t smem; unsigned blocks;
+  if (reduce_geometry(x, ppb, threads, smem, blocks)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * x.C * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  chan_reduce_kernel<0><<<blocks, threads, smem, st>>>(x, View{}, View{}, nullptr, nullptr, 0, ppb, sums);
+  return cudaGetLastError();
+}
+
+cudaError_t bn_finalize_launch(const double* sums, int C, double count, const float* gamma, const float* beta,
+                               const float* conv_bias, float* mean, float* invstd, float* scale, float* shift,
+                               float* run_mean, float* run_var, cudaStream_t st) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, count, gamma, beta, conv_bias, 1e-5f, 0.1f, mean, invstd,
+                                                      scale, shift, run_mean, run_var);
+  return cudaGetLastError();
+}
+
+cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
+                               const float* gamma, double* sums, int relu, int acc_dx, int acc_dres, float* dgamma,
+                               float* dbeta, cudaStream_t st) {
+  long ppb; int threads; size_t smem; unsigned blocks;
+  if (reduce_geometry(x, ppb, threads, smem, blocks)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * x.C * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  chan_reduce_kernel<1><<<blocks, threads, smem, st>>>(x, dz, z, mean, invstd, relu, ppb, sums);
+  const long total = static_cast<long>(x.N) * x.H * x.W * (x.C / 8);
+  const double count = static_cast<double>(x.N) * x.H * x.W;
+  bn_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, dz, z, dx, dres, mean, invstd, gamma, sums, count, relu,
+                                                             acc_dx, acc_dres, dgamma, dbeta);
+  return cudaGetLastError();
+}
+
+cudaError_t pack_weights_launch(const PackJob& j, cudaStream_t st) {
+  const long total = static_cast<long>(j.rows_pad) * j.ntaps * j.chunks * j.BK;
+  pack_weights_kernel<<<blocks_for(total, 256), 256, 0, st>>>(j);
+  return cudaGetLastError();
+}
+
+cudaError_t nchw_to_nhwc_launch(const float* x, int N, int C, int H, int W, View out, cudaStream_t st) {
+  nchw_to_nhwc_kernel<<<blocks_for(static_cast<long>(N) * H * W, 256), 256, 0, st>>>(x, N, C, H, W, out);
+  return cudaGetLastError();
+}
+
+cudaError_t upsample_transpose_launch(View dhi, View dlow, int accumulate, cudaStream_t st) {
+  const long total = static_cast<long>(dlow.N) * dlow.H * dlow.W * (dlow.C / 8);
+  upsample_transpose_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dhi, dlow, accumulate);
+  return cudaGetLastError();
+}
+
+cudaError_t pool_transpose_launch(View dy, View dx, int k, int stride, int pad, int accumulate, cudaStream_t st) {
+  const long total = static_cast<long>(dx.N) * dx.H * dx.W * (dx.C / 8);
+  pool_transpose_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dy, dx, k, stride, pad, accumulate);
+  return cudaGetLastError();
+}
+
+cudaError_t pag_train_fwd_launch(View x, View xk, View yq, View y, View out, float* gate, cudaStream_t st) {
+  const int LPX = x.C / 8;
+  const long total = static_cast<long>(x.N) * x.H * x.W * LPX;
+  const unsigned nb = blocks_for(total, 256);
+  switch (LPX) {
+    case 2: pag_train_fwd_kernel<2><<<nb, 256, 0, st>>>(x, xk, yq, y, out, gate); break;
+    case 4: pag_train_fwd_kernel<4><<<nb, 256, 0, st>>>(x, xk, yq, y, out, gate); break;
+    case 8: pag_train_fwd_kernel<8><<<nb, 256, 0, st>>>(x, xk, yq, y, out, gate); break;
+    case 16: pag_train_fwd_kernel<16><<<nb, 256, 0, st>>>(x, xk, yq, y, out, gate); break;
+    case 32: pag_train_fwd_kernel<32><<<nb, 256, 0, st>>>(x, xk, yq, y, out, gate); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t pag_train_bwd_launch(View x, View xk, View yq, View y, View out, View dout, const float* gate, View dx,
+                                 int acc_dx, View dxk, View t1, View t2, cudaStream_t st) {
+  const int LPX = x.C / 8;
+  const long total = static_cast<long>(x.N) * x.H * x.W * LPX;
+  const unsigned nb = blocks_for(total, 256);
+  switch (LPX) {
+    case 2: pag_train_bwd_kernel<2><<<nb, 256, 0, st>>>(x, xk, yq, y, out, dout, gate, dx, acc_dx, dxk, t1, t2); break;
+    case 4: pag_train_bwd_kernel<4><<<nb, 256, 0, st>>>(x, xk, yq, y, out, dout, gate, dx, acc_dx, dxk, t1, t2); break;
+    case 8: pag_train_bwd_kernel<8><<<nb, 256, 0, st>>>(x, xk, yq, y, out, dout, gate, dx, acc_dx, dxk, t1, t2); break;
+    case 16: pag_train_bwd_kernel<16><<<nb, 256, 0, st>>>(x, xk, yq, y, out, dout, gate, dx, acc_dx, dxk, t1, t2); break;
+    case 32: pag_train_bwd_kernel<32><<<nb, 256, 0, st>>>(x, xk, yq, y, out, dout, gate, dx, acc_dx, dxk, t1, t2); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t lightbag_bwd_launch(View p, View il, View d, View duv, View dp, int acc_dp, View dd, int acc_dd, View ti,
+                                cudaStream_t st) {
+  const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
+  lightbag_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, il, d, duv, dp, acc_dp, dd, acc_dd, ti);
+  return cudaGetLastError();
+}
+
+cudaError_t add_sums_launch(const double* sums, float* dst, int C, cudaStream_t st) {
+  add_sums_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dst, C);
+  return cudaGetLastError();
+}
+
+cudaError_t masked_add_launch(View a, View mask, View out, int accumulate, cudaStream_t st) {
+  const long total = static_cast<long>(out.N) * out.H * out.W * (out.C / 8);
+  masked_add_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, mask, out, accumulate);
+  return cudaGetLastError();
+}
+
+}  // namespace pidnet

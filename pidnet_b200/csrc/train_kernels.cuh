@@ -1,0 +1,73 @@
+// Training-mode kernels (see train_kernels.cu, wgrad_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "kernels.cuh"
+
+namespace pidnet {
+
+// ---- BatchNorm with batch statistics
+// sums: device double[2*C] scratch (sum, sum of squares | sum dz', sum dz'*xhat)
+cudaError_t bn_stats_launch(View x, double* sums, cudaStream_t st);
+// mean / invstd / folded (scale, shift) for the apply kernel; running stats updated in place when non-null
+// (momentum 0.1, unbiased variance; `conv_bias` is added to the tracked mean for convs whose bias we drop)
+cudaError_t bn_finalize_launch(const double* sums, int C, double count, const float* gamma, const float* beta,
+                               const float* conv_bias, float* mean, float* invstd, float* scale, float* shift,
+                               float* run_mean, float* run_var, cudaStream_t st);
+// z = act(scale*x + shift (+res)) is the existing upadd kernel (kernels.cuh).  Backward:
+//   dz' = dz*[z>0];  dgamma += sum dz'*xhat;  dbeta += sum dz';  dx (+)= gamma*invstd*(dz' - mean(dz') - xhat*mean(dz'*xhat));
+//   dres (+)= dz'
+cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
+                               const float* gamma, double* sums, int relu, int acc_dx, int acc_dres, float* dgamma,
+                               float* dbeta, cudaStream_t st);
+
+// ---- device-side weight packing: fp32 [Cout][Cin_total][k][k] -> bf16 packed rows (forward: row = co; dgrad: row = ci)
+struct PackJob {
+  const float* src;
+  bf16* dst;
+  long Ktot, kofs;        // destination row length / offset of this source's K range
+  int rows_pad;           // destination rows (zero-filled beyond the valid ones)
+  int Cout, Cin, Cin_total, ci_off, k;
+  int BK, chunks, ntaps;
+  int dgrad;
+  unsigned char taps[9];  // (r << 4) | s of the SOURCE weight tap feeding destination tap i
+};
+cudaError_t pack_weights_launch(const PackJob& j, cudaStream_t st);
+
+cudaError_t nchw_to_nhwc_launch(const float* x, int N, int C, int H, int W, View out, cudaStream_t st);
+// dlow (+)= U^T dhi  (bilinear, align_corners=False);  dx (+)= P^T dy (AvgPool count_include_pad; k==0 global)
+cudaError_t upsample_transpose_launch(View dhi, View dlow, int accumulate, cudaStream_t st);
+cudaError_t pool_transpose_launch(View dy, View dx, int k, int stride, int pad, int accumulate, cudaStream_t st);
+// out (+)= a * [mask > 0]  (mask optional)
+cudaError_t masked_add_launch(View a, View mask, View out, int accumulate, cudaStream_t st);
+
+// ---- PagFM / Light_Bag in training form (gate saved for backward)
+cudaError_t pag_train_fwd_launch(View x, View xk, View yq, View y, View out, float* gate, cudaStream_t st);
+cudaError_t pag_train_bwd_launch(View x, View xk, View yq, View y, View out, View dout, const float* gate, View dx,
+                                 int acc_dx, View dxk, View t1, View t2, cudaStream_t st);
+cudaError_t lightbag_bwd_launch(View p, View il, View d, View duv, View dp, int acc_dp, View dd, int acc_dd, View ti,
+                                cudaStream_t st);
+// dst[c] += sums[c]  (bias gradients from a per-channel reduction)
+cudaError_t add_sums_launch(const double* sums, float* dst, int C, cudaStream_t st);
+
+// ---- wgrad on tcgen05 with MN-major operands (wgrad_tc.cu):
+//   dW[co][ci_off+ci][r][s] += sum_pixels dY[p][co] * X[tap(p)][ci]       (fp32 atomics into the torch-layout gradient)
+struct WgradParams {
+  CUtensorMap tmY;                 // dY  [N,Ho,Wo,Cout]  box {64, 8, 8, 1}
+  CUtensorMap tmX[kConvMaxMaps];   // X (parity) maps      box {64, 8, 8, 1}
+  uint32_t taps[kConvMaxTaps];     // map | (dh+8) << 8 | (dw+8) << 16 | (r << 24) | (s << 28)
+  int ntaps;
+  int tiles_w, tiles_h, N;         // 8x8-pixel tiles of the OUTPUT grid
+  int Cout, Cin, Cin_total, ci_off, k;
+  float* dW;                       // [Cout][Cin_total][k][k] fp32
+};
+struct WgradLaunch {
+  WgradParams p;
+  dim3 grid;  // (pixel splits, co tiles, ci tiles * tap groups)
+  int taps_per_group;
+};
+cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st);
+cudaError_t wgrad_tc_init();
+
+}  // namespace pidnet

@@ -1,0 +1,159 @@
+// Weight-gradient GEMM on tcgen05 with MN-major operands:
+//     dW[co][ci][r][s] += sum over output pixels p of  dY[p][co] * X[tap_{r,s}(p)][ci]
+// Per filter tap this is D[co, ci] = A^T B with A = dY tile [64 pixels][128 co] and B = X tile [64 pixels][64 ci]:
+// both operands are channel-contiguous ("MN-major") exactly as TMA delivers an 8x8-pixel box of an NHWC tensor
+// (64 rows of 128 B, SWIZZLE_128B; descriptor: SBO = 1024 B per 8 pixel rows, LBO = 8192 B between 64-channel
+// blocks -- verified by the probe in probe.cu).  The pixel dimension is the GEMM K: each CTA owns a (co tile,
+// ci tile, tap group) and a strided subset of the pixel tiles (split-K), keeps one fp32 accumulator per tap in
+// TMEM for its whole life, and finally adds its partial to the fp32 gradient with atomics.  Stride-2 convs use
+// the same parity tensor maps as the forward kernel; zero padding / ragged tiles are TMA out-of-bounds fills.
+#include "train_kernels.cuh"
+#include "ptx.cuh"
+
+namespace pidnet {
+namespace {
+
+constexpr int kWgThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer (+TMEM), warps 2..5: epilogue
+constexpr int kWgStages = 4;
+
+template <int T>  // taps per CTA (1 or 3)
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int kABytes = 2 * 8192, kBBytes = T * 8192, kStageBytes = kABytes + kBBytes;
+  constexpr int kCols = T == 1 ? 64 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + kWgStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kWgStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kWgStages);
+  const uint32_t tmem_slot = done_bar + 8u;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + kWgStages * kStageBytes + 8 * (2 * kWgStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ngroups = (p.ntaps + T - 1) / T;
+  const int ci_tile = blockIdx.z / ngroups, grp = blockIdx.z % ngroups;
+  const int co0 = blockIdx.y * 128, ci0 = ci_tile * 64;
+  const int tap0 = grp * T;
+  const int ntap = min(T, p.ntaps - tap0);
+  const int per_img = p.tiles_w * p.tiles_h;
+  const int m_tiles = p.N * per_img;
+  const bool second_a = co0 + 64 < p.Cout;   // the upper 64-channel block exists (else rows 64..127 are unused)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+
+  int my_tiles = 0;
+  for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) ++my_tiles;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+        const int n = tile / per_img;
+        const int rem = tile - n * per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        const int w0 = tw * 8, h0 = th * 8;
+        const int st = it % kWgStages;
+        const uint32_t ph = (it / kWgStages) & 1;
+        mbar_wait(empty_bar(st), ph ^ 1);
+        mbar_arrive_expect_tx(full_bar(st), (second_a ? 2 : 1) * 8192 + ntap * 8192);
+        const uint32_t sb = base + st * kStageBytes;
+        tma_load_4d(sb, &p.tmY, full_bar(st), co0, w0, h0, n);
+        if (second_a) tma_load_4d(sb + 8192, &p.tmY, full_bar(st), co0 + 64, w0, h0, n);
+        for (int j = 0; j < ntap; ++j) {
+          const uint32_t tp = p.taps[tap0 + j];
+          const int dh = static_cast<int>((tp >> 8) & 0xFF) - 8, dw = static_cast<int>((tp >> 16) & 0xFF) - 8;
+          tma_load_4d(sb + kABytes + j * 8192, &p.tmX[tp & 0xFF], full_bar(st), ci0, w0 + dw, h0 + dh, n);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // idesc: fp32 accumulate, bf16 x bf16, A and B MN-major
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+    constexpr uint64_t hi = (static_cast<uint64_t>(8192 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                            (1ull << 46) | (2ull << 61);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int st = it % kWgStages;
+      const uint32_t ph = (it / kWgStages) & 1;
+      mbar_wait(full_bar(st), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sb = base + st * kStageBytes;
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+          if (j < ntap) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a_desc = hi | static_cast<uint64_t>(((sb + k * 2048) & 0x3FFFF) >> 4);
+              const uint64_t b_desc = hi | static_cast<uint64_t>(((sb + kABytes + j * 8192 + k * 2048) & 0x3FFFF) >> 4);
+              umma_bf16(tmem + j * 64, a_desc, b_desc, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(empty_bar(st));
+        if (it == my_tiles - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+    }
+  } else if (my_tiles > 0) {
+    // epilogue: lane quarter q of TMEM = co rows 32q..32q+31
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int kk = p.k * p.k;
+    for (int j = 0; j < ntap; ++j) {
+      const uint32_t tp = p.taps[tap0 + j];
+      const int r = (tp >> 24) & 0xF, s = (tp >> 28) & 0xF;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t v[32];
+        tmem_ld32(tmem + j * 64 + g * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          float* row = p.dW + (static_cast<size_t>(co) * p.Cin_total + p.ci_off) * kk + r * p.k + s;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int ci = ci0 + g * 32 + e;
+            if (ci < p.Cin) atomicAdd(row + static_cast<size_t>(ci) * kk, __uint_as_float(v[e]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kCols>(tmem);
+}
+
+template <int T>
+size_t wg_smem() { return static_cast<size_t>(kWgStages) * (2 * 8192 + T * 8192) + 256 + 1024; }
+
+}  // namespace
+
+cudaError_t wgrad_tc_init() {
+  cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(wg_smem<1>()));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wg_smem<3>()));
+}
+
+cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
+  if (L.taps_per_group == 1) wgrad_tc_kernel<1><<<L.grid, kWgThreads, wg_smem<1>(), st>>>(L.p);
+  else if (L.taps_per_group == 3) wgrad_tc_kernel<3><<<L.grid, kWgThreads, wg_smem<3>(), st>>>(L.p);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+}  // namespace pidnet
