@@ -124,6 +124,9 @@ class FullModel(nn.Module):
         """Train mode: one engine call does forward (BN batch statistics), criterion and backward; the returned
         loss is attached to autograd so `loss.mean().backward()` delivers the parameter gradients."""
         from .train import EngineTrainer, _TrainStepFn
+        from .pidnet import PIDNet
+        if not isinstance(self.model, PIDNet):
+            raise TypeError('pidnet_b200.FullModel trains pidnet_b200.PIDNet models only (call .eval() for loss evaluation)')
         if getattr(self, '_trainer', None) is None:
             self._trainer = EngineTrainer(self.model)
         names = [k for k, _ in self.model.named_parameters()]

@@ -89,7 +89,7 @@ def test_upsample_and_fullmodel_surface():
             return list(self.o)
     outs, labels, bd = CO.synthetic_batch(2, 19, 64, 128, 31)
     weight = torch.tensor(CO.CITYSCAPES_CLASS_WEIGHTS)
-    fm = FullModel(Dummy([o.to(dev) for o in outs]), OhemCrossEntropy(255, 0.9, 131072, weight), BondaryLoss())
+    fm = FullModel(Dummy([o.to(dev) for o in outs]), OhemCrossEntropy(255, 0.9, 131072, weight), BondaryLoss()).eval()
     loss, ups, acc, ll = fm(torch.zeros(1, device=dev), labels.to(dev), bd.to(dev))
     r = CO.full_model_forward(outs, labels, bd, weight, {})
     assert close(loss.mean().item(), r[0].mean().item()) and close(ll[0].mean().item(), r[3][0].mean().item())
