@@ -1549,6 +1549,29 @@ int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x, const int
     if (out_d) CK(cudaMemcpyAsync(out_d, t.logits[2], lp * 4, cudaMemcpyDeviceToDevice, st));
   });
 }
+/* measurement: per-launch device times of one training step.  Writes a text table (one line per launch:
+ * "F|B <ms> <kernel> <name>") into buf; returns the criterion time separately. */
+int pidnet_train_profile(pidnet_trainer* h, void* stream, const float* x, const int64_t* labels, const float* bd_gt,
+                         const float* class_weights, const pidnet_criterion_cfg* cfg, char* buf, size_t cap, float* crit_ms) {
+  return guard([&] {
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    std::vector<float> f, bw;
+    float cm = 0;
+    t.profile(reinterpret_cast<cudaStream_t>(stream), x, labels, bd_gt, class_weights, *cfg, f, bw, cm);
+    if (crit_ms) *crit_ms = cm;
+    std::string out;
+    char line[512];
+    for (size_t i = 0; i < f.size(); ++i) {
+      std::snprintf(line, sizeof(line), "F %.5f %s %s\n", f[i], t.b.ops[i].kernel.empty() ? "-" : t.b.ops[i].kernel.c_str(), t.b.ops[i].name.c_str());
+      out += line;
+    }
+    for (size_t i = 0; i < bw.size(); ++i) {
+      std::snprintf(line, sizeof(line), "B %.5f %s %s\n", bw[i], t.bops[i].kernel.empty() ? "-" : t.bops[i].kernel.c_str(), t.bops[i].name.c_str());
+      out += line;
+    }
+    if (buf && cap) std::snprintf(buf, cap, "%s", out.c_str());
+  });
+}
 static void dump_nhwc(const T& t, float* host_out, int64_t* shape4) {
   if (shape4) { shape4[0] = t.N; shape4[1] = t.C; shape4[2] = t.H; shape4[3] = t.W; }
   if (!host_out) return;

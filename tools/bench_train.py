@@ -65,6 +65,20 @@ def main():
                 data='synthetic', config=dict(workload=f'PIDNet-S train fwd + OHEM/boundary loss + bwd, {B}x3x{H}x{W} per GPU, NCCL all-reduce of {tr.n_param} fp32 gradients',
                 batch_per_gpu=B), launches=dict(forward=f.value, backward=b.value), loss=float(out12[0]),
                 conv_tflops=flops / (ms * 1e-3) / 1e12, grad_allreduce_bytes=4 * tr.n_param)
+    if rank == 0 and os.environ.get('PROFILE'):
+        buf = C.create_string_buffer(1 << 20)
+        cm = C.c_float()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        cw = weight.to(dev)
+        tr.lib.pidnet_train_profile(tr.h, None, p(x), p(labels), p(bd), p(cw), C.byref(crit.cfg), buf, 1 << 20, C.byref(cm))
+        rows = [l.split(' ', 3) for l in buf.value.decode().splitlines()]
+        agg = {}
+        for ph, ms_, kern, nm in rows:
+            key = (ph, kern if kern != '-' else nm.split('.')[-1])
+            a = agg.setdefault(key, [0, 0.0]); a[0] += 1; a[1] += float(ms_)
+        line['profile'] = dict(criterion_ms=cm.value, groups=sorted([dict(phase=k[0], kernel=k[1], launches=v[0], ms=round(v[1], 3)) for k, v in agg.items()], key=lambda d: -d['ms'])[:24])
+        with open(os.environ['PROFILE'], 'w') as f:
+            f.write(buf.value.decode())
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
