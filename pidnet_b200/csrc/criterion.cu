@@ -77,13 +77,22 @@ __device__ __forceinline__ float interp(const float* __restrict__ p, const Pixel
 }
 
 // --------------------------------------------------------------------------------------- pass 1
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// CMAX: compile-time bound of the class loop (logits stay in registers; no dynamically indexed arrays)
+template <int CMAX>
 __global__ void __launch_bounds__(256) crit_pixel_kernel(CritParams p) {
   __shared__ double red[A_NLT2 + 1][8];
   const long npix = static_cast<long>(p.N) * p.H * p.W;
   const long pix = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  double acc[A_NLT2 + 1];
+  // every slot receives at most one value per thread: the warp reduction runs in fp32 (exact for the
+  // counters, one rounding for the losses), the cross-warp / cross-block accumulation in fp64
+  float acc[A_NLT2 + 1];
 #pragma unroll
-  for (int i = 0; i <= A_NLT2; ++i) acc[i] = 0.0;
+  for (int i = 0; i <= A_NLT2; ++i) acc[i] = 0.f;
   if (pix < npix) {
     const PixelCtx c = make_ctx(pix, p.H, p.W, p.h, p.w);
     const long t64 = p.labels[pix];
@@ -93,42 +102,50 @@ __global__ void __launch_bounds__(256) crit_pixel_kernel(CritParams p) {
     const float* xm = p.x_m + static_cast<size_t>(c.n) * p.C * plane;
     const float* xp = p.x_p + static_cast<size_t>(c.n) * p.C * plane;
     // main head: softmax prob of the target, weighted CE, argmax
-    float vm[kMaxC];
-    float mx = -FLT_MAX;
+    float vm[CMAX];
+    float mx = -FLT_MAX, vt = 0.f;
     int amax = 0;
-    for (int k = 0; k < p.C; ++k) {
-      vm[k] = interp(xm + k * plane, c, p.w);
-      if (vm[k] > mx) { mx = vm[k]; amax = k; }
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) {
+      if (k < p.C) {
+        vm[k] = interp(xm + k * plane, c, p.w);
+        if (vm[k] > mx) { mx = vm[k]; amax = k; }
+        if (k == t) vt = vm[k];
+      }
     }
     float se = 0.f;
-    for (int k = 0; k < p.C; ++k) se += expf(vm[k] - mx);
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) if (k < p.C) se += expf(vm[k] - mx);
     const float lse = mx + logf(se);
     const float wt = (valid1 && p.class_w) ? __ldg(p.class_w + t) : 1.f;
-    const float pm = expf(vm[t] - lse);
-    const float cem = wt * (lse - vm[t]);
-    acc[A_ACC] = (static_cast<long>(amax) == t64) ? 1.0 : 0.0;   // pixel_acc counts every pixel (label >= 0), utils.py:31
+    const float pm = expf(vt - lse);
+    const float cem = wt * (lse - vt);
+    acc[A_ACC] = (static_cast<long>(amax) == t64) ? 1.f : 0.f;   // pixel_acc counts every pixel (label >= 0), utils.py:31
     // aux head: plain weighted CE, reduction none (ignored pixels contribute 0)
     if (valid1) {
-      float mp = -FLT_MAX, vt = 0.f, sp = 0.f;
-      float vp[kMaxC];
-      for (int k = 0; k < p.C; ++k) {
-        vp[k] = interp(xp + k * plane, c, p.w);
-        mp = fmaxf(mp, vp[k]);
+      float mp = -FLT_MAX, vtp = 0.f, sp = 0.f;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < p.C) {
+          vm[k] = interp(xp + k * plane, c, p.w);
+          mp = fmaxf(mp, vm[k]);
+          if (k == t) vtp = vm[k];
+        }
       }
-      for (int k = 0; k < p.C; ++k) sp += expf(vp[k] - mp);
-      vt = vp[t];
-      acc[A_CE_P] = wt * (mp + logf(sp) - vt);
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) if (k < p.C) sp += expf(vm[k] - mp);
+      acc[A_CE_P] = wt * (mp + logf(sp) - vtp);
     }
     // boundary head
     const float xd = interp(p.x_d + static_cast<size_t>(c.n) * plane, c, p.w);
     const float z = p.bd_gt[pix];
     const float bce = fmaxf(xd, 0.f) - xd * z + log1pf(expf(-fabsf(xd)));
-    if (z == 1.f) { acc[A_BCE_POS] = bce; acc[A_NPOS] = 1.0; }
-    else if (z == 0.f) { acc[A_BCE_NEG] = bce; acc[A_NNEG] = 1.0; }
+    if (z == 1.f) { acc[A_BCE_POS] = bce; acc[A_NPOS] = 1.f; }
+    else if (z == 0.f) { acc[A_BCE_NEG] = bce; acc[A_NNEG] = 1.f; }
     const float sg = 1.f / (1.f + expf(-xd));
     const bool valid2 = valid1 && sg > p.bd_threshold;
-    if (valid1) { acc[A_NV1] = 1.0; if (pm < p.ohem_thres) acc[A_NLT1] = 1.0; }
-    if (valid2) { acc[A_NV2] = 1.0; if (pm < p.ohem_thres) acc[A_NLT2] = 1.0; }
+    if (valid1) { acc[A_NV1] = 1.f; if (pm < p.ohem_thres) acc[A_NLT1] = 1.f; }
+    if (valid2) { acc[A_NV2] = 1.f; if (pm < p.ohem_thres) acc[A_NLT2] = 1.f; }
     p.ws_p[pix] = pm;
     p.ws_ce[pix] = cem;
     p.ws_flags[pix] = static_cast<unsigned char>((valid1 ? 1 : 0) | (valid2 ? 2 : 0));
@@ -136,8 +153,8 @@ __global__ void __launch_bounds__(256) crit_pixel_kernel(CritParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i <= A_NLT2; ++i) {
-    const double v = warp_sum(acc[i]);
-    if (lane == 0) red[i][warp] = v;
+    const float v = warp_sum_f(acc[i]);
+    if (lane == 0) red[i][warp] = static_cast<double>(v);
   }
   __syncthreads();
   if (threadIdx.x <= A_NLT2) {
@@ -357,6 +374,131 @@ __global__ void __launch_bounds__(256) crit_backward_kernel(CritParams p, const 
   }
 }
 
+// Tiled backward: same 32 x 8 label tile per block, but (a) the low-res logits of the tile's footprint are staged
+// in shared memory once, (b) the class loops are register-resident (CMAX), and (c) the transposed interpolation
+// along x is a segmented warp reduction -- lanes that share the left low-res column (contiguous runs of ~8 lanes)
+// are summed with shuffles and only the run heads touch the shared gradient tile, which removes the ~8-way
+// same-address shared-atomic serialisation of the plain scatter.
+template <int CMAX>
+__global__ void __launch_bounds__(256) crit_backward_tiled_kernel(CritParams p, const SelState* st) {
+  extern __shared__ float sm[];
+  const int CH = 2 * p.C + 1;
+  constexpr int kLP = kLH * kLW;
+  float* lo = sm;                 // [CH][kLH][kLW] staged logits: [0,C) aux head, [C,2C) main head, 2C boundary
+  float* tile = sm + CH * kLP;    // [CH][kLH][kLW] gradient accumulators
+  const int tiles_x = (p.W + kTileW - 1) / kTileW, tiles_y = (p.H + kTileH - 1) / kTileH;
+  const int n = blockIdx.x / (tiles_x * tiles_y);
+  const int rem = blockIdx.x - n * tiles_x * tiles_y;
+  const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+  const int ly0 = lerp_ac(ty * kTileH, p.h, p.H).i0, lx0 = lerp_ac(tx * kTileW, p.w, p.W).i0;
+  const size_t plane = static_cast<size_t>(p.h) * p.w;
+  for (int i = threadIdx.x; i < CH * kLP; i += blockDim.x) {
+    const int ch = i / kLP, r = i - ch * kLP;
+    const int ly = min(ly0 + r / kLW, p.h - 1), lx = min(lx0 + r % kLW, p.w - 1);
+    const float* src = ch < p.C ? p.x_p + (static_cast<size_t>(n) * p.C + ch) * plane
+                                : (ch < 2 * p.C ? p.x_m + (static_cast<size_t>(n) * p.C + (ch - p.C)) * plane
+                                                : p.x_d + static_cast<size_t>(n) * plane);
+    lo[i] = __ldg(src + static_cast<size_t>(ly) * p.w + lx);
+    tile[i] = 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int xr = tx * kTileW + lane, yr = ty * kTileH + (threadIdx.x >> 5);
+  const bool inside = xr < p.W && yr < p.H;
+  const int x = min(xr, p.W - 1), y = min(yr, p.H - 1);
+  const Lerp ly = lerp_ac(y, p.h, p.H), lx = lerp_ac(x, p.w, p.W);
+  const int a00 = (ly.i0 - ly0) * kLW + (lx.i0 - lx0), a01 = (ly.i0 - ly0) * kLW + (lx.i1 - lx0);
+  const int a10 = (ly.i1 - ly0) * kLW + (lx.i0 - lx0), a11 = (ly.i1 - ly0) * kLW + (lx.i1 - lx0);
+  // runs of lanes with the same left column: predicate bit b = "lane + 2^b belongs to my run"
+  unsigned same = 0;
+#pragma unroll
+  for (int b = 0; b < 5; ++b) {
+    const int other = __shfl_down_sync(0xffffffffu, lx.i0, 1 << b);
+    if (lane + (1 << b) < 32 && other == lx.i0) same |= 1u << b;
+  }
+  const int prev = __shfl_up_sync(0xffffffffu, lx.i0, 1);
+  const bool head = lane == 0 || prev != lx.i0;
+  const float wy0 = 1.f - ly.l, wy1 = ly.l, wx0 = 1.f - lx.l, wx1 = lx.l;
+  auto value = [&](int ch) {   // torch's evaluation order: rows first, then columns
+    const float* q = lo + ch * kLP;
+    return wy0 * (wx0 * q[a00] + wx1 * q[a01]) + wy1 * (wx0 * q[a10] + wx1 * q[a11]);
+  };
+  auto contribute = [&](int ch, float g) {   // executed by all 32 lanes
+    float v0 = g * wx0, v1 = g * wx1;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      const float t0 = __shfl_down_sync(0xffffffffu, v0, 1 << b), t1 = __shfl_down_sync(0xffffffffu, v1, 1 << b);
+      if (same & (1u << b)) { v0 += t0; v1 += t1; }
+    }
+    if (head) {
+      float* tb = tile + ch * kLP;
+      if (v0 != 0.f) { atomicAdd(tb + a00, v0 * wy0); atomicAdd(tb + a10, v0 * wy1); }
+      if (v1 != 0.f) { atomicAdd(tb + a01, v1 * wy0); atomicAdd(tb + a11, v1 * wy1); }
+    }
+  };
+  const double nhw = static_cast<double>(p.N) * p.H * p.W;
+  const long pix = (static_cast<long>(n) * p.H + y) * p.W + x;
+  const unsigned f = inside ? p.ws_flags[pix] : 0u;
+  const int t = (f & 1) ? static_cast<int>(p.labels[pix]) : -1;
+  const float wt = ((f & 1) && p.class_w) ? __ldg(p.class_w + t) : 1.f;
+  float v[CMAX];
+  // main head: coefficient from both OHEM selections
+  float coef = 0.f;
+  if (f & 1) {
+    const float pm = p.ws_p[pix];
+    if (pm < st->thr[0]) coef += static_cast<float>(p.bw1 / p.accum[A_K1]);
+    if ((f & 2) && pm < st->thr[1]) coef += static_cast<float>(p.sb / p.accum[A_K2]);
+  }
+  if (__any_sync(0xffffffffu, coef != 0.f)) {
+    float mx = -FLT_MAX, se = 0.f;
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) if (k < p.C) { v[k] = value(p.C + k); mx = fmaxf(mx, v[k]); }
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) if (k < p.C) { v[k] = __expf(v[k] - mx); se += v[k]; }
+    const float cf = coef * wt, inv = 1.f / se;
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) if (k < p.C) contribute(p.C + k, cf * (v[k] * inv - (k == t ? 1.f : 0.f)));
+  }
+  // aux head
+  if (__any_sync(0xffffffffu, (f & 1) != 0)) {
+    float mx = -FLT_MAX, se = 0.f;
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) if (k < p.C) { v[k] = value(k); mx = fmaxf(mx, v[k]); }
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) if (k < p.C) { v[k] = __expf(v[k] - mx); se += v[k]; }
+    const float cf = (f & 1) ? static_cast<float>(p.bw0 / nhw) * wt : 0.f, inv = 1.f / se;
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) if (k < p.C) contribute(k, cf * (v[k] * inv - (k == t ? 1.f : 0.f)));
+  }
+  // boundary head
+  {
+    float g = 0.f;
+    if (inside) {
+      const float xd = value(2 * p.C);
+      const float z = p.bd_gt[pix];
+      const double nb = p.accum[A_NPOS] + p.accum[A_NNEG];
+      float om = 0.f;
+      if (z == 1.f) om = static_cast<float>(p.accum[A_NNEG] / nb);
+      else if (z == 0.f) om = static_cast<float>(p.accum[A_NPOS] / nb);
+      const float sg = 1.f / (1.f + __expf(-xd));
+      g = static_cast<float>(p.coeff_bce / nhw) * om * (sg - z);
+    }
+    contribute(2 * p.C, g);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CH * kLP; i += blockDim.x) {
+    const float g = tile[i];
+    if (g == 0.f) continue;
+    const int ch = i / kLP, r = i - ch * kLP;
+    const int gy = ly0 + r / kLW, gx = lx0 + r % kLW;
+    if (gy >= p.h || gx >= p.w) continue;
+    float* dst = ch < p.C ? p.g_p + (static_cast<size_t>(n) * p.C + ch) * plane
+                          : (ch < 2 * p.C ? p.g_m + (static_cast<size_t>(n) * p.C + (ch - p.C)) * plane
+                                          : p.g_d + static_cast<size_t>(n) * plane);
+    atomicAdd(dst + static_cast<size_t>(gy) * p.w + gx, g);
+  }
+}
+
 // --------------------------------------------------------------------------------------- x8 upsample (returned outputs)
 __global__ void __launch_bounds__(256) upsample_ac_kernel(const float* __restrict__ x, int NC, int h, int w,
                                                           float* __restrict__ out, int H, int W) {
@@ -396,7 +538,9 @@ cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaS
   cudaError_t e;
   if ((e = cudaMemsetAsync(p.accum, 0, A_COUNT * sizeof(double) + 512 + 2 * 4096 * sizeof(unsigned) + 256, st)) != cudaSuccess) return e;
   const unsigned blocks = static_cast<unsigned>((npix + 255) / 256);
-  crit_pixel_kernel<<<blocks, 256, 0, st>>>(p);
+  if (p.C <= 12) crit_pixel_kernel<12><<<blocks, 256, 0, st>>>(p);
+  else if (p.C <= 20) crit_pixel_kernel<20><<<blocks, 256, 0, st>>>(p);
+  else crit_pixel_kernel<kMaxC><<<blocks, 256, 0, st>>>(p);
   crit_select_init_kernel<<<1, 32, 0, st>>>(p, sel);
   const unsigned hb = blocks < 1184 ? blocks : 1184;
   // exact k-th order statistic of p: radix select over the 32-bit pattern (12 + 12 + 8 bits)
@@ -418,7 +562,15 @@ cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaS
     auto span = [](int t, int in, int out) { return out > 1 ? (static_cast<long>(t - 1) * (in - 1)) / (out - 1) + 3 : 1; };
     p.direct_scatter = (span(kTileW, p.w, p.W) > kLW || span(kTileH, p.h, p.H) > kLH) ? 1 : 0;
     const size_t smem = static_cast<size_t>(2 * p.C + 1) * kLH * kLW * sizeof(float);
-    crit_backward_kernel<<<p.N * tiles, 256, smem, st>>>(p, sel);
+    if (p.direct_scatter) {
+      crit_backward_kernel<<<p.N * tiles, 256, smem, st>>>(p, sel);
+    } else if (p.C <= 12) {
+      crit_backward_tiled_kernel<12><<<p.N * tiles, 256, 2 * smem, st>>>(p, sel);
+    } else if (p.C <= 20) {
+      crit_backward_tiled_kernel<20><<<p.N * tiles, 256, 2 * smem, st>>>(p, sel);
+    } else {
+      crit_backward_tiled_kernel<kMaxC><<<p.N * tiles, 256, 2 * smem, st>>>(p, sel);
+    }
   }
   return cudaGetLastError();
 }

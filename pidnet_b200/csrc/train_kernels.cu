@@ -31,7 +31,9 @@ inline unsigned blocks_for(long total, int threads) { return static_cast<unsigne
 
 // ----------------------------------------------------------------------------- per-channel reductions
 // grid.x = pixel chunks, block = 256 threads = (C/8 channel groups) x (pixel lanes); each thread strides over
-// pixels of its chunk; fp32 partials per block, fp64 atomics across blocks.
+// the pixels of its chunk four at a time (independent 16-byte loads in flight); fp32 partials per block, fp64
+// atomics across blocks.  The chunk size adapts to the tensor (reduce_geometry) so that small maps still fill
+// the machine.  `out` must be zero on entry; its consumers (finalize / coef / add_sums) clear it again.
 // MODE 0: sum x, sum x^2 (forward statistics)
 // MODE 1: sum dz', sum dz' * xhat with dz' = dz * [z > 0 if relu]   (BN backward)
 template <int MODE>
@@ -53,26 +55,42 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(View x, View dz, View 
 #pragma unroll
     for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = invstd[cg * 8 + e]; }
   }
-  if (ln < lanes) {
-    for (long p = p0 + ln; p < p1; p += lanes) {
-      const F8 xv = ld8(x.ptr + p * x.ps + cg * 8);
-      if (MODE == 0) {
+  constexpr int U = 4;
+  for (long p = p0 + ln; p < p1; p += static_cast<long>(lanes) * U) {
+    F8 xv[U], gv[U], zv[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { a[e] += xv.v[e]; b[e] += xv.v[e] * xv.v[e]; }
-      } else {
-        F8 g = ld8(dz.ptr + p * dz.ps + cg * 8);
-        if (relu) {
-          const F8 zv = ld8(z.ptr + p * z.ps + cg * 8);
+    for (int u = 0; u < U; ++u) {
+      const long q = p + static_cast<long>(u) * lanes;
+      const bool ok = q < p1;
+      const long qq = ok ? q : p;
+      xv[u] = ld8(x.ptr + qq * x.ps + cg * 8);
+      if (MODE == 1) {
+        gv[u] = ld8(dz.ptr + qq * dz.ps + cg * 8);
+        if (relu) zv[u] = ld8(z.ptr + qq * z.ps + cg * 8);
+      }
+      if (!ok) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { a[e] += g.v[e]; b[e] += g.v[e] * (xv.v[e] - mu[e]) * is[e]; }
+        for (int e = 0; e < 8; ++e) { if (MODE == 0) xv[u].v[e] = 0.f; else gv[u].v[e] = 0.f; }
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { red[(ln * groups + cg) * 16 + e] = a[e]; red[(ln * groups + cg) * 16 + 8 + e] = b[e]; }
+    for (int u = 0; u < U; ++u) {
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] += xv[u].v[e]; b[e] += xv[u].v[e] * xv[u].v[e]; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float g = gv[u].v[e];
+          if (relu && !(zv[u].v[e] > 0.f)) g = 0.f;
+          a[e] += g;
+          b[e] += g * (xv[u].v[e] - mu[e]) * is[e];
+        }
+      }
+    }
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { red[(ln * groups + cg) * 16 + e] = a[e]; red[(ln * groups + cg) * 16 + 8 + e] = b[e]; }
   __syncthreads();
   for (int i = threadIdx.x; i < groups * 16; i += blockDim.x) {
     float s = 0.f;
@@ -83,7 +101,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(View x, View dz, View 
 }
 
 // ----------------------------------------------------------------------------- BN finalize (forward)
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps,
                                    float momentum, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ run_mean,
@@ -92,6 +110,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
   if (c >= C) return;
   const double m = sums[c] / count;
   double var = sums[C + c] / count - m * m;
+  sums[c] = 0.0; sums[C + c] = 0.0;   // leave the accumulator clear for the backward reduction
   if (var < 0) var = 0;
   const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   const float g = gamma[c];
@@ -108,24 +127,37 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
   }
 }
 
-// ----------------------------------------------------------------------------- BN backward apply
+// ----------------------------------------------------------------------------- BN backward
 //   dz' = dz * [z > 0]        (relu)
-//   dx  = gamma*invstd * (dz' - sum(dz')/M - xhat * sum(dz' xhat)/M)      (+= if accumulate)
+//   dx  = gamma*invstd * (dz' - sum(dz')/M - xhat * sum(dz' xhat)/M)  =  A*dz' + B*x + D  per channel    (+= if accumulate)
 //   dres (+)= dz'             (residual added before the ReLU)
+// coef kernel: per-channel A, B, D (written over the forward's scale/shift/mean scratch), dgamma/dbeta accumulation,
+// and clears the fp64 accumulator for the next step.
+__global__ void bn_bwd_coef_kernel(double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                                   float* __restrict__ coef /*[3][C]*/, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double sb = sums[c], sg = sums[C + c];
+  sums[c] = 0.0; sums[C + c] = 0.0;
+  if (dgamma) { dbeta[c] += static_cast<float>(sb); dgamma[c] += static_cast<float>(sg); }
+  const double is = invstd[c], A = static_cast<double>(gamma[c]) * is;
+  const double B = -A * is * (sg / count);
+  coef[c] = static_cast<float>(A);
+  coef[C + c] = static_cast<float>(B);
+  coef[2 * C + c] = static_cast<float>(-A * (sb / count) - B * static_cast<double>(mean[c]));
+}
+
+__device__ __forceinline__ void ldc8(const float* p, float* o) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View x, View dz, View z, View dx, View dres,
-                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                           const float* __restrict__ gamma, const double* __restrict__ sums,
-                                                           double count, int relu, int acc_dx, int acc_dres,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                           const float* __restrict__ coef, int relu, int acc_dx,
+                                                           int acc_dres) {
   const int groups = x.C >> 3;
   const long total = static_cast<long>(x.N) * x.H * x.W * groups;
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (blockIdx.x == 0 && dgamma) {
-    for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
-      dbeta[c] += static_cast<float>(sums[c]);
-      dgamma[c] += static_cast<float>(sums[x.C + c]);
-    }
-  }
   if (idx >= total) return;
   const int cg = static_cast<int>(idx % groups);
   const long p = idx / groups;
@@ -146,15 +178,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View x, View dz, View
   }
   if (dx.ptr) {
     const F8 xv = ld8(x.ptr + p * x.ps + cg * 8);
+    float A[8], B[8], D[8];
+    ldc8(coef + cg * 8, A); ldc8(coef + x.C + cg * 8, B); ldc8(coef + 2 * x.C + cg * 8, D);
     F8 o;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = cg * 8 + e;
-      const float is = invstd[c];
-      const float xh = (xv.v[e] - mean[c]) * is;
-      const float sb = static_cast<float>(sums[c] / count), sg = static_cast<float>(sums[x.C + c] / count);
-      o.v[e] = gamma[c] * is * (g.v[e] - sb - xh * sg);
-    }
+    for (int e = 0; e < 8; ++e) o.v[e] = fmaf(A[e], g.v[e], fmaf(B[e], xv.v[e], D[e]));
     if (acc_dx) {
       const F8 old = ld8(dx.ptr + p * dx.ps + cg * 8);
 #pragma unroll
@@ -477,35 +505,40 @@ __global__ void __launch_bounds__(256) lightbag_bwd_kernel(View p, View il, View
   st8(ti.ptr + pix * ti.ps + cg * 8, ot);
 }
 
-__global__ void add_sums_kernel(const double* __restrict__ sums, float* __restrict__ dst, int C) {
+__global__ void add_sums_kernel(double* __restrict__ sums, float* __restrict__ dst, int C, int Cacc) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) dst[c] += static_cast<float>(sums[c]);
+  if (c < 2 * Cacc) sums[c] = 0.0;   // both halves of the [2][Cacc] accumulator
 }
 
 }  // namespace
 
-static int reduce_geometry(const View& x, long& pix_per_block, int& threads, size_t& smem, unsigned& blocks) {
+static int reduce_geometry(const View& x, int num_sms, long& pix_per_block, int& threads, size_t& smem, unsigned& blocks) {
   const int groups = x.C / 8;
-  if (groups < 1 || groups > 256) return -1;
+  if (groups < 1 || groups > 256 || x.C % 8) return -1;
   const int lanes = 256 / groups;
   threads = lanes * groups;
   const long npix = static_cast<long>(x.N) * x.H * x.W;
-  pix_per_block = 2048;
-  blocks = static_cast<unsigned>((npix + pix_per_block - 1) / pix_per_block);
+  // ~4 blocks per SM; at least 8 pixels per lane so the block-level reduction and atomics stay amortised
+  const long target = static_cast<long>(num_sms) * 4;
+  long ppb = (npix + target - 1) / target;
+  const long unit = static_cast<long>(lanes) * 4;
+  if (ppb < 2 * unit) ppb = 2 * unit;
+  ppb = (ppb + unit - 1) / unit * unit;
+  pix_per_block = ppb;
+  blocks = static_cast<unsigned>((npix + ppb - 1) / ppb);
   smem = static_cast<size_t>(threads) * 16 * sizeof(float);
   return 0;
 }
 
-cudaError_t bn_stats_launch(View x, double* sums, cudaStream_t st) {
+cudaError_t bn_stats_launch(View x, double* sums, int num_sms, cudaStream_t st) {
   long ppb; int threads; size_t smem; unsigned blocks;
-  if (reduce_geometry(x, ppb, threads, smem, blocks)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * x.C * sizeof(double), st);
-  if (e != cudaSuccess) return e;
+  if (reduce_geometry(x, num_sms, ppb, threads, smem, blocks)) return cudaErrorInvalidValue;
   chan_reduce_kernel<0><<<blocks, threads, smem, st>>>(x, View{}, View{}, nullptr, nullptr, 0, ppb, sums);
   return cudaGetLastError();
 }
 
-cudaError_t bn_finalize_launch(const double* sums, int C, double count, const float* gamma, const float* beta,
+cudaError_t bn_finalize_launch(double* sums, int C, double count, const float* gamma, const float* beta,
                                const float* conv_bias, float* mean, float* invstd, float* scale, float* shift,
                                float* run_mean, float* run_var, cudaStream_t st) {
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, count, gamma, beta, conv_bias, 1e-5f, 0.1f, mean, invstd,
@@ -514,17 +547,16 @@ cudaError_t bn_finalize_launch(const double* sums, int C, double count, const fl
 }
 
 cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
-                               const float* gamma, double* sums, int relu, int acc_dx, int acc_dres, float* dgamma,
-                               float* dbeta, cudaStream_t st) {
+                               const float* gamma, double* sums, float* coef, int relu, int acc_dx, int acc_dres,
+                               float* dgamma, float* dbeta, int num_sms, cudaStream_t st) {
   long ppb; int threads; size_t smem; unsigned blocks;
-  if (reduce_geometry(x, ppb, threads, smem, blocks)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * x.C * sizeof(double), st);
-  if (e != cudaSuccess) return e;
+  if (reduce_geometry(x, num_sms, ppb, threads, smem, blocks)) return cudaErrorInvalidValue;
   chan_reduce_kernel<1><<<blocks, threads, smem, st>>>(x, dz, z, mean, invstd, relu, ppb, sums);
   const long total = static_cast<long>(x.N) * x.H * x.W * (x.C / 8);
   const double count = static_cast<double>(x.N) * x.H * x.W;
-  bn_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, dz, z, dx, dres, mean, invstd, gamma, sums, count, relu,
-                                                             acc_dx, acc_dres, dgamma, dbeta);
+  bn_bwd_coef_kernel<<<(x.C + 127) / 128, 128, 0, st>>>(sums, x.C, count, gamma, mean, invstd, coef, dgamma, dbeta);
+  if (dx.ptr || dres.ptr)
+    bn_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, dz, z, dx, dres, coef, relu, acc_dx, acc_dres);
   return cudaGetLastError();
 }
 
@@ -589,8 +621,8 @@ cudaError_t lightbag_bwd_launch(View p, View il, View d, View duv, View dp, int 
   return cudaGetLastError();
 }
 
-cudaError_t add_sums_launch(const double* sums, float* dst, int C, cudaStream_t st) {
-  add_sums_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dst, C);
+cudaError_t add_sums_launch(double* sums, float* dst, int C, int Cacc, cudaStream_t st) {
+  add_sums_kernel<<<(2 * Cacc + 127) / 128, 128, 0, st>>>(sums, dst, C, Cacc);
   return cudaGetLastError();
 }
 

@@ -9,18 +9,19 @@ namespace pidnet {
 
 // ---- BatchNorm with batch statistics
 // sums: device double[2*C] scratch (sum, sum of squares | sum dz', sum dz'*xhat)
-cudaError_t bn_stats_launch(View x, double* sums, cudaStream_t st);
+// `sums` must be zero on entry (the arena is cleared at plan time; finalize / backward / add_sums clear it after use)
+cudaError_t bn_stats_launch(View x, double* sums, int num_sms, cudaStream_t st);
 // mean / invstd / folded (scale, shift) for the apply kernel; running stats updated in place when non-null
 // (momentum 0.1, unbiased variance; `conv_bias` is added to the tracked mean for convs whose bias we drop)
-cudaError_t bn_finalize_launch(const double* sums, int C, double count, const float* gamma, const float* beta,
+cudaError_t bn_finalize_launch(double* sums, int C, double count, const float* gamma, const float* beta,
                                const float* conv_bias, float* mean, float* invstd, float* scale, float* shift,
                                float* run_mean, float* run_var, cudaStream_t st);
 // z = act(scale*x + shift (+res)) is the existing upadd kernel (kernels.cuh).  Backward:
 //   dz' = dz*[z>0];  dgamma += sum dz'*xhat;  dbeta += sum dz';  dx (+)= gamma*invstd*(dz' - mean(dz') - xhat*mean(dz'*xhat));
 //   dres (+)= dz'
 cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
-                               const float* gamma, double* sums, int relu, int acc_dx, int acc_dres, float* dgamma,
-                               float* dbeta, cudaStream_t st);
+                               const float* gamma, double* sums, float* coef /*[3*C] scratch*/, int relu, int acc_dx,
+                               int acc_dres, float* dgamma, float* dbeta, int num_sms, cudaStream_t st);
 
 // ---- device-side weight packing: fp32 [Cout][Cin_total][k][k] -> bf16 packed rows (forward: row = co; dgrad: row = ci)
 struct PackJob {
@@ -49,7 +50,7 @@ cudaError_t pag_train_bwd_launch(View x, View xk, View yq, View y, View out, Vie
 cudaError_t lightbag_bwd_launch(View p, View il, View d, View duv, View dp, int acc_dp, View dd, int acc_dd, View ti,
                                 cudaStream_t st);
 // dst[c] += sums[c]  (bias gradients from a per-channel reduction)
-cudaError_t add_sums_launch(const double* sums, float* dst, int C, cudaStream_t st);
+cudaError_t add_sums_launch(double* sums, float* dst, int C, int Cacc, cudaStream_t st);
 
 // ---- wgrad on tcgen05 with MN-major operands (wgrad_tc.cu):
 //   dW[co][ci_off+ci][r][s] += sum_pixels dY[p][co] * X[tap(p)][ci]       (fp32 atomics into the torch-layout gradient)
