@@ -1595,6 +1595,18 @@ int pidnet_train_debug_tensor(pidnet_trainer* h, const char* name, int grad, flo
     dump_nhwc(grad ? t.tt[it->second].g : t.tt[it->second].v, host_out, shape4);
   });
 }
+int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value) {
+  return guard([&] {
+    if (!h || !name) fail("null argument");
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    if (std::string(name) == "use_graph") {
+      t.use_graph = value != 0;
+      t.drop_graphs();
+    } else {
+      fail(std::string("unknown training option '") + name + "'");
+    }
+  });
+}
 int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd) {
   return guard([&] {
     TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;

@@ -26,7 +26,7 @@ class EngineTrainer:
         self.device = dev
         params = [(k, p) for k, p in model.named_parameters()]
         bufs = [(k, b) for k, b in model.named_buffers() if b.dtype.is_floating_point]
-        n_p = sum(p.numel() for _, p in params)
+        n_p = sum((p.numel() + 3) // 4 * 4 for _, p in params)      # every view starts 16-byte aligned
         n_b = sum(b.numel() for _, b in bufs)
         self.flat_param = torch.zeros(n_p + 256, dtype=torch.float32, device=dev)     # +pad: biases are read in tiles of 32
         self.flat_grad = torch.zeros(n_p + 256, dtype=torch.float32, device=dev)
@@ -47,8 +47,6 @@ class EngineTrainer:
                 self.grad_views[k] = g
                 self._bind(k, view, g)
                 off += (n + 3) // 4 * 4
-                if off > n_p + 256 - 4:
-                    off = n_p                                    # keep inside the buffer (alignment padding exhausted)
             off = 0
             for k, b in bufs:
                 n = b.numel()
@@ -98,6 +96,10 @@ class EngineTrainer:
             if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None:
                 m.num_batches_tracked += 1
         return self.out12, outs
+
+    def set_option(self, name, value):
+        """Engine option of the training path: "use_graph" (1 = replay CUDA graphs after the first step)."""
+        _lib.check(self.lib.pidnet_train_set_option(self.h, name.encode(), int(value)))
 
     def debug_tensor(self, name, grad=False):
         shape = (C.c_int64 * 4)()
