@@ -1602,6 +1602,9 @@ int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value) {
     if (std::string(name) == "use_graph") {
       t.use_graph = value != 0;
       t.drop_graphs();
+    } else if (std::string(name) == "overlap_wgrad") {
+      t.overlap_wgrad = value != 0;
+      t.drop_graphs();
     } else {
       fail(std::string("unknown training option '") + name + "'");
     }
@@ -1610,7 +1613,7 @@ int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value) {
 int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd) {
   return guard([&] {
     TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
-    if (fwd) *fwd = static_cast<int>(t.b.ops.size() + t.b.pack_jobs.size());
+    if (fwd) *fwd = static_cast<int>(t.b.ops.size() + 1);   // + the batched weight packing
     if (bwd) *bwd = static_cast<int>(t.bops.size());
   });
 }

@@ -195,10 +195,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View x, View dz, View
 // ----------------------------------------------------------------------------- weight packing
 // dst[row][kofs + (tap_i*chunks + cc)*BK + j] (bf16); forward: row = co, channel = ci; dgrad: row = ci, channel = co
 // and the tap is mirrored.  One thread per destination element of this source's K range.
-__global__ void __launch_bounds__(256) pack_weights_kernel(PackJob j) {
+__device__ __forceinline__ void pack_one(const PackJob& j, long idx) {
   const long per_row = static_cast<long>(j.ntaps) * j.chunks * j.BK;
   const long total = static_cast<long>(j.rows_pad) * per_row;
-  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int row = static_cast<int>(idx / per_row);
   const long k = idx % per_row;
@@ -212,6 +211,19 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackJob j) {
     v = j.src[((static_cast<long>(co) * j.Cin_total + j.ci_off + ci) * j.k + r) * j.k + s];
   }
   j.dst[static_cast<long>(row) * j.Ktot + j.kofs + k] = __float2bfloat16_rn(v);
+}
+__global__ void __launch_bounds__(256) pack_weights_kernel(PackJob j) {
+  pack_one(j, static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x);
+}
+// all jobs of a step in one launch: block_start[i] = first block of job i (block_start[njobs] = grid size)
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs, const unsigned* __restrict__ block_start,
+                                                       int njobs) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {   // last job whose first block is <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (block_start[mid] <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  pack_one(jobs[lo], static_cast<long>(blockIdx.x - block_start[lo]) * blockDim.x + threadIdx.x);
 }
 
 // ----------------------------------------------------------------------------- layout converters
@@ -563,6 +575,16 @@ cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, cons
 cudaError_t pack_weights_launch(const PackJob& j, cudaStream_t st) {
   const long total = static_cast<long>(j.rows_pad) * j.ntaps * j.chunks * j.BK;
   pack_weights_kernel<<<blocks_for(total, 256), 256, 0, st>>>(j);
+  return cudaGetLastError();
+}
+
+unsigned pack_job_blocks(const PackJob& j) {
+  return blocks_for(static_cast<long>(j.rows_pad) * j.ntaps * j.chunks * j.BK, 256);
+}
+cudaError_t pack_all_launch(const PackJob* dev_jobs, const unsigned* dev_block_start, int njobs, unsigned total_blocks,
+                            cudaStream_t st) {
+  if (njobs <= 0) return cudaSuccess;
+  pack_all_kernel<<<total_blocks, 256, 0, st>>>(dev_jobs, dev_block_start, njobs);
   return cudaGetLastError();
 }
 

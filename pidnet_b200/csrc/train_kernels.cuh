@@ -35,6 +35,10 @@ struct PackJob {
   unsigned char taps[9];  // (r << 4) | s of the SOURCE weight tap feeding destination tap i
 };
 cudaError_t pack_weights_launch(const PackJob& j, cudaStream_t st);
+// batched form: job table + first-block prefix in device memory, one launch for every conv of the step
+unsigned pack_job_blocks(const PackJob& j);
+cudaError_t pack_all_launch(const PackJob* dev_jobs, const unsigned* dev_block_start, int njobs, unsigned total_blocks,
+                            cudaStream_t st);
 
 cudaError_t nchw_to_nhwc_launch(const float* x, int N, int C, int H, int W, View out, cudaStream_t st);
 // dlow (+)= U^T dhi  (bilinear, align_corners=False);  dx (+)= P^T dy (AvgPool count_include_pad; k==0 global)

@@ -14,10 +14,12 @@ namespace pidnet {
 namespace {
 
 constexpr int kWgThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer (+TMEM), warps 2..5: epilogue
-constexpr int kWgStages = 4;
+// pipeline depth per taps-per-CTA variant: stage = (2 + T) * 8 KB, kept under the 227 KB limit
+template <int T> struct WgStages { static constexpr int value = T == 1 ? 8 : 5; };
 
 template <int T>  // taps per CTA (1 or 3)
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int kWgStages = WgStages<T>::value;
   constexpr int kABytes = 2 * 8192, kBBytes = T * 8192, kStageBytes = kABytes + kBBytes;
   constexpr int kCols = T == 1 ? 64 : 256;
   extern __shared__ uint8_t smem_raw[];
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 }
 
 template <int T>
-size_t wg_smem() { return static_cast<size_t>(kWgStages) * (2 * 8192 + T * 8192) + 256 + 1024; }
+size_t wg_smem() { return static_cast<size_t>(WgStages<T>::value) * (2 * 8192 + T * 8192) + 256 + 1024; }
 
 }  // namespace
 
