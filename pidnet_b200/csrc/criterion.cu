@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cfloat>
+#include <algorithm>
 #include "criterion.cuh"
 
 namespace pidnet {
@@ -499,6 +500,335 @@ __global__ void __launch_bounds__(256) crit_backward_tiled_kernel(CritParams p, 
   }
 }
 
+// --------------------------------------------------------------------------------------- run kernels
+// Fast path of both passes when the low-res footprint of a 256 x 8 label tile fits shared memory (always the case
+// for the x8 heads): every thread owns a RUN of 8 consecutive label pixels of one row.
+//  * the low-res logits of the tile footprint are staged in smem once (LDS instead of 4 global loads per class);
+//  * the interpolation is one 4-term dot product with per-pixel weights (same value as torch's two-stage lerp up
+//    to fp32 rounding), the softmax uses ex2 on pre-scaled arguments;
+//  * backward: the 8 pixels of a run share their left low-res column (or switch once), so the transposed
+//    interpolation is accumulated in REGISTERS and flushed to the smem gradient tile at most twice per run --
+//    lanes of a warp are 8 pixels (~1 low-res column) apart and therefore hit distinct addresses.
+constexpr int kPX = 8, kRW = 32 * kPX, kRH = 8, kRLW = 36, kRLH = 4, kRLP = kRLW * kRLH;
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+struct RunTile {
+  int n, ty, tx, ly0, lx0;
+};
+__device__ __forceinline__ RunTile run_tile(const CritParams& p) {
+  RunTile t;
+  const int tiles_x = (p.W + kRW - 1) / kRW, tiles_y = (p.H + kRH - 1) / kRH;
+  t.n = blockIdx.x / (tiles_x * tiles_y);
+  const int rem = blockIdx.x - t.n * tiles_x * tiles_y;
+  t.ty = rem / tiles_x;
+  t.tx = rem - t.ty * tiles_x;
+  t.ly0 = lerp_ac(t.ty * kRH, p.h, p.H).i0;
+  t.lx0 = lerp_ac(t.tx * kRW, p.w, p.W).i0;
+  return t;
+}
+// lo[ch][kRLH][kRLW]: [0,C) aux head, [C,2C) main head, 2C boundary
+__device__ __forceinline__ void stage_lowres(const CritParams& p, const RunTile& t, float* lo, float* zero) {
+  const int CH = 2 * p.C + 1;
+  const size_t plane = static_cast<size_t>(p.h) * p.w;
+  for (int i = threadIdx.x; i < CH * kRLP; i += blockDim.x) {
+    const int ch = i / kRLP, r = i - ch * kRLP;
+    const int ly = min(t.ly0 + r / kRLW, p.h - 1), lx = min(t.lx0 + r % kRLW, p.w - 1);
+    const float* src = ch < p.C ? p.x_p + (static_cast<size_t>(t.n) * p.C + ch) * plane
+                                : (ch < 2 * p.C ? p.x_m + (static_cast<size_t>(t.n) * p.C + (ch - p.C)) * plane
+                                                : p.x_d + static_cast<size_t>(t.n) * plane);
+    lo[i] = __ldg(src + static_cast<size_t>(ly) * p.w + lx);
+    if (zero) zero[i] = 0.f;
+  }
+}
+
+// forward: lane l of warp w handles pixels x = tile_x0 + l + 32 j (j = 0..7) of row w -- coalesced IO, rolled loop
+template <int CMAX>
+__global__ void __launch_bounds__(256) crit_pixel_run_kernel(CritParams p) {
+  extern __shared__ float lo[];
+  __shared__ double red[A_NLT2 + 1][8];
+  const RunTile t = run_tile(p);
+  stage_lowres(p, t, lo, nullptr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int y = t.ty * kRH + warp;
+  float acc[A_NLT2 + 1];
+#pragma unroll
+  for (int i = 0; i <= A_NLT2; ++i) acc[i] = 0.f;
+  if (y < p.H) {
+    const Lerp ly = lerp_ac(y, p.h, p.H);
+    const int r0 = (ly.i0 - t.ly0) * kRLW - t.lx0, r1 = (ly.i1 - t.ly0) * kRLW - t.lx0;
+    const float wy0 = 1.f - ly.l, wy1 = ly.l;
+    const long row = (static_cast<long>(t.n) * p.H + y) * p.W;
+#pragma unroll 1
+    for (int j = 0; j < kPX; ++j) {
+      const int x = t.tx * kRW + j * 32 + lane;
+      if (x >= p.W) break;
+      const long pix = row + x;
+      const Lerp lx = lerp_ac(x, p.w, p.W);
+      const float w00 = wy0 * (1.f - lx.l), w01 = wy0 * lx.l, w10 = wy1 * (1.f - lx.l), w11 = wy1 * lx.l;
+      const int a00 = r0 + lx.i0, a01 = r0 + lx.i1, a10 = r1 + lx.i0, a11 = r1 + lx.i1;
+      auto value = [&](int ch) {
+        const float* q = lo + ch * kRLP;
+        return fmaf(w00, q[a00], fmaf(w01, q[a01], fmaf(w10, q[a10], w11 * q[a11])));
+      };
+      const long t64 = p.labels[pix];
+      const bool valid1 = t64 != p.ignore_label;
+      const int tg = valid1 ? static_cast<int>(t64) : 0;
+      float v[CMAX];
+      float mx = -FLT_MAX, vt = 0.f;
+      int amax = 0;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < p.C) {
+          v[k] = value(p.C + k);
+          if (v[k] > mx) { mx = v[k]; amax = k; }
+          if (k == tg) vt = v[k];
+        }
+      }
+      float se = 0.f;
+      const float mxs = -mx * kLog2e;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) if (k < p.C) se += ex2f(fmaf(v[k], kLog2e, mxs));
+      const float lse = mx + logf(se);
+      const float wt = (valid1 && p.class_w) ? __ldg(p.class_w + tg) : 1.f;
+      const float pm = expf(vt - lse);
+      if (static_cast<long>(amax) == t64) acc[A_ACC] += 1.f;   // pixel_acc counts every pixel (label >= 0), utils.py:31
+      if (valid1) {
+        float mp = -FLT_MAX, vtp = 0.f, sp = 0.f;
+#pragma unroll
+        for (int k = 0; k < CMAX; ++k) {
+          if (k < p.C) {
+            v[k] = value(k);
+            mp = fmaxf(mp, v[k]);
+            if (k == tg) vtp = v[k];
+          }
+        }
+        const float mps = -mp * kLog2e;
+#pragma unroll
+        for (int k = 0; k < CMAX; ++k) if (k < p.C) sp += ex2f(fmaf(v[k], kLog2e, mps));
+        acc[A_CE_P] += wt * (mp + logf(sp) - vtp);
+      }
+      const float xd = value(2 * p.C);
+      const float z = p.bd_gt[pix];
+      const float bce = fmaxf(xd, 0.f) - xd * z + log1pf(expf(-fabsf(xd)));
+      if (z == 1.f) { acc[A_BCE_POS] += bce; acc[A_NPOS] += 1.f; }
+      else if (z == 0.f) { acc[A_BCE_NEG] += bce; acc[A_NNEG] += 1.f; }
+      const float sg = 1.f / (1.f + expf(-xd));
+      const bool valid2 = valid1 && sg > p.bd_threshold;
+      if (valid1) { acc[A_NV1] += 1.f; if (pm < p.ohem_thres) acc[A_NLT1] += 1.f; }
+      if (valid2) { acc[A_NV2] += 1.f; if (pm < p.ohem_thres) acc[A_NLT2] += 1.f; }
+      p.ws_p[pix] = pm;
+      p.ws_ce[pix] = wt * (lse - vt);
+      p.ws_flags[pix] = static_cast<unsigned char>((valid1 ? 1 : 0) | (valid2 ? 2 : 0));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i <= A_NLT2; ++i) {
+    const float v = warp_sum_f(acc[i]);
+    if (lane == 0) red[i][warp] = static_cast<double>(v);
+  }
+  __syncthreads();
+  if (threadIdx.x <= A_NLT2) {
+    double v = 0.0;
+    for (int q = 0; q < 8; ++q) v += red[threadIdx.x][q];
+    if (v != 0.0) atomicAdd(p.accum + threadIdx.x, v);
+  }
+}
+
+// backward.  Phase 1 (coalesced): per pixel a code word {target | kept-by-OHEM-1 | kept-by-OHEM-2 | valid} and the
+// boundary target go to smem (row stride 32*9 so the run phase reads conflict-free).  Phase 2: every thread owns the
+// run x = tile_x0 + 8 lane + j; loops over heads and pixels are rolled (the unrolled form thrashed the I-cache).
+constexpr int kRS = 32 * (kPX + 1);   // padded smem row: pixel (lane, j) at lane * 9 + j
+template <int CMAX>
+__global__ void __launch_bounds__(256, CMAX <= 20 ? 2 : 1) crit_backward_run_kernel(CritParams p, const SelState* st) {
+  extern __shared__ float sm[];
+  const int CH = 2 * p.C + 1;
+  float* lo = sm;
+  float* tile = sm + CH * kRLP;
+  int* s_code = reinterpret_cast<int*>(tile + CH * kRLP);   // [kRH][kRS]
+  float* s_z = reinterpret_cast<float*>(s_code + kRH * kRS);
+  const RunTile t = run_tile(p);
+  stage_lowres(p, t, lo, tile);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int y = t.ty * kRH + warp;
+  const float thr0 = st->thr[0], thr1 = st->thr[1];
+  if (y < p.H) {
+    const long row = (static_cast<long>(t.n) * p.H + y) * p.W;
+#pragma unroll
+    for (int i = 0; i < kPX; ++i) {
+      const int xl = i * 32 + lane, x = t.tx * kRW + xl;   // pixel xl of the tile row = (lane' = xl / 8, j = xl % 8)
+      int code = 0;
+      float z = -1.f;
+      if (x < p.W) {
+        const unsigned f = p.ws_flags[row + x];
+        z = p.bd_gt[row + x];
+        if (f & 1) {
+          const float pm = p.ws_p[row + x];
+          code = (static_cast<int>(p.labels[row + x]) & 0xFF) | 0x400;
+          if (pm < thr0) code |= 0x100;
+          if ((f & 2) && pm < thr1) code |= 0x200;
+        }
+      }
+      const int slot = warp * kRS + (xl >> 3) * (kPX + 1) + (xl & 7);
+      s_code[slot] = code;
+      s_z[slot] = z;
+    }
+  }
+  __syncthreads();
+  const int x0 = t.tx * kRW + lane * kPX;
+  if (y < p.H && x0 < p.W) {
+    const Lerp ly = lerp_ac(y, p.h, p.H);
+    const int r0 = (ly.i0 - t.ly0) * kRLW - t.lx0, r1 = (ly.i1 - t.ly0) * kRLW - t.lx0;
+    const float wy0 = 1.f - ly.l, wy1 = ly.l;
+    const double nhw = static_cast<double>(p.N) * p.H * p.W;
+    const float c_k1 = static_cast<float>(p.bw1 / p.accum[A_K1]), c_k2 = static_cast<float>(p.sb / p.accum[A_K2]);
+    const float c_aux = static_cast<float>(p.bw0 / nhw);
+    const int* my_code = s_code + warp * kRS + lane * (kPX + 1);
+    const float* my_z = s_z + warp * kRS + lane * (kPX + 1);
+    const int npx = min(kPX, p.W - x0);
+    float a0[CMAX], a1[CMAX];
+#pragma unroll 1
+    for (int hd = 0; hd < 2; ++hd) {   // 0: main head (OHEM coefficients), 1: aux head
+      const int ch0 = hd == 0 ? p.C : 0;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) a0[k] = a1[k] = 0.f;
+      int cur = -1;
+      auto flush = [&](int col) {
+        const int c1 = min(col + 1, p.w - 1);
+#pragma unroll
+        for (int k = 0; k < CMAX; ++k) {
+          if (k < p.C) {
+            float* tb = tile + (ch0 + k) * kRLP;
+            if (a0[k] != 0.f) { atomicAdd(tb + r0 + col, a0[k] * wy0); atomicAdd(tb + r1 + col, a0[k] * wy1); }
+            if (a1[k] != 0.f) { atomicAdd(tb + r0 + c1, a1[k] * wy0); atomicAdd(tb + r1 + c1, a1[k] * wy1); }
+            a0[k] = a1[k] = 0.f;
+          }
+        }
+      };
+#pragma unroll 1
+      for (int j = 0; j < npx; ++j) {
+        const int code = my_code[j];
+        if (!(code & 0x400)) continue;
+        const int tg = code & 0xFF;
+        const float wt = p.class_w ? __ldg(p.class_w + tg) : 1.f;
+        const float cf = wt * (hd == 0 ? ((code & 0x100) ? c_k1 : 0.f) + ((code & 0x200) ? c_k2 : 0.f) : c_aux);
+        if (cf == 0.f) continue;
+        const Lerp lx = lerp_ac(x0 + j, p.w, p.W);
+        if (lx.i0 != cur) {
+          if (cur >= 0) flush(cur);
+          cur = lx.i0;
+        }
+        const float w00 = wy0 * (1.f - lx.l), w01 = wy0 * lx.l, w10 = wy1 * (1.f - lx.l), w11 = wy1 * lx.l;
+        const int a00 = r0 + lx.i0, a01 = r0 + lx.i1, a10 = r1 + lx.i0, a11 = r1 + lx.i1;
+        float v[CMAX];
+        float mx = -FLT_MAX, se = 0.f;
+#pragma unroll
+        for (int k = 0; k < CMAX; ++k) {
+          if (k < p.C) {
+            const float* q = lo + (ch0 + k) * kRLP;
+            v[k] = fmaf(w00, q[a00], fmaf(w01, q[a01], fmaf(w10, q[a10], w11 * q[a11])));
+            mx = fmaxf(mx, v[k]);
+          }
+        }
+        const float mxs = -mx * kLog2e;
+#pragma unroll
+        for (int k = 0; k < CMAX; ++k) if (k < p.C) { v[k] = ex2f(fmaf(v[k], kLog2e, mxs)); se += v[k]; }
+        const float sc = cf / se, g0 = 1.f - lx.l, g1 = lx.l;
+#pragma unroll
+        for (int k = 0; k < CMAX; ++k) {
+          if (k < p.C) {
+            const float g = fmaf(v[k], sc, k == tg ? -cf : 0.f);
+            a0[k] = fmaf(g, g0, a0[k]);
+            a1[k] = fmaf(g, g1, a1[k]);
+          }
+        }
+      }
+      if (cur >= 0) flush(cur);
+    }
+    // boundary head (one channel): same run accumulation
+    {
+      const double nb = p.accum[A_NPOS] + p.accum[A_NNEG];
+      const float om_pos = static_cast<float>(p.accum[A_NNEG] / nb), om_neg = static_cast<float>(p.accum[A_NPOS] / nb);
+      const float c_bce = static_cast<float>(p.coeff_bce / nhw);
+      float b0 = 0.f, b1 = 0.f;
+      int cur = -1;
+      float* tb = tile + 2 * p.C * kRLP;
+      const float* q = lo + 2 * p.C * kRLP;
+      auto flush = [&](int col) {
+        const int c1 = min(col + 1, p.w - 1);
+        if (b0 != 0.f) { atomicAdd(tb + r0 + col, b0 * wy0); atomicAdd(tb + r1 + col, b0 * wy1); }
+        if (b1 != 0.f) { atomicAdd(tb + r0 + c1, b1 * wy0); atomicAdd(tb + r1 + c1, b1 * wy1); }
+        b0 = b1 = 0.f;
+      };
+#pragma unroll 1
+      for (int j = 0; j < npx; ++j) {
+        const float z = my_z[j];
+        const float om = z == 1.f ? om_pos : (z == 0.f ? om_neg : 0.f);
+        if (om == 0.f) continue;
+        const Lerp lx = lerp_ac(x0 + j, p.w, p.W);
+        if (lx.i0 != cur) {
+          if (cur >= 0) flush(cur);
+          cur = lx.i0;
+        }
+        const float w00 = wy0 * (1.f - lx.l), w01 = wy0 * lx.l, w10 = wy1 * (1.f - lx.l), w11 = wy1 * lx.l;
+        const float xd = fmaf(w00, q[r0 + lx.i0], fmaf(w01, q[r0 + lx.i1], fmaf(w10, q[r1 + lx.i0], w11 * q[r1 + lx.i1])));
+        const float sg = 1.f / (1.f + __expf(-xd));
+        const float g = c_bce * om * (sg - z);
+        b0 = fmaf(g, 1.f - lx.l, b0);
+        b1 = fmaf(g, lx.l, b1);
+      }
+      if (cur >= 0) flush(cur);
+    }
+  }
+  __syncthreads();
+  const size_t plane = static_cast<size_t>(p.h) * p.w;
+  for (int i = threadIdx.x; i < CH * kRLP; i += blockDim.x) {
+    const float g = tile[i];
+    if (g == 0.f) continue;
+    const int ch = i / kRLP, r = i - ch * kRLP;
+    const int gy = t.ly0 + r / kRLW, gx = t.lx0 + r % kRLW;
+    if (gy >= p.h || gx >= p.w) continue;
+    float* dst = ch < p.C ? p.g_p + (static_cast<size_t>(t.n) * p.C + ch) * plane
+                          : (ch < 2 * p.C ? p.g_m + (static_cast<size_t>(t.n) * p.C + (ch - p.C)) * plane
+                                          : p.g_d + static_cast<size_t>(t.n) * plane);
+    atomicAdd(dst + static_cast<size_t>(gy) * p.w + gx, g);
+  }
+}
+
+// does the low-res footprint of a (tw x th) label tile fit a (lw x lh) staging tile?
+inline bool footprint_fits(const CritParams& p, int tw, int th, int lw, int lh) {
+  auto span = [](int t, int in, int out) { return out > 1 ? (static_cast<long>(t - 1) * (in - 1)) / (out - 1) + 3 : 1; };
+  const long sw = std::min<long>(span(std::min(tw, p.W), p.w, p.W), p.w), sh = std::min<long>(span(std::min(th, p.H), p.h, p.H), p.h);
+  return sw <= lw && sh <= lh;
+}
+template <int CMAX>
+cudaError_t launch_run_kernels(const CritParams& p, const SelState* sel, bool backward, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>(p.N) * ((p.W + kRW - 1) / kRW) * ((p.H + kRH - 1) / kRH);
+  const size_t lo_bytes = static_cast<size_t>(2 * p.C + 1) * kRLP * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    const int max_bytes = (2 * CMAX + 1) * kRLP * static_cast<int>(sizeof(float));
+    cudaError_t e = cudaFuncSetAttribute(crit_pixel_run_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(crit_backward_run_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             2 * max_bytes + 2 * kRH * kRS * 4);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  if (!backward) crit_pixel_run_kernel<CMAX><<<blocks, 256, lo_bytes, st>>>(p);
+  else crit_backward_run_kernel<CMAX><<<blocks, 256, 2 * lo_bytes + 2 * kRH * kRS * 4, st>>>(p, sel);
+  return cudaGetLastError();
+}
+cudaError_t launch_run(const CritParams& p, const SelState* sel, bool backward, cudaStream_t st) {
+  if (p.C <= 12) return launch_run_kernels<12>(p, sel, backward, st);
+  if (p.C <= 20) return launch_run_kernels<20>(p, sel, backward, st);
+  return launch_run_kernels<kMaxC>(p, sel, backward, st);
+}
+
 // --------------------------------------------------------------------------------------- x8 upsample (returned outputs)
 __global__ void __launch_bounds__(256) upsample_ac_kernel(const float* __restrict__ x, int NC, int h, int w,
                                                           float* __restrict__ out, int H, int W) {
@@ -538,7 +868,9 @@ cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaS
   cudaError_t e;
   if ((e = cudaMemsetAsync(p.accum, 0, A_COUNT * sizeof(double) + 512 + 2 * 4096 * sizeof(unsigned) + 256, st)) != cudaSuccess) return e;
   const unsigned blocks = static_cast<unsigned>((npix + 255) / 256);
-  if (p.C <= 12) crit_pixel_kernel<12><<<blocks, 256, 0, st>>>(p);
+  const bool run_path = footprint_fits(p, kRW, kRH, kRLW, kRLH);
+  if (run_path) { if ((e = launch_run(p, nullptr, false, st)) != cudaSuccess) return e; }
+  else if (p.C <= 12) crit_pixel_kernel<12><<<blocks, 256, 0, st>>>(p);
   else if (p.C <= 20) crit_pixel_kernel<20><<<blocks, 256, 0, st>>>(p);
   else crit_pixel_kernel<kMaxC><<<blocks, 256, 0, st>>>(p);
   crit_select_init_kernel<<<1, 32, 0, st>>>(p, sel);
@@ -557,6 +889,7 @@ cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaS
     if ((e = cudaMemsetAsync(p.g_p, 0, lowres * p.C * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p.g_m, 0, lowres * p.C * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p.g_d, 0, lowres * 4, st)) != cudaSuccess) return e;
+    if (run_path) return launch_run(p, sel, true, st);
     const int tiles = ((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
     // low-res footprint of a 32 x 8 label tile (+1 for the i1 neighbour, +1 for the fractional start)
     auto span = [](int t, int in, int out) { return out > 1 ? (static_cast<long>(t - 1) * (in - 1)) / (out - 1) + 3 : 1; };
