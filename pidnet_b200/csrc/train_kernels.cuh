@@ -66,7 +66,9 @@ struct WgradParams {
   int tiles_w, tiles_h, N;         // 8x8-pixel tiles of the OUTPUT grid
   int Cout, Cin, Cin_total, ci_off, k;
   float* dW;                       // [Cout][Cin_total][k][k] fp32
+  float* ws;                       // split-K partials: [split][co tile][z][128 rows][T taps][64 ci] fp32
 };
+constexpr int kWgradTileFloats = 128 * 64;   // per tap
 struct WgradLaunch {
   WgradParams p;
   dim3 grid;  // (pixel splits, co tiles, ci tiles * tap groups)

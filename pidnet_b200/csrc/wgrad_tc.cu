@@ -5,8 +5,10 @@
 // (64 rows of 128 B, SWIZZLE_128B; descriptor: SBO = 1024 B per 8 pixel rows, LBO = 8192 B between 64-channel
 // blocks -- verified by the probe in probe.cu).  The pixel dimension is the GEMM K: each CTA owns a (co tile,
 // ci tile, tap group) and a strided subset of the pixel tiles (split-K), keeps one fp32 accumulator per tap in
-// TMEM for its whole life, and finally adds its partial to the fp32 gradient with atomics.  Stride-2 convs use
-// the same parity tensor maps as the forward kernel; zero padding / ragged tiles are TMA out-of-bounds fills.
+// TMEM for its whole life, and finally stores its partial tile to a workspace with plain vector stores; a small
+// second kernel sums the split-K partials into the torch-layout gradient (scattered fp32 atomics from every CTA
+// were the bottleneck of the first version: up to 7 M atomics per layer).  Stride-2 convs use the same parity
+// tensor maps as the forward kernel; zero padding / ragged tiles are TMA out-of-bounds fills.
 #include "train_kernels.cuh"
 #include "ptx.cuh"
 
@@ -113,22 +115,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const int co = co0 + q * 32 + lane;
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    const int kk = p.k * p.k;
+    // partial tile of this CTA: [row = co within the tile][tap j][64 ci]
+    float* tile = p.ws + ((static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * gridDim.z + blockIdx.z) *
+                             (static_cast<size_t>(T) * kWgradTileFloats);
+    const int nci = min(64, p.Cin - ci0);
     for (int j = 0; j < ntap; ++j) {
-      const uint32_t tp = p.taps[tap0 + j];
-      const int r = (tp >> 24) & 0xF, s = (tp >> 28) & 0xF;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
+        if (g * 32 >= nci) break;   // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem + j * 64 + g * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
         tmem_ld_wait();
         if (co < p.Cout) {
-          float* row = p.dW + (static_cast<size_t>(co) * p.Cin_total + p.ci_off) * kk + r * p.k + s;
+          float4* dst = reinterpret_cast<float4*>(tile + (static_cast<size_t>(q * 32 + lane) * T + j) * 64 + g * 32);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int ci = ci0 + g * 32 + e;
-            if (ci < p.Cin) atomicAdd(row + static_cast<size_t>(ci) * kk, __uint_as_float(v[e]));
-          }
+          for (int e = 0; e < 8; ++e)
+            dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                 __uint_as_float(v[4 * e + 3]));
         }
       }
     }
@@ -137,6 +140,32 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kCols>(tmem);
+}
+
+// dW[co][ci_off + ci][r][s] += sum over splits of the partial tiles (one thread per gradient element)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(WgradParams p, int T, int splits, int co_tiles, int nz) {
+  const long total = static_cast<long>(p.Cout) * p.ntaps * p.Cin;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ci = static_cast<int>(idx % p.Cin);
+  const int tapi = static_cast<int>((idx / p.Cin) % p.ntaps);
+  const int co = static_cast<int>(idx / (static_cast<long>(p.Cin) * p.ntaps));
+  const int ngroups = (p.ntaps + T - 1) / T;
+  const int z = (ci >> 6) * ngroups + tapi / T, j = tapi % T;
+  const size_t tile_floats = static_cast<size_t>(T) * kWgradTileFloats;
+  const float* src = p.ws + (static_cast<size_t>(co >> 7) * nz + z) * tile_floats +
+                     (static_cast<size_t>(co & 127) * T + j) * 64 + (ci & 63);
+  const size_t split_stride = static_cast<size_t>(co_tiles) * nz * tile_floats;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int sp = 0;
+  for (; sp + 4 <= splits; sp += 4) {
+    s0 += src[(sp + 0) * split_stride]; s1 += src[(sp + 1) * split_stride];
+    s2 += src[(sp + 2) * split_stride]; s3 += src[(sp + 3) * split_stride];
+  }
+  for (; sp < splits; ++sp) s0 += src[sp * split_stride];
+  const uint32_t tp = p.taps[tapi];
+  const int r = (tp >> 24) & 0xF, s = (tp >> 28) & 0xF;
+  p.dW[(static_cast<size_t>(co) * p.Cin_total + p.ci_off + ci) * (p.k * p.k) + r * p.k + s] += (s0 + s1) + (s2 + s3);
 }
 
 template <int T>
@@ -155,6 +184,11 @@ cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
   if (L.taps_per_group == 1) wgrad_tc_kernel<1><<<L.grid, kWgThreads, wg_smem<1>(), st>>>(L.p);
   else if (L.taps_per_group == 3) wgrad_tc_kernel<3><<<L.grid, kWgThreads, wg_smem<3>(), st>>>(L.p);
   else return cudaErrorInvalidValue;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const long total = static_cast<long>(L.p.Cout) * L.p.ntaps * L.p.Cin;
+  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(L.p, L.taps_per_group, static_cast<int>(L.grid.x),
+                                                                                static_cast<int>(L.grid.y), static_cast<int>(L.grid.z));
   return cudaGetLastError();
 }
 

@@ -55,6 +55,13 @@ class EngineTrainer:
                 b.data = view
                 self._bind(k, view, None)
                 off += n
+            # BatchNorm step counters: one flat int64 buffer, so the per-step increment is ONE launch
+            nbt = [m.num_batches_tracked for m in model.modules()
+                   if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None]
+            self.flat_nbt = torch.zeros(max(len(nbt), 1), dtype=torch.int64, device=dev)
+            for i, b in enumerate(nbt):
+                self.flat_nbt[i] = b
+                b.data = self.flat_nbt[i]
         self.n_param = n_p
         self.planned = None
         self.out12 = torch.zeros(12, dtype=torch.float32, device=dev)
@@ -92,9 +99,7 @@ class EngineTrainer:
             cw = class_weights.to(self.device, torch.float32).contiguous() if class_weights is not None else None
             _lib.check(self.lib.pidnet_train_step(self.h, C.c_void_p(stream), p(x), p(labels), p(bd_gt), p(cw), C.byref(crit_cfg),
                                                   int(backward), p(self.out12), p(outs[1]), p(outs[0]), p(outs[2])))
-        for m in self.model.modules():
-            if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None:
-                m.num_batches_tracked += 1
+        self.flat_nbt += 1                                      # nn.BatchNorm2d.num_batches_tracked of every layer
         return self.out12, outs
 
     def set_option(self, name, value):

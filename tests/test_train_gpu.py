@@ -117,6 +117,7 @@ def test_graph_replay_matches_eager_steps():
             out12, _ = tr.step(x, lab, bd, None, cc, backward=True, want_logits=False)
             losses.append(out12.clone())
         torch.cuda.synchronize()
+        assert int(model.conv1[1].num_batches_tracked) == 3 and int(model.state_dict()['spp.scale0.0.num_batches_tracked']) == 3
         res[run] = (torch.stack(losses).cpu(), tr.flat_grad.clone().cpu(), tr.flat_buf.clone().cpu())
     assert torch.allclose(res['graph'][0], res['eager'][0], rtol=1e-4, atol=1e-5), (res['graph'][0], res['eager'][0])
     assert torch.allclose(res['graph'][2], res['eager'][2], rtol=1e-4, atol=1e-6)
