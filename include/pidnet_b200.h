@@ -167,7 +167,8 @@ int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x_nchw, cons
                       float* out_main, float* out_p, float* out_d);
 int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd);
 /* options: "use_graph" 1 (default: the step replays two CUDA graphs after one eager step) | 0 (eager launches);
- *          "overlap_wgrad" 1 (default: weight-gradient GEMMs run on a side stream next to the dgrad chain) | 0 */
+ *          "overlap_wgrad" 1 (default: weight-gradient GEMMs run on a side stream next to the dgrad chain) | 0;
+ *          "fused_bn" 1 (default: single-launch BatchNorm kernels with a grid barrier) | 0 (3-kernel form; re-plan) */
 int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value);
 int pidnet_train_profile(pidnet_trainer* h, void* stream, const float* x_nchw, const int64_t* labels, const float* bd_gt,
                          const float* class_weights, const pidnet_criterion_cfg* cfg, char* buf, size_t cap, float* crit_ms);

@@ -3,6 +3,7 @@
 // K-major layouts of the conv kernels, forward and dgrad orientation), layout converters and the transposes
 // of the bilinear-upsample / average-pool operators.  Reference semantics: nn.BatchNorm2d(momentum=0.1,
 // eps=1e-5) in train mode (models/model_utils.py:8-9), SURVEY.md Appendix H.
+#include <cstdio>
 #include "train_kernels.cuh"
 
 namespace pidnet {
@@ -18,6 +19,14 @@ __device__ __forceinline__ F8 ld8(const bf16* p) {
   r.v[6] = __uint_as_float(u.w << 16); r.v[7] = __uint_as_float(u.w & 0xFFFF0000u);
   return r;
 }
+__device__ __forceinline__ F8 unpack8(const uint4& u) {
+  F8 r;
+  r.v[0] = __uint_as_float(u.x << 16); r.v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  r.v[2] = __uint_as_float(u.y << 16); r.v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  r.v[4] = __uint_as_float(u.z << 16); r.v[5] = __uint_as_float(u.z & 0xFFFF0000u);
+  r.v[6] = __uint_as_float(u.w << 16); r.v[7] = __uint_as_float(u.w & 0xFFFF0000u);
+  return r;
+}
 __device__ __forceinline__ uint32_t pk(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -26,6 +35,11 @@ __device__ __forceinline__ void st8(bf16* p, const F8& f) {
   uint4 o;
   o.x = pk(f.v[0], f.v[1]); o.y = pk(f.v[2], f.v[3]); o.z = pk(f.v[4], f.v[5]); o.w = pk(f.v[6], f.v[7]);
   *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ uint4 pack8(const F8& f) {
+  uint4 o;
+  o.x = pk(f.v[0], f.v[1]); o.y = pk(f.v[2], f.v[3]); o.z = pk(f.v[4], f.v[5]); o.w = pk(f.v[6], f.v[7]);
+  return o;
 }
 inline unsigned blocks_for(long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
@@ -189,6 +203,275 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View x, View dz, View
       for (int e = 0; e < 8; ++e) o.v[e] += old.v[e];
     }
     st8(dx.ptr + p * dx.ps + cg * 8, o);
+  }
+}
+
+// ----------------------------------------------------------------------------- fused single-launch BatchNorm
+// One persistent launch per BatchNorm (forward or backward): phase 1 streams the block's pixel range once,
+// accumulating the per-channel statistics and parking the loaded vectors in shared memory; a grid barrier; phase 2
+// derives the per-channel coefficients and applies them to the parked data (re-reading from L2/HBM only what did not
+// fit).  Versus the three-kernel form this removes one full read pass (forward) / three (backward) and two launches.
+// The grid is sized to be co-resident (2 blocks of 512 threads per SM); blocks of other streams that temporarily
+// hold an SM always terminate on their own, so the barrier cannot deadlock; the spin is bounded and traps.
+constexpr int kBnThreads = 384;   // 2 blocks x 384 threads x 64 regs leave register room for a co-resident wgrad CTA
+constexpr int kBnRedMin = kBnThreads * 4;                    // block reduction scratch: four rounds of 512 x 4 values
+__host__ __device__ inline int bn_red_floats(int C) { return 3 * C > kBnRedMin ? (3 * C + 3) / 4 * 4 : kBnRedMin; }   // also the coefficient table (3 x C)
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* arrive, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(arrive, 1u);
+    unsigned spins = 0;
+    while (ld_acquire_u32(arrive) < nblocks) {
+      __nanosleep(40);
+      if (++spins > (1u << 25)) { printf("pidnet_b200: BatchNorm grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+// after every thread has read the sums: the last block to leave clears sums and both counters for the next launch
+__device__ __forceinline__ void grid_depart(unsigned* sync, double* sums, int nsums, unsigned nblocks) {
+  __shared__ unsigned s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(sync + 1, 1u) == nblocks - 1 ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    for (int i = threadIdx.x; i < nsums; i += blockDim.x) sums[i] = 0.0;
+    if (threadIdx.x == 0) { sync[0] = 0u; sync[1] = 0u; }
+  }
+}
+// block-level reduction of 16 per-thread partials over the pixel lanes, then fp64 atomics: a[8] -> sums[0..C),
+// b[8] -> sums[C..2C)
+__device__ __forceinline__ void block_channel_reduce(float* red, const float (&a)[8], const float (&b)[8], int groups, int lanes,
+                                                     int cg, int ln, bool active, int C, double* sums) {
+#pragma unroll
+  for (int round = 0; round < 4; ++round) {   // a[0..3], a[4..7], b[0..3], b[4..7]
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[(ln * groups + cg) * 4 + e] = round < 2 ? a[(round & 1) * 4 + e] : b[(round & 1) * 4 + e];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < groups * 4; i += blockDim.x) {
+      float s = 0.f;
+      for (int q = 0; q < lanes; ++q) s += red[q * groups * 4 + i];
+      const int c = (i >> 2) * 8 + (round & 1) * 4 + (i & 3);
+      if (s != 0.f) atomicAdd(sums + (round >> 1) * C + c, static_cast<double>(s));
+    }
+  }
+}
+
+struct BnFwdParams {
+  View x, res, z;
+  const float *gamma, *beta, *conv_bias;
+  float *run_mean, *run_var, *mean, *invstd;
+  double* sums;      // [2C], zero on entry, cleared on exit
+  unsigned* sync;    // [2], zero on entry, cleared on exit
+  double count;
+  long pix_per_block;
+  int relu, stage_iters;
+};
+__global__ void __launch_bounds__(kBnThreads, 2) bn_fwd_fused_kernel(BnFwdParams p) {
+  extern __shared__ uint4 smem_v[];
+  float* red = reinterpret_cast<float*>(smem_v);
+  uint4* park = smem_v + bn_red_floats(p.x.C) / 4;   // [stage_iters][kBnThreads]
+  const int C = p.x.C, groups = C >> 3, lanes = kBnThreads / groups;
+  const int cg = threadIdx.x % groups, ln = threadIdx.x / groups;
+  const bool active = ln < lanes;
+  const long npix = static_cast<long>(p.x.N) * p.x.H * p.x.W;
+  const long p0 = static_cast<long>(blockIdx.x) * p.pix_per_block, p1 = min(p0 + p.pix_per_block, npix);
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+  if (active) {
+    int it = 0;
+    for (long q = p0 + ln; q < p1; q += static_cast<long>(lanes) * 4, it += 4) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long qq = q + static_cast<long>(k) * lanes;
+        u[k] = qq < p1 ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (it + k < p.stage_iters) park[(it + k) * kBnThreads + threadIdx.x] = u[k];
+        const F8 f = unpack8(u[k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] += f.v[e]; b[e] = fmaf(f.v[e], f.v[e], b[e]); }
+      }
+    }
+  }
+  block_channel_reduce(red, a, b, groups, lanes, cg, ln, active, C, p.sums);
+  grid_barrier(p.sync, gridDim.x);
+  // per-channel coefficients once per block (fp64 only for mean / variance), shared through the scratch table
+  {
+    const double inv = 1.0 / p.count;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double m = __ldcg(p.sums + c) * inv;
+      double var = __ldcg(p.sums + C + c) * inv - m * m;
+      if (var < 0) var = 0;
+      const float is = 1.f / sqrtf(static_cast<float>(var) + 1e-5f);
+      const float g = p.gamma[c];
+      red[c] = g * is;
+      red[C + c] = p.beta[c] - static_cast<float>(m) * g * is;
+      if (blockIdx.x == 0) {
+        p.mean[c] = static_cast<float>(m);
+        p.invstd[c] = is;
+        if (p.run_mean) {
+          // the conv bias (stem convs) cancels in the normalisation but is part of the batch mean the reference tracks
+          const float bm = static_cast<float>(m) + (p.conv_bias ? p.conv_bias[c] : 0.f);
+          const double unbiased = p.count > 1 ? var * p.count / (p.count - 1.0) : var;
+          p.run_mean[c] = 0.9f * p.run_mean[c] + 0.1f * bm;
+          p.run_var[c] = 0.9f * p.run_var[c] + 0.1f * static_cast<float>(unbiased);
+        }
+      }
+    }
+  }
+  grid_depart(p.sync, p.sums, 2 * C, gridDim.x);   // (contains the __syncthreads that publishes the table)
+  if (active) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = red[cg * 8 + e]; sh[e] = red[C + cg * 8 + e]; }
+    int it = 0;
+    for (long q = p0 + ln; q < p1; q += lanes, ++it) {
+      const uint4 u = it < p.stage_iters ? park[it * kBnThreads + threadIdx.x]
+                                         : __ldg(reinterpret_cast<const uint4*>(p.x.ptr + q * p.x.ps + cg * 8));
+      F8 f = unpack8(u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f.v[e] = fmaf(f.v[e], sc[e], sh[e]);
+      if (p.res.ptr) {
+        const F8 r = ld8(p.res.ptr + q * p.res.ps + cg * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f.v[e] += r.v[e];
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f.v[e] = fmaxf(f.v[e], 0.f);
+      }
+      st8(p.z.ptr + q * p.z.ps + cg * 8, f);
+    }
+  }
+}
+
+struct BnBwdParams {
+  View x, dz, z, dx, dres;
+  const float *mean, *invstd, *gamma;
+  float *dgamma, *dbeta;
+  double* sums;
+  unsigned* sync;
+  double count;
+  long pix_per_block;
+  int relu, acc_dx, acc_dres, stage_iters;
+};
+__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams p) {
+  extern __shared__ uint4 smem_v[];
+  float* red = reinterpret_cast<float*>(smem_v);
+  uint4* park = smem_v + bn_red_floats(p.x.C) / 4;   // [stage_iters][2][kBnThreads]: x, masked dz
+  const int C = p.x.C, groups = C >> 3, lanes = kBnThreads / groups;
+  const int cg = threadIdx.x % groups, ln = threadIdx.x / groups;
+  const bool active = ln < lanes;
+  const long npix = static_cast<long>(p.x.N) * p.x.H * p.x.W;
+  const long p0 = static_cast<long>(blockIdx.x) * p.pix_per_block, p1 = min(p0 + p.pix_per_block, npix);
+  float a[8], b[8], mu[8], is[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mu[e] = p.mean[cg * 8 + e]; is[e] = p.invstd[cg * 8 + e]; }
+    int it = 0;
+    for (long q = p0 + ln; q < p1; q += static_cast<long>(lanes) * 2, it += 2) {
+      uint4 ux[2], ug[2], uz[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const long qq = q + static_cast<long>(k) * lanes;
+        const bool ok = qq < p1;
+        ux[k] = ok ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
+        ug[k] = ok ? __ldg(reinterpret_cast<const uint4*>(p.dz.ptr + qq * p.dz.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
+        uz[k] = (ok && p.relu) ? __ldg(reinterpret_cast<const uint4*>(p.z.ptr + qq * p.z.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const F8 xv = unpack8(ux[k]);
+        F8 g = unpack8(ug[k]);
+        if (p.relu) {
+          const F8 zv = unpack8(uz[k]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
+          ug[k] = pack8(g);
+        }
+        if (it + k < p.stage_iters) {
+          park[((it + k) * 2 + 0) * kBnThreads + threadIdx.x] = ux[k];
+          park[((it + k) * 2 + 1) * kBnThreads + threadIdx.x] = ug[k];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] += g.v[e]; b[e] = fmaf(g.v[e], (xv.v[e] - mu[e]) * is[e], b[e]); }
+      }
+    }
+  }
+  block_channel_reduce(red, a, b, groups, lanes, cg, ln, active, C, p.sums);
+  grid_barrier(p.sync, gridDim.x);
+  {
+    const double inv = 1.0 / p.count;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double sb = __ldcg(p.sums + c), sg = __ldcg(p.sums + C + c);
+      const float isf = p.invstd[c], A = p.gamma[c] * isf;
+      const float B = -A * isf * static_cast<float>(sg * inv);
+      red[c] = A;
+      red[C + c] = B;
+      red[2 * C + c] = -A * static_cast<float>(sb * inv) - B * p.mean[c];
+      if (blockIdx.x == 0 && p.dgamma) {
+        p.dbeta[c] += static_cast<float>(sb);
+        p.dgamma[c] += static_cast<float>(sg);
+      }
+    }
+  }
+  grid_depart(p.sync, p.sums, 2 * C, gridDim.x);   // (contains the __syncthreads that publishes the table)
+  if (active && (p.dx.ptr || p.dres.ptr)) {
+    float cA[8], cB[8], cD[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { cA[e] = red[cg * 8 + e]; cB[e] = red[C + cg * 8 + e]; cD[e] = red[2 * C + cg * 8 + e]; }
+    int it = 0;
+    for (long q = p0 + ln; q < p1; q += lanes, ++it) {
+      F8 xv, g;
+      if (it < p.stage_iters) {
+        xv = unpack8(park[(it * 2 + 0) * kBnThreads + threadIdx.x]);
+        g = unpack8(park[(it * 2 + 1) * kBnThreads + threadIdx.x]);
+      } else {
+        xv = ld8(p.x.ptr + q * p.x.ps + cg * 8);
+        g = ld8(p.dz.ptr + q * p.dz.ps + cg * 8);
+        if (p.relu) {
+          const F8 zv = ld8(p.z.ptr + q * p.z.ps + cg * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
+        }
+      }
+      if (p.dres.ptr) {
+        F8 r = g;
+        if (p.acc_dres) {
+          const F8 o = ld8(p.dres.ptr + q * p.dres.ps + cg * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.v[e] += o.v[e];
+        }
+        st8(p.dres.ptr + q * p.dres.ps + cg * 8, r);
+      }
+      if (p.dx.ptr) {
+        F8 o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = fmaf(cA[e], g.v[e], fmaf(cB[e], xv.v[e], cD[e]));
+        if (p.acc_dx) {
+          const F8 old = ld8(p.dx.ptr + q * p.dx.ps + cg * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o.v[e] += old.v[e];
+        }
+        st8(p.dx.ptr + q * p.dx.ps + cg * 8, o);
+      }
+    }
   }
 }
 
@@ -569,6 +852,57 @@ cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, cons
   bn_bwd_coef_kernel<<<(x.C + 127) / 128, 128, 0, st>>>(sums, x.C, count, gamma, mean, invstd, coef, dgamma, dbeta);
   if (dx.ptr || dres.ptr)
     bn_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, dz, z, dx, dres, coef, relu, acc_dx, acc_dres);
+  return cudaGetLastError();
+}
+
+// ---- fused single-launch BatchNorm
+// shared memory per block (2 blocks per SM): small enough to co-reside with a wgrad CTA of the side stream
+static constexpr size_t kBnSmemBudget = 24 * 1024;
+static cudaError_t bn_fused_geometry(const View& x, int num_sms, int vec_per_iter, unsigned& blocks, long& ppb, int& stage_iters,
+                                     size_t& smem) {
+  const int groups = x.C / 8;
+  if (groups < 1 || groups > kBnThreads || x.C % 8) return cudaErrorInvalidValue;
+  const int lanes = kBnThreads / groups;
+  const long npix = static_cast<long>(x.N) * x.H * x.W;
+  blocks = static_cast<unsigned>(2 * num_sms);
+  const long unit = static_cast<long>(lanes) * 4;
+  ppb = (npix + blocks - 1) / blocks;
+  ppb = (ppb + unit - 1) / unit * unit;
+  const size_t red = static_cast<size_t>(bn_red_floats(x.C)) * sizeof(float);
+  const size_t per_iter = static_cast<size_t>(kBnThreads) * 16 * vec_per_iter;
+  stage_iters = red < kBnSmemBudget ? static_cast<int>((kBnSmemBudget - red) / per_iter) : 0;
+  smem = red + stage_iters * per_iter;
+  return cudaSuccess;
+}
+bool bn_fused_supported(int C) { return C % 8 == 0 && C / 8 >= 1 && C / 8 <= kBnThreads && 3 * C * sizeof(float) <= 40 * 1024; }
+
+cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma, const float* beta, const float* conv_bias,
+                                    float* mean, float* invstd, float* run_mean, float* run_var, double* sums, unsigned* sync,
+                                    int relu, int num_sms, cudaStream_t st) {
+  BnFwdParams p;
+  unsigned blocks = 0;
+  size_t smem = 0;
+  cudaError_t e = bn_fused_geometry(x, num_sms, 1, blocks, p.pix_per_block, p.stage_iters, smem);
+  if (e != cudaSuccess) return e;
+  p.x = x; p.res = res; p.z = z; p.gamma = gamma; p.beta = beta; p.conv_bias = conv_bias; p.mean = mean; p.invstd = invstd;
+  p.run_mean = run_mean; p.run_var = run_var; p.sums = sums; p.sync = sync; p.relu = relu;
+  p.count = static_cast<double>(x.N) * x.H * x.W;
+  bn_fwd_fused_kernel<<<blocks, kBnThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
+                                     const float* gamma, double* sums, unsigned* sync, int relu, int acc_dx, int acc_dres,
+                                     float* dgamma, float* dbeta, int num_sms, cudaStream_t st) {
+  BnBwdParams p;
+  unsigned blocks = 0;
+  size_t smem = 0;
+  cudaError_t e = bn_fused_geometry(x, num_sms, 2, blocks, p.pix_per_block, p.stage_iters, smem);
+  if (e != cudaSuccess) return e;
+  p.x = x; p.dz = dz; p.z = z; p.dx = dx; p.dres = dres; p.mean = mean; p.invstd = invstd; p.gamma = gamma;
+  p.dgamma = dgamma; p.dbeta = dbeta; p.sums = sums; p.sync = sync; p.relu = relu; p.acc_dx = acc_dx; p.acc_dres = acc_dres;
+  p.count = static_cast<double>(x.N) * x.H * x.W;
+  bn_bwd_fused_kernel<<<blocks, kBnThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 

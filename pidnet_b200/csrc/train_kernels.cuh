@@ -23,6 +23,16 @@ cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, cons
                                const float* gamma, double* sums, float* coef /*[3*C] scratch*/, int relu, int acc_dx,
                                int acc_dres, float* dgamma, float* dbeta, int num_sms, cudaStream_t st);
 
+// Fused single-launch forms (persistent grid + grid barrier, loaded vectors parked in shared memory between the
+// statistics pass and the apply pass).  `sync`: device unsigned[2], zero on entry (self-clearing like `sums`).
+bool bn_fused_supported(int C);
+cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma, const float* beta, const float* conv_bias,
+                                    float* mean, float* invstd, float* run_mean, float* run_var, double* sums, unsigned* sync,
+                                    int relu, int num_sms, cudaStream_t st);
+cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
+                                     const float* gamma, double* sums, unsigned* sync, int relu, int acc_dx, int acc_dres,
+                                     float* dgamma, float* dbeta, int num_sms, cudaStream_t st);
+
 // ---- device-side weight packing: fp32 [Cout][Cin_total][k][k] -> bf16 packed rows (forward: row = co; dgrad: row = ci)
 struct PackJob {
   const float* src;

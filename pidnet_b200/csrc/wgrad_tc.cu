@@ -17,7 +17,7 @@ namespace {
 
 constexpr int kWgThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer (+TMEM), warps 2..5: epilogue
 // pipeline depth per taps-per-CTA variant: stage = (2 + T) * 8 KB, kept under the 227 KB limit
-template <int T> struct WgStages { static constexpr int value = T == 1 ? 8 : 5; };
+template <int T> struct WgStages { static constexpr int value = T == 1 ? 6 : 4; };   // <= 160 KB: leaves room for the BatchNorm blocks of the main stream
 
 template <int T>  // taps per CTA (1 or 3)
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
