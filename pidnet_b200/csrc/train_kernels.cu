@@ -800,6 +800,69 @@ __global__ void __launch_bounds__(256) lightbag_bwd_kernel(View p, View il, View
   st8(ti.ptr + pix * ti.ps + cg * 8, ot);
 }
 
+// ---- Bag (model_utils.py:375-377), train mode: e = sigmoid(d); out = e p + (1-e) U(i)   (BN + ReLU + conv follow)
+__global__ void __launch_bounds__(256) bag_train_fwd_kernel(View p, View il, View d, View out) {
+  const int groups = p.C >> 3;
+  const long total = static_cast<long>(p.N) * p.H * p.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long pix = idx / groups;
+  const int w = static_cast<int>(pix % p.W);
+  const long t1 = pix / p.W;
+  const int h = static_cast<int>(t1 % p.H);
+  const int n = static_cast<int>(t1 / p.H);
+  const F8 iv = sample8(il, n, h, w, p.H, p.W, cg * 8);
+  const F8 pv = ld8(p.ptr + pix * p.ps + cg * 8);
+  const F8 dv = ld8(d.ptr + pix * d.ps + cg * 8);
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float g = 1.f / (1.f + __expf(-dv.v[e]));
+    o.v[e] = g * pv.v[e] + (1.f - g) * iv.v[e];
+  }
+  st8(out.ptr + pix * out.ps + cg * 8, o);
+}
+//   dp (+)= e g;  dd (+)= g (p - U(i)) e (1-e);  ti = (1-e) g  (-> U^T -> di_low)
+__global__ void __launch_bounds__(256) bag_train_bwd_kernel(View p, View il, View d, View dout, View dp, int acc_dp, View dd,
+                                                            int acc_dd, View ti) {
+  const int groups = p.C >> 3;
+  const long total = static_cast<long>(p.N) * p.H * p.W * groups;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % groups);
+  const long pix = idx / groups;
+  const int w = static_cast<int>(pix % p.W);
+  const long t1 = pix / p.W;
+  const int h = static_cast<int>(t1 % p.H);
+  const int n = static_cast<int>(t1 / p.H);
+  const F8 iv = sample8(il, n, h, w, p.H, p.W, cg * 8);
+  const F8 pv = ld8(p.ptr + pix * p.ps + cg * 8);
+  const F8 dv = ld8(d.ptr + pix * d.ps + cg * 8);
+  const F8 go = ld8(dout.ptr + pix * dout.ps + cg * 8);
+  F8 op, od, ot;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float g = 1.f / (1.f + __expf(-dv.v[e]));
+    op.v[e] = g * go.v[e];
+    od.v[e] = go.v[e] * (pv.v[e] - iv.v[e]) * g * (1.f - g);
+    ot.v[e] = (1.f - g) * go.v[e];
+  }
+  if (acc_dp) {
+    const F8 o = ld8(dp.ptr + pix * dp.ps + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) op.v[e] += o.v[e];
+  }
+  if (acc_dd) {
+    const F8 o = ld8(dd.ptr + pix * dd.ps + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) od.v[e] += o.v[e];
+  }
+  st8(dp.ptr + pix * dp.ps + cg * 8, op);
+  st8(dd.ptr + pix * dd.ps + cg * 8, od);
+  st8(ti.ptr + pix * ti.ps + cg * 8, ot);
+}
+
 __global__ void add_sums_kernel(double* __restrict__ sums, float* __restrict__ dst, int C, int Cacc) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) dst[c] += static_cast<float>(sums[c]);
@@ -974,6 +1037,18 @@ cudaError_t lightbag_bwd_launch(View p, View il, View d, View duv, View dp, int 
                                 cudaStream_t st) {
   const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
   lightbag_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, il, d, duv, dp, acc_dp, dd, acc_dd, ti);
+  return cudaGetLastError();
+}
+
+cudaError_t bag_train_fwd_launch(View p, View il, View d, View out, cudaStream_t st) {
+  const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
+  bag_train_fwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, il, d, out);
+  return cudaGetLastError();
+}
+cudaError_t bag_train_bwd_launch(View p, View il, View d, View dout, View dp, int acc_dp, View dd, int acc_dd, View ti,
+                                 cudaStream_t st) {
+  const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
+  bag_train_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, il, d, dout, dp, acc_dp, dd, acc_dd, ti);
   return cudaGetLastError();
 }
 

@@ -63,6 +63,11 @@ cudaError_t pag_train_bwd_launch(View x, View xk, View yq, View y, View out, Vie
                                  int acc_dx, View dxk, View t1, View t2, cudaStream_t st);
 cudaError_t lightbag_bwd_launch(View p, View il, View d, View duv, View dp, int acc_dp, View dd, int acc_dd, View ti,
                                 cudaStream_t st);
+// Bag (L topology), train mode: out = e p + (1-e) U(i) with e = sigmoid(d); backward: dp (+)= e g, dd (+)= g (p - U(i)) e (1-e),
+// ti = (1-e) g (hi-res gradient of U(i), reduced to the low-res map by upsample_transpose)
+cudaError_t bag_train_fwd_launch(View p, View i_low, View d, View out, cudaStream_t st);
+cudaError_t bag_train_bwd_launch(View p, View i_low, View d, View dout, View dp, int acc_dp, View dd, int acc_dd, View ti,
+                                 cudaStream_t st);
 // dst[c] += sums[c]  (bias gradients from a per-channel reduction)
 cudaError_t add_sums_launch(double* sums, float* dst, int C, int Cacc, cudaStream_t st);
 

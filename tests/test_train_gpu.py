@@ -29,7 +29,8 @@ def _dev():
     return torch.device('cuda:0')
 
 
-@pytest.mark.parametrize('case', [('pidnet_s', 19, 4, 256, 256), ('pidnet_m', 11, 4, 192, 256)], ids=str)
+@pytest.mark.parametrize('case', [('pidnet_s', 19, 4, 256, 256), ('pidnet_m', 11, 4, 192, 256), ('pidnet_l', 19, 4, 192, 256)],
+                         ids=str)
 def test_training_step_stage_local_parity(case):
     _dev()
     name, ncls, N, H, W = case
