@@ -174,6 +174,14 @@ int pidnet_train_profile(pidnet_trainer* h, void* stream, const float* x_nchw, c
                          const float* class_weights, const pidnet_criterion_cfg* cfg, char* buf, size_t cap, float* crit_ms);
 int pidnet_train_debug_tensor(pidnet_trainer* h, const char* name, int grad, float* host_out, int64_t* shape4);
 
+/* ---- optimizer step on flat buffers.
+ * Replaces torch.optim.SGD.step() as configured in tools/train.py:139-148 (momentum, weight decay, optional Nesterov) for ALL
+ * parameters in one launch:  d = grad_scale * g + wd * p;  buf = first_step ? d : momentum * buf + (1 - dampening) * d;
+ * d = nesterov ? d + momentum * buf : buf;  p -= lr * d.   n: floats (multiple of 4), pointers 16-byte aligned device fp32.
+ * The poly learning-rate schedule of utils/utils.py:154-160 is host arithmetic (pidnet_b200/optim.py:adjust_learning_rate). */
+int pidnet_sgd_step(void* stream, float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                    float dampening, float weight_decay, int nesterov, int first_step, float grad_scale);
+
 /* Hardware probe used by tools/probe_halo.py (documents how tcgen05 reads shifted windows of a
  * TMA-written halo patch; not on the product path). */
 int pidnet_probe_halo(void* stream, const void* x_18x10x64_bf16, const void* w_64x64_bf16, int r, int s, int mode,

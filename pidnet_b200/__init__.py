@@ -2,5 +2,7 @@
 `models/pidnet.py` surface.  See DESIGN.md / INTEGRATION.md."""
 from .pidnet import PIDNet, get_pred_model, get_seg_model  # noqa: F401
 from .criterion import BondaryLoss, FullModel, OhemCrossEntropy  # noqa: F401
+from .optim import FusedSGD, adjust_learning_rate  # noqa: F401
 
-__all__ = ['PIDNet', 'get_pred_model', 'get_seg_model', 'OhemCrossEntropy', 'BondaryLoss', 'FullModel']
+__all__ = ['PIDNet', 'get_pred_model', 'get_seg_model', 'OhemCrossEntropy', 'BondaryLoss', 'FullModel', 'FusedSGD',
+           'adjust_learning_rate']

@@ -138,6 +138,14 @@ class FullModel(nn.Module):
         ups = [upsample_align_corners(o, (h, w)) for o in (x_p, x_m)] if self.return_outputs else []
         return loss, ups, out12[3], [out12[1], out12[2]]
 
+    @property
+    def trainer(self):
+        """The `EngineTrainer` behind the train-mode forward (created on first use)."""
+        from .train import EngineTrainer
+        if getattr(self, '_trainer', None) is None:
+            self._trainer = EngineTrainer(self.model)
+        return self._trainer
+
     def check_valid(self, out):
         """The reference raises IndexError when an OHEM set has no valid pixel (criterion.py:73)."""
         if float(out[8]) == 0 or float(out[9]) == 0:

@@ -1622,6 +1622,19 @@ int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd) {
   });
 }
 
+// ---- optimizer step
+int pidnet_sgd_step(void* stream, float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                    float dampening, float weight_decay, int nesterov, int first_step, float grad_scale) {
+  return guard([&] {
+    if (!param || !grad || (momentum != 0.f && !momentum_buf)) fail("null argument");
+    if (n < 0 || n % 4) fail("pidnet_sgd_step: n must be a non-negative multiple of 4 (pad the flat buffers)");
+    if (nesterov && (momentum <= 0.f || dampening != 0.f)) fail("Nesterov momentum requires a momentum and zero dampening");
+    cudaError_t e = sgd_step_launch(param, grad, momentum_buf ? momentum_buf : param, n, lr, momentum, dampening, weight_decay,
+                                    nesterov, first_step, grad_scale, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) fail(std::string("pidnet_sgd_step: ") + cudaGetErrorString(e));
+  });
+}
+
 // ---- criterion (FullModel / OhemCrossEntropy / BondaryLoss), see criterion.cu
 size_t pidnet_criterion_workspace_bytes(int N, int H, int W) { return criterion_workspace_bytes(N, H, W); }
 

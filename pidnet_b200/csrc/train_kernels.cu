@@ -863,6 +863,33 @@ __global__ void __launch_bounds__(256) bag_train_bwd_kernel(View p, View il, Vie
   st8(ti.ptr + pix * ti.ps + cg * 8, ot);
 }
 
+// ---- fused SGD on the flat parameter / gradient / momentum buffers (torch.optim.SGD semantics, tools/train.py:139-148):
+//   d = g + wd * p;  buf = first ? d : momentum * buf + (1 - dampening) * d;  d = nesterov ? d + momentum * buf : buf;  p -= lr * d
+__global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                                       long n4, float lr, float momentum, float dampening, float wd, int nesterov,
+                                                       int first, float grad_scale) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 pv = reinterpret_cast<float4*>(p)[i];
+  const float4 gv = reinterpret_cast<const float4*>(g)[i];
+  float4 bv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(buf)[i];
+  float* pp = reinterpret_cast<float*>(&pv);
+  const float* gp = reinterpret_cast<const float*>(&gv);
+  float* bp = reinterpret_cast<float*>(&bv);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float d = gp[e] * grad_scale;
+    if (wd != 0.f) d = d + wd * pp[e];
+    if (momentum != 0.f) {
+      bp[e] = first ? d : momentum * bp[e] + (1.f - dampening) * d;
+      d = nesterov ? d + momentum * bp[e] : bp[e];
+    }
+    pp[e] = pp[e] - lr * d;
+  }
+  reinterpret_cast<float4*>(p)[i] = pv;
+  if (momentum != 0.f) reinterpret_cast<float4*>(buf)[i] = bv;
+}
+
 __global__ void add_sums_kernel(double* __restrict__ sums, float* __restrict__ dst, int C, int Cacc) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) dst[c] += static_cast<float>(sums[c]);
@@ -1049,6 +1076,16 @@ cudaError_t bag_train_bwd_launch(View p, View il, View d, View dout, View dp, in
                                  cudaStream_t st) {
   const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
   bag_train_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, il, d, dout, dp, acc_dp, dd, acc_dd, ti);
+  return cudaGetLastError();
+}
+
+cudaError_t sgd_step_launch(float* p, const float* g, float* buf, long n, float lr, float momentum, float dampening, float wd,
+                            int nesterov, int first, float grad_scale, cudaStream_t st) {
+  if (n % 4 || (reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(buf)) % 16)
+    return cudaErrorInvalidValue;
+  const long n4 = n / 4;
+  if (n4 == 0) return cudaSuccess;
+  sgd_step_kernel<<<blocks_for(n4, 256), 256, 0, st>>>(p, g, buf, n4, lr, momentum, dampening, wd, nesterov, first, grad_scale);
   return cudaGetLastError();
 }
 

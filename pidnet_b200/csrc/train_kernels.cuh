@@ -33,6 +33,10 @@ cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres
                                      const float* gamma, double* sums, unsigned* sync, int relu, int acc_dx, int acc_dres,
                                      float* dgamma, float* dbeta, int num_sms, cudaStream_t st);
 
+// ---- fused SGD step over flat fp32 buffers (n a multiple of 4, pointers 16-byte aligned); `first` = no momentum history yet
+cudaError_t sgd_step_launch(float* p, const float* g, float* buf, long n, float lr, float momentum, float dampening, float wd,
+                            int nesterov, int first, float grad_scale, cudaStream_t st);
+
 // ---- device-side weight packing: fp32 [Cout][Cin_total][k][k] -> bf16 packed rows (forward: row = co; dgrad: row = ci)
 struct PackJob {
   const float* src;

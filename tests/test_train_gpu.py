@@ -129,3 +129,41 @@ def test_graph_replay_matches_eager_steps():
     gd = rel(res['graph'][1], res['eager'][1])
     print('gradient rel diff: graph vs eager %.3e, eager vs eager %.3e' % (gd, noise))
     assert gd < max(1e-3, 3 * noise), (gd, noise)
+
+
+@pytest.mark.gpu
+def test_fused_sgd_matches_torch_sgd_and_oracle():
+    """pidnet_sgd_step (one launch over the flat buffers) == torch.optim.SGD on every parameter, several steps with the
+    poly schedule, momentum 0.9 / wd 5e-4 as in the reference configs (tools/train.py:139-148), plus Nesterov."""
+    from oracle import sgd_oracle as SO
+    from pidnet_b200 import FusedSGD, adjust_learning_rate
+    from pidnet_b200.train import EngineTrainer
+    dev = _dev()
+    cfg = O.config_for('tiny_s', 7, True)
+    for nesterov in (False, True):
+        model = PIDNet(m=cfg['m'], n=cfg['n'], num_classes=7, planes=cfg['planes'], ppm_planes=cfg['ppm_planes'],
+                       head_planes=cfg['head_planes'], augment=True)
+        model.load_state_dict(O.make_state_dict(cfg, 2))
+        model = model.to(dev).train()
+        tr = EngineTrainer(model)
+        ref_p = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+        ref_opt = torch.optim.SGD(ref_p, lr=0.01, momentum=0.9, weight_decay=5e-4, nesterov=nesterov)
+        opt = FusedSGD(tr, lr=0.01, momentum=0.9, weight_decay=5e-4, nesterov=nesterov)
+        p0 = tr.flat_param[:1000].cpu().numpy().copy()
+        buf = None
+        g = torch.Generator(device='cpu').manual_seed(4)
+        for it in range(5):
+            lr = adjust_learning_rate(opt, 0.01, 50, it)
+            assert lr == SO.adjust_learning_rate(0.01, 50, it)
+            ref_opt.param_groups[0]['lr'] = lr
+            tr.flat_grad.copy_(torch.randn(tr.flat_grad.shape, generator=g).to(dev))
+            for rp, (k, _) in zip(ref_p, model.named_parameters()):
+                rp.grad = tr.grad_views[k].clone()
+            g0 = tr.flat_grad[:1000].cpu().numpy().copy()
+            opt.step()
+            ref_opt.step()
+            p0, buf = SO.sgd_step(p0, g0, buf, lr, momentum=0.9, weight_decay=5e-4, nesterov=nesterov, first=(it == 0))
+        torch.cuda.synchronize()
+        for rp, p in zip(ref_p, model.parameters()):
+            assert torch.allclose(p.detach(), rp.detach(), rtol=2e-6, atol=1e-7)
+        assert torch.allclose(tr.flat_param[:1000].cpu(), torch.from_numpy(p0), rtol=2e-6, atol=1e-7)

@@ -53,6 +53,15 @@ def main():
     for _ in range(3): tr.step(x, labels, bd, weight, crit.cfg, backward=False, want_logits=False)
     ef1.record(); torch.cuda.synchronize()
     fwd_ms = ef0.elapsed_time(ef1) / 3
+    # full iteration incl. the fused optimizer step (row f3): step + all-reduce + pidnet_sgd_step
+    from pidnet_b200 import FusedSGD, adjust_learning_rate
+    opt = FusedSGD(tr, lr=0.01, momentum=0.9, weight_decay=5e-4)
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record()
+    for i in range(steps):
+        one(); opt.step(); adjust_learning_rate(opt, 0.01, 1000, i)
+    es1.record(); torch.cuda.synchronize()
+    sgd_ms = es0.elapsed_time(es1) / steps
     if world > 1:
         t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     import ctypes as C
@@ -61,6 +70,7 @@ def main():
     flops = 3 * 50.295e9 * B    # fwd (augment) 50.295 GFLOP / image at 1024x1024, fwd+bwd = 3x
     line = dict(metric='pidnet_s_train_1024x1024_images_per_sec', value=world * B * 1e3 / ms, unit='img/s', n_gpus=world,
                 steps=steps, warmup=warmup, ms_per_step=ms, fwd_plus_criterion_ms=fwd_ms, bwd_ms=ms - fwd_ms,
+                ms_per_step_with_sgd=sgd_ms,
                 higher_is_better=True, scaling='weak', dtype='bf16 activations/gradients, fp32 master weights and weight gradients',
                 data='synthetic', config=dict(workload=f'PIDNet-S train fwd + OHEM/boundary loss + bwd, {B}x3x{H}x{W} per GPU, NCCL all-reduce of {tr.n_param} fp32 gradients',
                 batch_per_gpu=B), launches=dict(forward=f.value, backward=b.value), loss=float(out12[0]),
