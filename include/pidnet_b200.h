@@ -174,6 +174,16 @@ int pidnet_train_profile(pidnet_trainer* h, void* stream, const float* x_nchw, c
                          const float* class_weights, const pidnet_criterion_cfg* cfg, char* buf, size_t cap, float* crit_ms);
 int pidnet_train_debug_tensor(pidnet_trainer* h, const char* name, int grad, float* host_out, int64_t* shape4);
 
+/* ---- post-processing.
+ * Fused bilinear upsample (align_corners=True) + argmax of the [N,C,h,w] fp32 logits to label size:
+ *   pred      (optional) uint8 [N,H,W]: torch.argmax(F.interpolate(pred, size, 'bilinear', align_corners=True), 1)
+ *             -- datasets/base_dataset.py:136-150 (`.exp()` is monotonic), tools/custom.py:90-92;
+ *   confusion (optional) uint64 [C*C] += histogram of (label, prediction) over labels != ignore_label
+ *             -- get_confusion_matrix, utils/utils.py:129-152 (row = ground truth, column = prediction).
+ * The [N,C,H,W] tensor is never materialised.  All pointers are device pointers. */
+int pidnet_postprocess(void* stream, const float* logits, int N, int C, int h, int w, int H, int W, unsigned char* pred,
+                       const int64_t* labels, int64_t ignore_label, unsigned long long* confusion);
+
 /* ---- optimizer step on flat buffers.
  * Replaces torch.optim.SGD.step() as configured in tools/train.py:139-148 (momentum, weight decay, optional Nesterov) for ALL
  * parameters in one launch:  d = grad_scale * g + wd * p;  buf = first_step ? d : momentum * buf + (1 - dampening) * d;

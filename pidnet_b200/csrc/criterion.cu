@@ -829,6 +829,100 @@ cudaError_t launch_run(const CritParams& p, const SelState* sel, bool backward, 
   return launch_run_kernels<kMaxC>(p, sel, backward, st);
 }
 
+// --------------------------------------------------------------------------------------- post-processing
+// Fused x8 bilinear upsample (align_corners=True) + argmax (+ confusion-matrix histogram): replaces
+// F.interpolate -> [exp] -> argmax -> .cpu() of datasets/base_dataset.py:136-150 / tools/custom.py:90-92 and
+// get_confusion_matrix of utils/utils.py:129-152 without materialising the [N,C,H,W] fp32 tensor (159 MB per
+// 1024x2048 image).  The interpolation is evaluated in torch's operation order WITHOUT fma contraction so the class
+// index is bit-identical to the numpy restatement in oracle/postproc_oracle.py.
+struct PostParams {
+  const float* x;            // [N,C,h,w] fp32 logits
+  unsigned char* pred;       // [N,H,W] class index (optional)
+  const int64_t* labels;     // [N,H,W] (optional, with conf)
+  unsigned long long* conf;  // [C*C] += (row = label, column = prediction)
+  int N, C, h, w, H, W, staged;
+  long ignore_label;
+};
+template <int CMAX>
+__global__ void __launch_bounds__(256) upsample_argmax_kernel(PostParams p) {
+  extern __shared__ float lo[];                    // [C][kRLH][kRLW] when staged
+  __shared__ unsigned hist[kMaxC * kMaxC];
+  const int tiles_x = (p.W + kRW - 1) / kRW, tiles_y = (p.H + kRH - 1) / kRH;
+  const int n = blockIdx.x / (tiles_x * tiles_y);
+  const int rem = blockIdx.x - n * tiles_x * tiles_y;
+  const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+  const int ly0 = lerp_ac(ty * kRH, p.h, p.H).i0, lx0 = lerp_ac(tx * kRW, p.w, p.W).i0;
+  const size_t plane = static_cast<size_t>(p.h) * p.w;
+  const float* xn = p.x + static_cast<size_t>(n) * p.C * plane;
+  if (p.staged) {
+    for (int i = threadIdx.x; i < p.C * kRLP; i += blockDim.x) {
+      const int ch = i / kRLP, r = i - ch * kRLP;
+      const int ly = min(ly0 + r / kRLW, p.h - 1), lx = min(lx0 + r % kRLW, p.w - 1);
+      lo[i] = __ldg(xn + ch * plane + static_cast<size_t>(ly) * p.w + lx);
+    }
+  }
+  if (p.conf) for (int i = threadIdx.x; i < p.C * p.C; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int y = ty * kRH + warp;
+  if (y < p.H) {
+    const Lerp ly = lerp_ac(y, p.h, p.H);
+    const float wy1 = ly.l, wy0 = 1.f - ly.l;
+    const long row = (static_cast<long>(n) * p.H + y) * p.W;
+#pragma unroll 1
+    for (int j = 0; j < kPX; ++j) {
+      const int x = tx * kRW + j * 32 + lane;
+      if (x >= p.W) break;
+      const Lerp lx = lerp_ac(x, p.w, p.W);
+      const float wx1 = lx.l, wx0 = 1.f - lx.l;
+      float best = -FLT_MAX;
+      int arg = 0;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < p.C) {
+          float a, b, d, e;
+          if (p.staged) {
+            const float* q = lo + k * kRLP;
+            const int r0 = (ly.i0 - ly0) * kRLW - lx0, r1 = (ly.i1 - ly0) * kRLW - lx0;
+            a = q[r0 + lx.i0]; b = q[r0 + lx.i1]; d = q[r1 + lx.i0]; e = q[r1 + lx.i1];
+          } else {
+            const float* q = xn + k * plane;
+            a = __ldg(q + ly.i0 * p.w + lx.i0); b = __ldg(q + ly.i0 * p.w + lx.i1);
+            d = __ldg(q + ly.i1 * p.w + lx.i0); e = __ldg(q + ly.i1 * p.w + lx.i1);
+          }
+          // h0 * (w0 * a + w1 * b) + h1 * (w0 * d + w1 * e), every product and sum rounded (no fma)
+          const float top = __fadd_rn(__fmul_rn(wx0, a), __fmul_rn(wx1, b));
+          const float bot = __fadd_rn(__fmul_rn(wx0, d), __fmul_rn(wx1, e));
+          const float v = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
+          if (v > best) { best = v; arg = k; }     // first maximum wins, like torch.argmax / np.argmax
+        }
+      }
+      if (p.pred) p.pred[row + x] = static_cast<unsigned char>(arg);
+      if (p.conf) {
+        const long t = p.labels[row + x];
+        if (t != p.ignore_label && t >= 0 && t < p.C) atomicAdd(&hist[static_cast<int>(t) * p.C + arg], 1u);
+      }
+    }
+  }
+  if (p.conf) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.C * p.C; i += blockDim.x)
+      if (hist[i]) atomicAdd(p.conf + i, static_cast<unsigned long long>(hist[i]));
+  }
+}
+
+template <int CMAX>
+cudaError_t launch_post(const PostParams& p, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>(p.N) * ((p.W + kRW - 1) / kRW) * ((p.H + kRH - 1) / kRH);
+  const size_t smem = p.staged ? static_cast<size_t>(p.C) * kRLP * sizeof(float) : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(upsample_argmax_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  upsample_argmax_kernel<CMAX><<<blocks, 256, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 // --------------------------------------------------------------------------------------- x8 upsample (returned outputs)
 __global__ void __launch_bounds__(256) upsample_ac_kernel(const float* __restrict__ x, int NC, int h, int w,
                                                           float* __restrict__ out, int H, int W) {
@@ -906,6 +1000,20 @@ cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaS
     }
   }
   return cudaGetLastError();
+}
+
+cudaError_t postprocess_launch(const float* x, int N, int C, int h, int w, int H, int W, unsigned char* pred,
+                               const int64_t* labels, long ignore_label, unsigned long long* conf, cudaStream_t st) {
+  if (C < 1 || C > kMaxC) return cudaErrorInvalidValue;
+  PostParams p;
+  p.x = x; p.pred = pred; p.labels = labels; p.conf = conf; p.N = N; p.C = C; p.h = h; p.w = w; p.H = H; p.W = W;
+  p.ignore_label = ignore_label;
+  CritParams fp;   // footprint test only
+  fp.h = h; fp.w = w; fp.H = H; fp.W = W;
+  p.staged = footprint_fits(fp, kRW, kRH, kRLW, kRLH) ? 1 : 0;
+  if (C <= 12) return launch_post<12>(p, st);
+  if (C <= 20) return launch_post<20>(p, st);
+  return launch_post<kMaxC>(p, st);
 }
 
 cudaError_t upsample_ac_launch(const float* x, int NC, int h, int w, float* out, int H, int W, cudaStream_t st) {
