@@ -68,6 +68,16 @@ int pidnet_plan(pidnet_engine* h, int N, int H, int W, size_t* arena_bytes);
 int pidnet_forward(pidnet_engine* h, void* stream, const float* x_nchw, float* out_main, float* out_p, float* out_d,
                    int use_graph);
 
+/* the same forward fed with camera frames as cv2.imread delivers them.
+ *   bgr_hwc  : device uint8 [N,H,W,3], channel order B,G,R
+ *   mean_rgb, std_rgb : host double[3] indexed R,G,B (datasets/base_dataset.py:27-28 defaults 0.485/0.456/0.406, 0.229/0.224/0.225)
+ * The stem kernel applies the reference's input_transform (datasets/base_dataset.py:36-44, tools/custom.py:52-57:
+ * image[..., ::-1] / 255.0 - mean, / std, HWC -> CHW) on load through a 3x256 table evaluated with numpy's exact
+ * arithmetic (float32 division, then float64 subtract / divide each rounded back to float32), so the result equals
+ * pidnet_forward on the host-normalised fp32 NCHW tensor while the H2D copy shrinks 4x (6.3 MB vs 25.2 MB per 1024x2048 frame). */
+int pidnet_forward_u8(pidnet_engine* h, void* stream, const unsigned char* bgr_hwc, const double* mean_rgb, const double* std_rgb,
+                      float* out_main, float* out_p, float* out_d, int use_graph);
+
 /* Kernel launches issued by one forward (for bench.py's `gpu_launches`). */
 int pidnet_num_launches(pidnet_engine* h);
 /* Algorithmic conv FLOPs (2*MACs, no padding waste) of one forward at the planned shape. */

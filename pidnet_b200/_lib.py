@@ -33,6 +33,7 @@ SIGNATURES = {
     'pidnet_set_param': (_i, [_vp, C.c_char_p, _vp, _i64p, _i]),
     'pidnet_plan': (_i, [_vp, _i, _i, _i, C.POINTER(C.c_size_t)]),
     'pidnet_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    'pidnet_forward_u8': (_i, [_vp, _vp, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp, _vp, _i]),
     'pidnet_num_launches': (_i, [_vp]),
     'pidnet_conv_flops': (C.c_double, [_vp]),
     'pidnet_profile': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),

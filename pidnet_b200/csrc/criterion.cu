@@ -834,7 +834,7 @@ cudaError_t launch_run(const CritParams& p, const SelState* sel, bool backward, 
 // F.interpolate -> [exp] -> argmax -> .cpu() of datasets/base_dataset.py:136-150 / tools/custom.py:90-92 and
 // get_confusion_matrix of utils/utils.py:129-152 without materialising the [N,C,H,W] fp32 tensor (159 MB per
 // 1024x2048 image).  The interpolation is evaluated in torch's operation order WITHOUT fma contraction so the class
-// index is bit-identical to the numpy restatement in oracle/postproc_oracle.py.
+// index is bit-identical to a plain fp32 restatement of that formula (what the parity tests compare against).
 struct PostParams {
   const float* x;            // [N,C,h,w] fp32 logits
   unsigned char* pred;       // [N,H,W] class index (optional)

@@ -140,6 +140,9 @@ struct T {  // NHWC bf16 view
 struct RunArgs {
   const float* x;
   float* out[3];  // main, p, d
+  // alternative input: uint8 HWC BGR frames + the input_transform constants (pidnet_forward_u8); x is then null
+  const uint8_t* x_u8 = nullptr;
+  const float* lut = nullptr;   // device [3][256]: input_transform of every byte value per model channel
 };
 
 struct Op {
@@ -625,6 +628,31 @@ struct Engine {
   int use_ws = 1;
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;  // capture origin (the caller's stream may be the legacy default stream)
+  // uint8 input path: per-channel table of the reference's input_transform (datasets/base_dataset.py:36-44), evaluated
+  // with numpy's arithmetic: `image / 255.0` is float32; `image -= mean` and `image /= std` (python-float lists) run in
+  // float64 and are rounded back to float32 after each statement
+  float* dev_lut = nullptr;
+  std::vector<float> host_lut;
+  double lut_mean[3] = {0, 0, 0}, lut_std[3] = {0, 0, 0};
+  const float* u8_lut(const double* mean, const double* stdv, cudaStream_t st) {
+    for (int c = 0; c < 3; ++c)
+      if (!(stdv[c] > 0.0)) fail("pidnet_forward_u8: std must be positive");
+    const bool same = dev_lut && std::memcmp(mean, lut_mean, sizeof(lut_mean)) == 0 && std::memcmp(stdv, lut_std, sizeof(lut_std)) == 0;
+    if (same) return dev_lut;
+    if (!dev_lut) CK(cudaMalloc(&dev_lut, 3 * 256 * sizeof(float)));
+    CK(cudaStreamSynchronize(st));   // the previous table may still be in use (rare path: the constants changed)
+    host_lut.resize(3 * 256);
+    for (int c = 0; c < 3; ++c)
+      for (int b = 0; b < 256; ++b) {
+        const float a = static_cast<float>(b) / 255.0f;
+        const float m = static_cast<float>(static_cast<double>(a) - mean[c]);
+        host_lut[c * 256 + b] = static_cast<float>(static_cast<double>(m) / stdv[c]);
+      }
+    CK(cudaMemcpy(dev_lut, host_lut.data(), host_lut.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::memcpy(lut_mean, mean, sizeof(lut_mean));
+    std::memcpy(lut_std, stdv, sizeof(lut_std));
+    return dev_lut;
+  }
   std::vector<cudaEvent_t> events;  // one per op that records
   std::vector<int> ev_of_op;
   cudaEvent_t ev_start = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -650,6 +678,7 @@ struct Engine {
     if (cap_stream) { cudaStreamDestroy(cap_stream); cap_stream = nullptr; }
     if (b.act_base) { cudaFree(b.act_base); b.act_base = nullptr; }
     if (b.wt_base) { cudaFree(b.wt_base); b.wt_base = nullptr; }
+    if (dev_lut) { cudaFree(dev_lut); dev_lut = nullptr; }
     planned = false;
   }
 
@@ -991,8 +1020,11 @@ struct Engine {
       x1.prod = b.add_op("conv1.0", {}, [ov, wd, bd, n_, h_, w_, sp, stem_tc, Pn, sms](cudaStream_t st, const RunArgs& a) mutable {
         if (stem_tc) {
           sp.x = a.x;
+          sp.x_u8 = a.x_u8;
+          sp.lut = a.lut;
           return stem_tc_launch(sp, Pn, sms, st);
         }
+        if (a.x_u8) return cudaErrorNotSupported;   // the uint8 path exists in the tcgen05 stem only
         return stem_conv_launch(a.x, n_, h_, w_, ov, wd, bd, st);
       });
       b.label(x1.prod, stem_tc ? "stem_tc" : "stem_conv", 4.0 * N * 3 * H * W + Builder::tbytes(x1),
@@ -1190,7 +1222,7 @@ struct Engine {
 
   void forward(cudaStream_t stream, const RunArgs& a, bool use_graph) {
     if (!planned) fail("pidnet_forward called before pidnet_plan");
-    if (!a.x || !a.out[0]) fail("null input/output pointer");
+    if ((!a.x && !a.x_u8) || !a.out[0]) fail("null input/output pointer");
     if (cfg.augment && (!a.out[1] || !a.out[2])) fail("augment=1 needs out_p and out_d");
     if (!use_graph) {
       enqueue(stream, a);
@@ -1319,6 +1351,17 @@ int pidnet_forward(pidnet_engine* h, void* stream, const float* x, float* out_ma
   return guard([&] {
     if (!h) fail("null handle");
     RunArgs a{x, {out_main, out_p, out_d}};
+    h->e.forward(reinterpret_cast<cudaStream_t>(stream), a, use_graph != 0);
+  });
+}
+
+int pidnet_forward_u8(pidnet_engine* h, void* stream, const unsigned char* bgr_hwc, const double* mean_rgb, const double* std_rgb,
+                      float* out_main, float* out_p, float* out_d, int use_graph) {
+  return guard([&] {
+    if (!h || !bgr_hwc || !mean_rgb || !std_rgb) fail("null argument");
+    RunArgs a{nullptr, {out_main, out_p, out_d}};
+    a.x_u8 = bgr_hwc;
+    a.lut = h->e.u8_lut(mean_rgb, std_rgb, reinterpret_cast<cudaStream_t>(stream));
     h->e.forward(reinterpret_cast<cudaStream_t>(stream), a, use_graph != 0);
   });
 }

@@ -28,6 +28,10 @@ cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, cons
 struct StemParams {
   CUtensorMap tmD;      // output as flat [rows = N*Ho*Wo][Cout] bf16, box {Cout, 128, 1, 1}, swizzle = Cout*2 bytes
   const float* x;       // fp32 NCHW image
+  // alternative input: uint8 HWC BGR frames as cv2.imread delivers them; the reference's
+  // input_transform (datasets/base_dataset.py:36-44: [..., ::-1] / 255 - mean, / std) is applied on load
+  const uint8_t* x_u8;  // [N,H,W,3] or nullptr
+  const float* lut;     // [3][256] device table: normalised value of byte b for model (RGB) channel c
   const uint8_t* w_swz; // [Cout][32] bf16 K-major (k = (ci*3+r)*3+s, zero padded), pre-swizzled SWIZZLE_64B
   const float* bias;    // [Cout]
   int H, W, Ho, Wo;

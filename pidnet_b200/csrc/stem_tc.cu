@@ -18,7 +18,7 @@ __device__ __forceinline__ uint32_t pk2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN>  // Cout (32 or 64)
+template <int BN, bool U8>  // Cout (32 or 64); U8: uint8 HWC BGR input normalised on load
 __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ StemParams p) {
   constexpr int kRowB = BN * 2;              // output row bytes == swizzle span of the store map
   __shared__ __align__(1024) uint8_t a_s[128 * 64];       // A tile: 128 rows x 64 B, SWIZZLE_64B
@@ -61,10 +61,30 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ St
       const long t1 = pix / p.Wo;
       const int oh = static_cast<int>(t1 % p.Ho);
       const int n = static_cast<int>(t1 / p.Ho);
-      const float* xn = p.x + static_cast<long>(n) * 3 * plane;
       const int ih0 = oh * 2 - 1, iw0 = ow * 2 - 1;
+      if (U8) {
+        const uint8_t* xn = p.x_u8 + static_cast<long>(n) * 3 * plane;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
+        for (int r = 0; r < 3; ++r) {
+          const int ih = ih0 + r;
+          const bool rok = ih >= 0 && ih < p.H;
+          const uint8_t* rp = xn + static_cast<long>(rok ? ih : 0) * p.W * 3;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int iw = iw0 + s;
+            if (rok && iw >= 0 && iw < p.W) {
+#pragma unroll
+              for (int ci = 0; ci < 3; ++ci) {   // model channel ci (RGB) = byte 2 - ci of the BGR pixel
+                // 256-entry table per channel, built on the host with numpy's exact arithmetic (engine.cu: u8_lut)
+                v[(ci * 3 + r) * 3 + s] = __ldg(p.lut + ci * 256 + __ldg(rp + iw * 3 + (2 - ci)));
+              }
+            }
+          }
+        }
+      }
+      const float* xn = p.x + static_cast<long>(n) * 3 * plane;
+#pragma unroll
+      for (int ci = 0; ci < 3 && !U8; ++ci)
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int ih = ih0 + r;
@@ -144,8 +164,12 @@ cudaError_t stem_tc_launch(const StemParams& p, int Cout, int num_sms, cudaStrea
   long blocks = p.tiles;
   const long cap = static_cast<long>(num_sms) * 8;
   if (blocks > cap) blocks = cap;
-  if (Cout == 32) stem_tc_kernel<32><<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
-  else if (Cout == 64) stem_tc_kernel<64><<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
+  if (p.x_u8) {
+    if (Cout == 32) stem_tc_kernel<32, true><<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
+    else if (Cout == 64) stem_tc_kernel<64, true><<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
+    else return cudaErrorInvalidValue;
+  } else if (Cout == 32) stem_tc_kernel<32, false><<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
+  else if (Cout == 64) stem_tc_kernel<64, false><<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

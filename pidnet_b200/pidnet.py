@@ -221,7 +221,8 @@ class PIDNet(nn.Module):
     # ----------------------------------------------------------------------- forward
     def forward(self, x):
         if self.training:
-            raise NotImplementedError('pidnet_b200: the training forward/backward is not built yet; call .eval()')
+            raise NotImplementedError('pidnet_b200: train-mode steps run through pidnet_b200.FullModel (forward + loss + '
+                                      'backward in one engine call); call .eval() for inference')
         if not x.is_cuda:
             raise RuntimeError('pidnet_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback')
         if x.dim() != 4 or x.shape[1] != 3:
@@ -243,6 +244,48 @@ class PIDNet(nn.Module):
                 C.c_void_p(outs[0].data_ptr()) if self.augment else None,
                 C.c_void_p(outs[2].data_ptr()) if self.augment else None, int(self.use_graph)))
         return outs if self.augment else out
+
+    # ----------------------------------------------------------------------- camera-frame input
+    IMAGENET_MEAN = (0.485, 0.456, 0.406)      # datasets/base_dataset.py:27-28, tools/custom.py:18-19 (RGB order)
+    IMAGENET_STD = (0.229, 0.224, 0.225)
+
+    def forward_u8(self, frames, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None, out_p=None, out_d=None, use_graph=None):
+        """Eval forward on uint8 HWC BGR frames [N,H,W,3] (what cv2.imread returns): the reference's input_transform
+        (datasets/base_dataset.py:36-44: BGR->RGB, /255, -mean, /std, HWC->CHW) is fused into the stem kernel, so the
+        result equals forward(input_transform(frames)) while the host->device copy is 4x smaller."""
+        if self.training:
+            raise NotImplementedError('forward_u8 is an inference entry point; call .eval()')
+        if not frames.is_cuda:
+            raise RuntimeError('pidnet_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback')
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
+            raise ValueError(f'expected uint8 frames [N,H,W,3], got {frames.dtype} {tuple(frames.shape)}')
+        frames = frames.contiguous()
+        N, H, W, _ = frames.shape
+        lib = self._sync(N, H, W, frames.device)
+        ncls = self._cfg['num_classes']
+        h8, w8 = H // 8, W // 8
+        mk = lambda c: torch.empty((N, c, h8, w8), device=frames.device, dtype=torch.float32)
+        out = mk(ncls) if out is None else out
+        if self.augment:
+            out_p = mk(ncls) if out_p is None else out_p
+            out_d = mk(1) if out_d is None else out_d
+        m3, s3 = (C.c_double * 3)(*mean), (C.c_double * 3)(*std)
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        with torch.cuda.device(frames.device):
+            _lib.check(lib.pidnet_forward_u8(
+                self._engine, C.c_void_p(stream), C.c_void_p(frames.data_ptr()), m3, s3, C.c_void_p(out.data_ptr()),
+                C.c_void_p(out_p.data_ptr()) if self.augment else None,
+                C.c_void_p(out_d.data_ptr()) if self.augment else None,
+                int(self.use_graph if use_graph is None else use_graph)))
+        return [out_p, out, out_d] if self.augment else out
+
+    def segment(self, frames, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        """tools/custom.py:86-92 on the device: uint8 BGR frames -> uint8 label maps [N,H,W] (fused input transform,
+        network, x8 align_corners upsample and argmax; only 3 B/pixel go up and 1 B/pixel comes back)."""
+        from .postprocess import upsample_argmax
+        outs = self.forward_u8(frames, mean, std)
+        logits = outs[1] if self.augment else outs
+        return upsample_argmax(logits, frames.shape[1:3])
 
     # ----------------------------------------------------------------------- introspection for tests / bench
     def forward_into(self, x, out, out_p=None, out_d=None, use_graph=True):

@@ -136,3 +136,34 @@ def test_state_dict_update_is_picked_up():
         ref = O.pidnet_forward(sd2, x.cpu())
     assert not torch.equal(a, b)
     assert O.rel_l2(b.cpu(), ref) < E2E_TOL
+
+
+@pytest.mark.gpu
+def test_forward_u8_equals_forward_of_input_transform():
+    """Row f2: uint8 BGR frames through the fused input transform == the reference's host-side input_transform
+    (datasets/base_dataset.py:36-44) followed by the fp32 forward -- bit-identical logits (same fp32 op order, same
+    bf16 rounding of the stem operand), incl. an odd geometry and the whole `segment` pipeline."""
+    import numpy as np
+    from oracle import postproc_oracle as PO
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    dev = torch.device('cuda:0')
+    cfg = O.config_for('pidnet_s', 19, False)
+    model = PIDNet(m=cfg['m'], n=cfg['n'], num_classes=19, planes=cfg['planes'], ppm_planes=cfg['ppm_planes'],
+                   head_planes=cfg['head_planes'], augment=False)
+    model.load_state_dict(O.make_state_dict(cfg, 1))
+    model = model.to(dev).eval()
+    rng = np.random.default_rng(0)
+    for (N, H, W) in [(2, 128, 256), (1, 72, 120)]:
+        frames = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+        # reference input_transform, numpy float32 exactly as written there
+        img = frames.astype(np.float32)[:, :, :, ::-1]
+        img = img / 255.0
+        img -= np.array([0.485, 0.456, 0.406], dtype=np.float64)
+        img /= np.array([0.229, 0.224, 0.225], dtype=np.float64)
+        x = torch.from_numpy(np.ascontiguousarray(img.transpose(0, 3, 1, 2))).to(dev)
+        want = model(x)
+        got = model.forward_u8(torch.from_numpy(frames).to(dev))
+        assert torch.equal(got, want)
+        seg = model.segment(torch.from_numpy(frames).to(dev))
+        assert np.array_equal(seg.cpu().numpy(), PO.argmax_labels(want.cpu().numpy(), H, W))
