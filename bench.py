@@ -174,6 +174,19 @@ def measured_peaks():
     return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source='B200_PROFILING.md fallback')
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of
+    this same command (profiles/r01/traffic.json, written by tools/ncu_traffic.py); None if that kernel was not captured."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01', 'traffic.json')
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        e = t.get(kernel)
+        return None if e is None else e['dram_bytes_per_launch']
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def make_model(a, dev):
     from pidnet_b200 import get_pred_model
     torch.manual_seed(0)
@@ -259,7 +272,7 @@ def run_ours(a):
             'achieved': tf if tensor_bound else gbs, 'peak': peaks['tc_sustained'] if tensor_bound else peaks['hbm'],
             'unit': 'TFLOP/s' if tensor_bound else 'GB/s',
             'frac': (tf / peaks['tc_sustained']) if tensor_bound else (gbs / peaks['hbm']),
-            'traffic': None, 'peak_source': peaks['source'] + (' bf16 sustained' if tensor_bound else ' hbm copy'),
+            'traffic': measured_traffic(dom['kernel']), 'peak_source': peaks['source'] + (' bf16 sustained' if tensor_bound else ' hbm copy'),
             'launches_per_step': dom['launches'], 'avg_launch_ms': dom['ms'] / dom['launches'],
             'algorithmic_gflop_per_launch': dom['flops'] / dom['launches'] / 1e9,
             'algorithmic_mb_per_launch': dom['bytes'] / dom['launches'] / 1e6,
@@ -279,6 +292,8 @@ def run_ours(a):
         # ---- e2e through the public API: pinned host input -> H2D -> PIDNet.forward -> D2H of the logits
         e2e_steps = max(4, min(a.steps, 12))
         line['e2e'] = run_e2e(model, a, dev, world, e2e_steps, x_host)
+        # the same loop on camera frames: 4x fewer bytes up, label maps instead of logits down
+        line['e2e_u8_pipeline'] = run_e2e(model, a, dev, world, e2e_steps, x_host, u8=True)
         # ---- batch-1 latency (north-star target < 2 ms), L2 flushed between iterations
         if rank == 0:
             line['latency_bs1'] = run_latency(a, dev, use_graph)
@@ -291,14 +306,23 @@ def run_ours(a):
         print(json.dumps(line), flush=True)
 
 
-def run_e2e(model, a, dev, world, steps, x_host):
+def run_e2e(model, a, dev, world, steps, x_host, u8=False):
     """Public-API loop: every step copies its pinned host batch to the GPU, calls model(x) and reads the
-    logits back; copies are double-buffered against compute on separate streams."""
+    logits back; copies are double-buffered against compute on separate streams.
+    u8=True: the tools/custom.py pipeline instead -- uint8 BGR frames up, `PIDNet.segment` (fused input transform,
+    network, x8 upsample + argmax), uint8 label maps down."""
     import torch.distributed as dist
     B, H, W = a.batch, a.height, a.width
-    hin = [x_host, x_host.clone().pin_memory()]
-    din = [torch.empty_like(x_host, device=dev) for _ in range(2)]
-    hout = [torch.empty(B, a.classes, H // 8, W // 8).pin_memory() for _ in range(2)]
+    if u8:
+        g = torch.Generator(device='cpu').manual_seed(99)
+        f0 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).pin_memory()
+        hin = [f0, f0.clone().pin_memory()]
+        din = [torch.empty_like(f0, device=dev) for _ in range(2)]
+        hout = [torch.empty(B, H, W, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    else:
+        hin = [x_host, x_host.clone().pin_memory()]
+        din = [torch.empty_like(x_host, device=dev) for _ in range(2)]
+        hout = [torch.empty(B, a.classes, H // 8, W // 8).pin_memory() for _ in range(2)]
     s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
@@ -320,7 +344,7 @@ def run_e2e(model, a, dev, world, steps, x_host):
                 if i >= 2:
                     s_cmp.wait_event(ev_read[k])       # previous logits of this slot are on the host
                 with torch.no_grad():
-                    outs[k] = model(din[k])
+                    outs[k] = model.segment(din[k]) if u8 else model(din[k])
                 ev_free[k].record(s_cmp)
                 ev_done[k].record(s_cmp)
             with torch.cuda.stream(s_out):
@@ -345,6 +369,11 @@ def run_e2e(model, a, dev, world, steps, x_host):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if u8:
+        return {'value': world * B * steps / (ms / 1e3), 'unit': UNIT, 'steps': steps, 'ms_per_step': ms / steps,
+                'wall_ms_per_step': wall * 1e3 / steps, 'h2d_bytes_per_step': B * 3 * H * W, 'd2h_bytes_per_step': B * H * W,
+                'api': 'pidnet_b200.PIDNet.segment (uint8 HWC BGR frames in, uint8 label maps out: input transform, '
+                       'network, x8 upsample + argmax on the device -- the tools/custom.py pipeline)'}
     return {'value': world * B * steps / (ms / 1e3), 'unit': UNIT, 'steps': steps, 'ms_per_step': ms / steps,
             'wall_ms_per_step': wall * 1e3 / steps,
             'h2d_bytes_per_step': B * 3 * H * W * 4, 'd2h_bytes_per_step': B * a.classes * (H // 8) * (W // 8) * 4,
