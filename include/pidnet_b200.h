@@ -190,9 +190,12 @@ int pidnet_train_debug_tensor(pidnet_trainer* h, const char* name, int grad, flo
  *             -- datasets/base_dataset.py:136-150 (`.exp()` is monotonic), tools/custom.py:90-92;
  *   confusion (optional) uint64 [C*C] += histogram of (label, prediction) over labels != ignore_label
  *             -- get_confusion_matrix, utils/utils.py:129-152 (row = ground truth, column = prediction).
- * The [N,C,H,W] tensor is never materialised.  All pointers are device pointers. */
+ * The [N,C,H,W] tensor is never materialised.  All pointers are device pointers.
+ * cell_mask_ws (optional): scratch of N*h*w uint32; when given, a first kernel marks per low-res cell the classes that can
+ * win anywhere inside it (all others are dominated at the four corners) and the per-pixel kernel interpolates only those --
+ * identical output, several times fewer interpolations on real logits. */
 int pidnet_postprocess(void* stream, const float* logits, int N, int C, int h, int w, int H, int W, unsigned char* pred,
-                       const int64_t* labels, int64_t ignore_label, unsigned long long* confusion);
+                       const int64_t* labels, int64_t ignore_label, unsigned long long* confusion, unsigned* cell_mask_ws);
 
 /* ---- optimizer step on flat buffers.
  * Replaces torch.optim.SGD.step() as configured in tools/train.py:139-148 (momentum, weight decay, optional Nesterov) for ALL

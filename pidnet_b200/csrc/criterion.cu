@@ -840,9 +840,76 @@ struct PostParams {
   unsigned char* pred;       // [N,H,W] class index (optional)
   const int64_t* labels;     // [N,H,W] (optional, with conf)
   unsigned long long* conf;  // [C*C] += (row = label, column = prediction)
+  const unsigned* cell_mask; // [N,h,w] candidate classes per low-res cell (argmax_cell_mask_kernel) or nullptr
   int N, C, h, w, H, W, staged;
   long ignore_label;
 };
+// Candidate classes per low-res cell: inside the cell spanned by the nodes (cy,cx)..(cy+1,cx+1) every upsampled logit
+// is a convex combination of the four corner logits, and fp32 rounding of that combination is monotone in each corner
+// value.  So class k can never be the FIRST maximum anywhere in the cell if some class j dominates it at all four
+// corners with j < k (ties go to the lower index), or strictly with a margin far above the rounding error when j > k.
+// Testing only the <= 4 corner leaders keeps it O(C); typical cells end up with one or two candidates, and the
+// per-pixel kernel then interpolates just those -- the result is identical to the exhaustive loop.
+template <int CMAX>
+__global__ void __launch_bounds__(128) argmax_cell_mask_kernel(const float* __restrict__ x, int N, int C, int h, int w,
+                                                               unsigned* __restrict__ mask) {
+  const long cell = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= static_cast<long>(N) * h * w) return;
+  const int cx = static_cast<int>(cell % w);
+  const long t1 = cell / w;
+  const int cy = static_cast<int>(t1 % h);
+  const int n = static_cast<int>(t1 / h);
+  const int x1 = min(cx + 1, w - 1), y1 = min(cy + 1, h - 1);
+  const size_t plane = static_cast<size_t>(h) * w;
+  const float* xn = x + static_cast<size_t>(n) * C * plane;
+  float v[CMAX][4], best[4], lv[4][4];
+  int lead[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { best[c] = -FLT_MAX; lead[c] = 0; }
+#pragma unroll
+  for (int k = 0; k < CMAX; ++k) {
+    if (k < C) {
+      const float* q = xn + k * plane;
+      v[k][0] = __ldg(q + cy * w + cx); v[k][1] = __ldg(q + cy * w + x1);
+      v[k][2] = __ldg(q + y1 * w + cx); v[k][3] = __ldg(q + y1 * w + x1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (k == 0 || v[k][c] > best[c]) {
+          best[c] = v[k][c]; lead[c] = k;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) lv[c][q4] = v[k][q4];
+        }
+      }
+    }
+  }
+  unsigned m = 0;
+#pragma unroll
+  for (int k = 0; k < CMAX; ++k) {
+    if (k < C) {
+      bool dominated = false;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = lead[c];
+        if (j == k) continue;
+        bool dom = true;
+        if (j < k) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) dom = dom && lv[c][q4] >= v[k][q4];
+        } else {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float margin = 1e-4f * fmaxf(1.f, fmaxf(fabsf(lv[c][q4]), fabsf(v[k][q4])));
+            dom = dom && (lv[c][q4] - v[k][q4] > margin);
+          }
+        }
+        dominated = dominated || dom;
+      }
+      if (!dominated) m |= 1u << k;
+    }
+  }
+  mask[cell] = m;
+}
+
 template <int CMAX>
 __global__ void __launch_bounds__(256) upsample_argmax_kernel(PostParams p) {
   extern __shared__ float lo[];                    // [C][kRLH][kRLW] when staged
@@ -854,7 +921,7 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(PostParams p) {
   const int ly0 = lerp_ac(ty * kRH, p.h, p.H).i0, lx0 = lerp_ac(tx * kRW, p.w, p.W).i0;
   const size_t plane = static_cast<size_t>(p.h) * p.w;
   const float* xn = p.x + static_cast<size_t>(n) * p.C * plane;
-  if (p.staged) {
+  if (p.staged && !p.cell_mask) {
     for (int i = threadIdx.x; i < p.C * kRLP; i += blockDim.x) {
       const int ch = i / kRLP, r = i - ch * kRLP;
       const int ly = min(ly0 + r / kRLW, p.h - 1), lx = min(lx0 + r % kRLW, p.w - 1);
@@ -877,9 +944,26 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(PostParams p) {
       const float wx1 = lx.l, wx0 = 1.f - lx.l;
       float best = -FLT_MAX;
       int arg = 0;
+      if (p.cell_mask) {
+        unsigned m = __ldg(p.cell_mask + (static_cast<size_t>(n) * p.h + ly.i0) * p.w + lx.i0);
+        if ((m & (m - 1)) == 0) {
+          arg = __ffs(m) - 1;                      // a single candidate: no interpolation needed
+        } else {
+          for (; m; m &= m - 1) {                  // ascending class index: the first maximum wins
+            const int k = __ffs(m) - 1;
+            const float* q = xn + k * plane;
+            const float a = __ldg(q + ly.i0 * p.w + lx.i0), b = __ldg(q + ly.i0 * p.w + lx.i1);
+            const float d = __ldg(q + ly.i1 * p.w + lx.i0), e = __ldg(q + ly.i1 * p.w + lx.i1);
+            const float top = __fadd_rn(__fmul_rn(wx0, a), __fmul_rn(wx1, b));
+            const float bot = __fadd_rn(__fmul_rn(wx0, d), __fmul_rn(wx1, e));
+            const float v = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
+            if (v > best) { best = v; arg = k; }
+          }
+        }
+      }
 #pragma unroll
       for (int k = 0; k < CMAX; ++k) {
-        if (k < p.C) {
+        if (k < p.C && !p.cell_mask) {
           float a, b, d, e;
           if (p.staged) {
             const float* q = lo + k * kRLP;
@@ -914,7 +998,12 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(PostParams p) {
 template <int CMAX>
 cudaError_t launch_post(const PostParams& p, cudaStream_t st) {
   const unsigned blocks = static_cast<unsigned>(p.N) * ((p.W + kRW - 1) / kRW) * ((p.H + kRH - 1) / kRH);
-  const size_t smem = p.staged ? static_cast<size_t>(p.C) * kRLP * sizeof(float) : 0;
+  const size_t smem = (p.staged && !p.cell_mask) ? static_cast<size_t>(p.C) * kRLP * sizeof(float) : 0;
+  if (p.cell_mask) {
+    const long cells = static_cast<long>(p.N) * p.h * p.w;
+    argmax_cell_mask_kernel<CMAX><<<static_cast<unsigned>((cells + 127) / 128), 128, 0, st>>>(p.x, p.N, p.C, p.h, p.w,
+                                                                                             const_cast<unsigned*>(p.cell_mask));
+  }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(upsample_argmax_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -1003,10 +1092,11 @@ cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaS
 }
 
 cudaError_t postprocess_launch(const float* x, int N, int C, int h, int w, int H, int W, unsigned char* pred,
-                               const int64_t* labels, long ignore_label, unsigned long long* conf, cudaStream_t st) {
+                               const int64_t* labels, long ignore_label, unsigned long long* conf, unsigned* cell_mask_ws,
+                               cudaStream_t st) {
   if (C < 1 || C > kMaxC) return cudaErrorInvalidValue;
   PostParams p;
-  p.x = x; p.pred = pred; p.labels = labels; p.conf = conf; p.N = N; p.C = C; p.h = h; p.w = w; p.H = H; p.W = W;
+  p.x = x; p.pred = pred; p.labels = labels; p.conf = conf; p.cell_mask = cell_mask_ws; p.N = N; p.C = C; p.h = h; p.w = w; p.H = H; p.W = W;
   p.ignore_label = ignore_label;
   CritParams fp;   // footprint test only
   fp.h = h; fp.w = w; fp.H = H; fp.W = W;

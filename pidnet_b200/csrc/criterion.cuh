@@ -30,9 +30,11 @@ struct CritParams {
 
 size_t criterion_workspace_bytes(int N, int H, int W);
 cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaStream_t st);
-// fused x8 upsample (align_corners=True) + argmax -> uint8 labels (optional) and/or confusion-matrix accumulation (optional)
+// fused x8 upsample (align_corners=True) + argmax -> uint8 labels (optional) and/or confusion-matrix accumulation (optional);
+// cell_mask_ws: optional device scratch of N*h*w uint32 enabling the candidate-pruned path (same result, fewer interpolations)
 cudaError_t postprocess_launch(const float* x, int N, int C, int h, int w, int H, int W, unsigned char* pred,
-                               const int64_t* labels, long ignore_label, unsigned long long* conf, cudaStream_t st);
+                               const int64_t* labels, long ignore_label, unsigned long long* conf, unsigned* cell_mask_ws,
+                               cudaStream_t st);
 cudaError_t upsample_ac_launch(const float* x, int NC, int h, int w, float* out, int H, int W, cudaStream_t st);
 
 }  // namespace pidnet

@@ -1667,14 +1667,14 @@ int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd) {
 
 // ---- post-processing
 int pidnet_postprocess(void* stream, const float* logits, int N, int C, int h, int w, int H, int W, unsigned char* pred,
-                       const int64_t* labels, int64_t ignore_label, unsigned long long* confusion) {
+                       const int64_t* labels, int64_t ignore_label, unsigned long long* confusion, unsigned* cell_mask_ws) {
   return guard([&] {
     if (!logits || (!pred && !confusion)) fail("pidnet_postprocess: nothing to compute (null logits, or neither pred nor confusion)");
     if (confusion && !labels) fail("pidnet_postprocess: the confusion matrix needs labels");
     if (N < 1 || h < 1 || w < 1 || H < 1 || W < 1) fail("pidnet_postprocess: empty tensor");
     if (C < 1 || C > 32) fail("pidnet_postprocess supports 1..32 classes");
     cudaError_t e = postprocess_launch(logits, N, C, h, w, H, W, pred, labels, static_cast<long>(ignore_label), confusion,
-                                       reinterpret_cast<cudaStream_t>(stream));
+                                       cell_mask_ws, reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) fail(std::string("pidnet_postprocess: ") + cudaGetErrorString(e));
   });
 }

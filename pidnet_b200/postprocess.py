@@ -12,7 +12,10 @@ import torch
 from . import _lib
 
 
-def _call(logits, size, pred, labels, ignore, conf):
+_MASK_WS = {}     # (device, numel) -> uint32 scratch for the per-cell candidate masks
+
+
+def _call(logits, size, pred, labels, ignore, conf, prune=True):
     if not logits.is_cuda:
         raise RuntimeError('pidnet_b200 post-processing runs on CUDA only; there is no CPU fallback')
     lib = _lib.load()
@@ -20,15 +23,23 @@ def _call(logits, size, pred, labels, ignore, conf):
     N, Cc, h, w = logits.shape
     H, W = int(size[0]), int(size[1])
     p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    ws = None
+    if prune and Cc > 1:
+        key = (logits.device, N * h * w)
+        ws = _MASK_WS.get(key)
+        if ws is None:
+            ws = _MASK_WS[key] = torch.empty(N * h * w, dtype=torch.int32, device=logits.device)
     with torch.cuda.device(logits.device):
         stream = torch.cuda.current_stream(logits.device).cuda_stream
-        _lib.check(lib.pidnet_postprocess(C.c_void_p(stream), p(logits), N, Cc, h, w, H, W, p(pred), p(labels), int(ignore), p(conf)))
+        _lib.check(lib.pidnet_postprocess(C.c_void_p(stream), p(logits), N, Cc, h, w, H, W, p(pred), p(labels), int(ignore),
+                                          p(conf), p(ws)))
 
 
-def upsample_argmax(logits, size):
-    """uint8 [N,H,W] == torch.argmax(F.interpolate(logits, size, mode='bilinear', align_corners=True), dim=1)."""
+def upsample_argmax(logits, size, prune=True):
+    """uint8 [N,H,W] == torch.argmax(F.interpolate(logits, size, mode='bilinear', align_corners=True), dim=1).
+    prune=False forces the exhaustive per-pixel class loop (same result; used by the parity tests)."""
     pred = torch.empty(logits.shape[0], int(size[0]), int(size[1]), dtype=torch.uint8, device=logits.device)
-    _call(logits, size, pred, None, -1, None)
+    _call(logits, size, pred, None, -1, None, prune)
     return pred
 
 

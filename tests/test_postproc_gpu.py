@@ -36,6 +36,7 @@ def test_upsample_argmax_bit_exact(shape):
     want = PO.argmax_labels(x.numpy(), H, W)
     assert pred.dtype == torch.uint8 and tuple(pred.shape) == (N, H, W)
     assert np.array_equal(pred.cpu().numpy(), want)
+    assert torch.equal(PP.upsample_argmax(x.to(dev), (H, W), prune=False), pred)      # exhaustive loop == candidate-pruned path
     # against torch on the device: identical away from fp32-rounding-level ties
     up = torch.nn.functional.interpolate(x.to(dev), size=(H, W), mode='bilinear', align_corners=True)
     assert (up.argmax(1) != pred.long()).float().mean() < (0.35 if C > 1 and h > 1 else 1.0)
@@ -57,6 +58,25 @@ def test_confusion_matrix_bit_exact(shape):
     assert ref_like.dtype == np.float64 and np.array_equal(ref_like, want)
     # size-independent property: every non-ignored pixel is counted exactly once
     assert int(cm.sum()) == 2 * int((labels != 255).sum())
+
+
+def test_pruned_path_on_smooth_and_adversarial_logits():
+    """The candidate pruning must be exact: smooth maps (one dominant class per cell), near-ties far below the pruning margin,
+    exact ties between a low and a high class index, constant maps."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    N, C, h, w, H, W = 2, 19, 24, 40, 192, 320
+    base = torch.nn.functional.interpolate(torch.randn(N, C, 4, 6, generator=g) * 4, size=(h, w), mode='bicubic')
+    cases = [base,                                                          # smooth
+             base + 1e-6 * torch.randn(N, C, h, w, generator=g),            # rounding-level perturbations
+             torch.zeros(N, C, h, w),                                       # all classes tie everywhere -> class 0
+             base.clone()]
+    cases[3][:, 7] = cases[3][:, 2]                                         # class 7 == class 2 exactly -> 2 wins its ties
+    cases.append(torch.randn(N, C, h, w, generator=g) * 1e-5)                # everything inside the margin
+    for x in cases:
+        got = PP.upsample_argmax(x.to(dev), (H, W))
+        assert np.array_equal(got.cpu().numpy(), PO.argmax_labels(x.numpy(), H, W))
+        assert torch.equal(got, PP.upsample_argmax(x.to(dev), (H, W), prune=False))
 
 
 def test_all_ignored_and_errors():
