@@ -26,8 +26,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # keep stdout to the single JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
-if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-    os.environ['NCCL_DEBUG'] = 'WARN'
+# (and at every higher level), so route NCCL's log to stderr and drop a bare VERSION request
+if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+    del os.environ['NCCL_DEBUG']
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 import torch  # noqa: E402
 

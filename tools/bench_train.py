@@ -4,8 +4,10 @@ synthetic 12 x 3 x 1024 x 1024 crops per GPU, NCCL all-reduce of the flat fp32 g
 Prints one JSON line (rank 0).  `torchrun --nproc-per-node N tools/bench_train.py` for N > 1."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-    os.environ['NCCL_DEBUG'] = 'WARN'
+# (and at every higher level), so route NCCL's log to stderr and drop a bare VERSION request
+if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+    del os.environ['NCCL_DEBUG']
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 import torch
 import torch.distributed as dist
 from pidnet_b200 import PIDNet, OhemCrossEntropy, BondaryLoss
