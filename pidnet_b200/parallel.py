@@ -33,6 +33,20 @@ def reduce_max(value, device=None):
     return float(t.item())
 
 
+def allreduce_flat_gradient(flat, numel=None, average=True):
+    """The ONE exchange step of data-parallel training: sum the flat fp32 gradient buffer
+    over all ranks and divide by the world size -- what nn.DataParallel's reduce-add to GPU 0 followed by
+    `losses.mean()` over replicas computes (tools/train.py:136, utils/function.py:44).  In place; 1 rank: identity.
+    Backend-agnostic (NCCL over NVLink on GPUs; gloo in the CPU tests)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat
+    view = flat if numel is None else flat[:numel]
+    dist.all_reduce(view, op=dist.ReduceOp.SUM)
+    if average:
+        view.div_(dist.get_world_size())
+    return flat
+
+
 class ShardedInference:
     """Runs `model` on this rank's slice of a global batch.  `gather=True` (tests / small batches only)
     all-gathers the logits so every rank sees the full result in the original order."""

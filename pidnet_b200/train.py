@@ -116,10 +116,8 @@ class EngineTrainer:
     def allreduce_gradients(self, average=True):
         """Sum (mean) the flat gradient over all ranks with one NCCL all-reduce (reference: DataParallel's
         reduce-add + `losses.mean()` over replicas, tools/train.py:136 / utils/function.py:44)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_grad[: self.n_param], op=dist.ReduceOp.SUM)
-            if average:
-                self.flat_grad[: self.n_param].div_(dist.get_world_size())
+        from .parallel import allreduce_flat_gradient
+        allreduce_flat_gradient(self.flat_grad, self.n_param, average)
 
 
 class _TrainStepFn(torch.autograd.Function):

@@ -36,6 +36,15 @@ def _worker(rank, world, port, ret):
         ref = _fake_model(g)
         ok = all(torch.equal(a, b) for a, b in zip(merged, ref))
         mx = PAR.reduce_max(10.0 + rank)
+        # the training exchange step: every rank ends with the MEAN of the per-rank flat gradients; the padding tail of
+        # the buffer (beyond numel) is not touched
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        PAR.allreduce_flat_gradient(flat, numel=8, average=True)
+        want = torch.arange(10, dtype=torch.float32) * 1.5
+        want[8:] = torch.arange(8, 10, dtype=torch.float32) * (rank + 1)
+        ok = ok and torch.equal(flat, want)
+        summed = PAR.allreduce_flat_gradient(torch.ones(4) * (rank + 1), average=False)
+        ok = ok and torch.equal(summed, torch.full((4,), 3.0))
         ret[rank] = (ok, mx)
     finally:
         dist.destroy_process_group()
