@@ -1006,7 +1006,7 @@ struct Engine {
       const uint8_t* wswd = reinterpret_cast<const uint8_t*>(b.alloc_wt(wsw.data(), wsw.size() * 2));
       StemParams sp;
       std::memset(&sp, 0, sizeof(sp));
-      sp.w_swz = wswd; sp.bias = bd; sp.H = H; sp.W = W; sp.Ho = x1.H; sp.Wo = x1.W;
+      sp.w_swz = wswd; sp.bias = bd; sp.H = H; sp.W = W; sp.Ho = x1.H; sp.Wo = x1.W; sp.relu = 1;
       sp.rows = static_cast<long>(N) * x1.H * x1.W;
       sp.tiles = (sp.rows + 127) / 128;
       if (stem_tc && !b.dry) {

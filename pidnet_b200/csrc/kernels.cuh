@@ -36,8 +36,11 @@ struct StemParams {
   const float* bias;    // [Cout]
   int H, W, Ho, Wo;
   long rows, tiles;     // N*Ho*Wo, ceil(rows / 128)
+  int relu;             // 1: inference (bias + ReLU); 0: training (raw conv output, BatchNorm follows)
 };
 cudaError_t stem_tc_launch(const StemParams& p, int Cout, int num_sms, cudaStream_t st);
+// training: fp32 [Cout][3][3][3] master weights -> the pre-swizzled bf16 [Cout][32] tile of the kernel above
+cudaError_t stem_pack_launch(const float* w, uint8_t* w_swz, int Cout, cudaStream_t st);
 
 // ---- PagFM fuse (model_utils.py:292-312 after the low-res algebra of DESIGN.md):
 //   low = [y | z | t | pad] at (h,w);  s = <x, U(z)> + U(t);  g = sigmoid(s);  out = relu((1-g) x + g U(y))

@@ -137,7 +137,10 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ St
         uint4 o;
         float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(acc[j * 8 + e]) + bias_s[c + e], 0.f);
+        for (int e = 0; e < 8; ++e) {
+          f[e] = __uint_as_float(acc[j * 8 + e]) + bias_s[c + e];
+          if (p.relu) f[e] = fmaxf(f[e], 0.f);
+        }
         o.x = pk2(f[0], f[1]); o.y = pk2(f[2], f[3]); o.z = pk2(f[4], f[5]); o.w = pk2(f[6], f[7]);
         *reinterpret_cast<uint4*>(o_s + row * kRowB + (((c >> 3) ^ o_swz) << 4)) = o;
       }
@@ -158,7 +161,21 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ St
   if (warp == 0) tmem_dealloc<BN>(tmem);
 }
 
+__global__ void stem_pack_kernel(const float* __restrict__ w, uint16_t* __restrict__ wsw, int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 32) return;
+  const int co = i >> 5, k = i & 31;
+  const int chunk = k >> 3, within = k & 7;
+  const __nv_bfloat16 v = __float2bfloat16_rn(k < 27 ? w[co * 27 + k] : 0.f);
+  wsw[co * 32 + ((chunk ^ ((co >> 1) & 3)) * 8) + within] = *reinterpret_cast<const uint16_t*>(&v);
+}
+
 }  // namespace
+
+cudaError_t stem_pack_launch(const float* w, uint8_t* w_swz, int Cout, cudaStream_t st) {
+  stem_pack_kernel<<<(Cout * 32 + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<uint16_t*>(w_swz), Cout);
+  return cudaGetLastError();
+}
 
 cudaError_t stem_tc_launch(const StemParams& p, int Cout, int num_sms, cudaStream_t st) {
   long blocks = p.tiles;
