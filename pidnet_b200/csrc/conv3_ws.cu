@@ -34,7 +34,7 @@ namespace {
 
 constexpr int kWsThreads = 384;
 constexpr int kTH = 16, kTW = 8, kPH = 18, kPW = 10;
-constexpr int kMaxPatch = 8;
+constexpr int kMaxPatch = 16;
 
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   const uint32_t stage_base = patch_base + npatch * G::kPatchStride;
   uint8_t* stage_gen = smem_gen + w_bytes + npatch * G::kPatchStride;
   const uint32_t bar_base = stage_base + 2 * kStageBytes;
-  // barriers (8 B each): w_full | patch_full[8] | patch_empty[8] | tmem_full[4] | tmem_empty[4] | res_full[2] |
-  //                      stage_free[2] | stage_ready[2]
+  // barriers (8 B each): w_full | patch_full[kMaxPatch] | patch_empty[kMaxPatch] | tmem_full[4] | tmem_empty[4] |
+  //                      res_full[2] | stage_free[2] | stage_ready[2] | tmem slot  -- 8 * (16 + 2 * kMaxPatch) <= 512 bytes
   const uint32_t w_full = bar_base;
   auto patch_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto patch_empty = [&](int s) { return bar_base + 8u * (1 + kMaxPatch + s); };
@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   auto stage_free = [&](int b) { return bar_base + 8u * (11 + 2 * kMaxPatch + b); };
   auto stage_ready = [&](int b) { return bar_base + 8u * (13 + 2 * kMaxPatch + b); };
   const uint32_t tmem_slot = bar_base + 8u * (15 + 2 * kMaxPatch);
-  float* bias_s = reinterpret_cast<float*>(stage_gen + 2 * kStageBytes + 256);   // BN floats after the barriers
+  static_assert(8 * (16 + 2 * kMaxPatch) <= 512, "barrier block overlaps the bias table");
+  float* bias_s = reinterpret_cast<float*>(stage_gen + 2 * kStageBytes + 512);   // BN floats (<= 512 B) after the barriers
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
       stage_gen + 2 * kStageBytes + 8 * (15 + 2 * kMaxPatch));
 
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
                         (first ? c : c - p.chunks0) * CK, w0, 0, 0);
           }
         }
-        if (p.has_res) {
+        if (p.has_res && p.out_mode != kOutNHWCbf16) {   // (bf16 outputs: the store warp prefetches residuals, see below)
           const int b = i & 1;
           const uint32_t u = static_cast<uint32_t>(i >> 1);
           mbar_wait(stage_free(b), (u & 1) ^ 1);
@@ -230,6 +231,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   } else if (warp == 11) {
     // ============================== TMA store warp ==============================
     if (p.out_mode == kOutNHWCbf16 && elect_one()) {
+      // This thread also prefetches the residual tiles: the staging buffer of lane b is free exactly when this thread has
+      // seen its store read the buffer out, so the residual of the lane's NEXT tile is requested right there (the TMA
+      // producer never blocks on a staging buffer, which used to serialise its patch loads behind the epilogue).
+      auto load_residual = [&](int tile, int b) {
+        int w0, h0, n;
+        tile_coord(tile, w0, h0, n);
+        mbar_arrive_expect_tx(res_full(b), kStageBytes);
+        for (int sl = 0; sl < kNumSlabs; ++sl)
+          tma_load_4d(stage_base + b * kStageBytes + sl * kSlabBytes, &p.tmR, res_full(b), c_out0 + sl * kSlabC, w0, h0, n);
+      };
+      if (p.has_res) {
+        tma_prefetch_desc(&p.tmR);
+        for (int b = 0; b < 2; ++b) {
+          const long t0 = static_cast<long>(blockIdx.x) + static_cast<long>(b) * gridDim.x;
+          if (t0 < m_tiles) load_residual(static_cast<int>(t0), b);
+        }
+      }
       int i = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
         int w0, h0, n;
@@ -242,7 +260,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
             tma_store_4d(&p.tmD, stage_base + b * kStageBytes + sl * kSlabBytes, c_out0 + sl * kSlabC, w0, h0, n);
         tma_store_commit();
         tma_store_wait_read();       // smem of this buffer has been read out
-        mbar_arrive(stage_free(b));
+        const long next = static_cast<long>(tile) + 2L * gridDim.x;
+        if (p.has_res) { if (next < m_tiles) load_residual(static_cast<int>(next), b); }
+        else mbar_arrive(stage_free(b));
       }
       tma_store_wait_all();
     }
