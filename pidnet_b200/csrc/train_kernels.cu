@@ -338,23 +338,32 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_fwd_fused_kernel(BnFwdParams
     float sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sc[e] = red[cg * 8 + e]; sh[e] = red[C + cg * 8 + e]; }
+    // four pixels per trip: all loads of the batch are issued before the first use (the parked vectors cover only the
+    // first stage_iters trips; the rest comes back from L2)
     int it = 0;
-    for (long q = p0 + ln; q < p1; q += lanes, ++it) {
-      const uint4 u = it < p.stage_iters ? park[it * kBnThreads + threadIdx.x]
-                                         : __ldg(reinterpret_cast<const uint4*>(p.x.ptr + q * p.x.ps + cg * 8));
-      F8 f = unpack8(u);
+    for (long q = p0 + ln; q < p1; q += static_cast<long>(lanes) * 4, it += 4) {
+      uint4 u[4], r[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f.v[e] = fmaf(f.v[e], sc[e], sh[e]);
-      if (p.res.ptr) {
-        const F8 r = ld8(p.res.ptr + q * p.res.ps + cg * 8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f.v[e] += r.v[e];
+      for (int k = 0; k < 4; ++k) {
+        const long qq = q + static_cast<long>(k) * lanes;
+        const bool ok = qq < p1;
+        u[k] = it + k < p.stage_iters ? park[(it + k) * kBnThreads + threadIdx.x]
+                                      : (ok ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : make_uint4(0, 0, 0, 0));
+        r[k] = (ok && p.res.ptr) ? __ldg(reinterpret_cast<const uint4*>(p.res.ptr + qq * p.res.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
       }
-      if (p.relu) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f.v[e] = fmaxf(f.v[e], 0.f);
+      for (int k = 0; k < 4; ++k) {
+        const long qq = q + static_cast<long>(k) * lanes;
+        if (qq >= p1) break;
+        F8 f = unpack8(u[k]);
+        const F8 rv = unpack8(r[k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f.v[e] = fmaf(f.v[e], sc[e], sh[e]) + rv.v[e];
+          if (p.relu) f.v[e] = fmaxf(f.v[e], 0.f);
+        }
+        st8(p.z.ptr + qq * p.z.ps + cg * 8, f);
       }
-      st8(p.z.ptr + q * p.z.ps + cg * 8, f);
     }
   }
 }
@@ -437,39 +446,46 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
 #pragma unroll
     for (int e = 0; e < 8; ++e) { cA[e] = red[cg * 8 + e]; cB[e] = red[C + cg * 8 + e]; cD[e] = red[2 * C + cg * 8 + e]; }
     int it = 0;
-    for (long q = p0 + ln; q < p1; q += lanes, ++it) {
-      F8 xv, g;
-      if (it < p.stage_iters) {
-        xv = unpack8(park[(it * 2 + 0) * kBnThreads + threadIdx.x]);
-        g = unpack8(park[(it * 2 + 1) * kBnThreads + threadIdx.x]);
-      } else {
-        xv = ld8(p.x.ptr + q * p.x.ps + cg * 8);
-        g = ld8(p.dz.ptr + q * p.dz.ps + cg * 8);
-        if (p.relu) {
-          const F8 zv = ld8(p.z.ptr + q * p.z.ps + cg * 8);
+    for (long q = p0 + ln; q < p1; q += static_cast<long>(lanes) * 2, it += 2) {   // two pixels per trip, loads first
+      uint4 ux[2], ug[2], uz[2], ur[2], uo[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const long qq = q + static_cast<long>(k) * lanes;
+        const bool ok = qq < p1, parked = it + k < p.stage_iters;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        ux[k] = parked ? park[((it + k) * 2 + 0) * kBnThreads + threadIdx.x]
+                       : (ok ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : zero);
+        ug[k] = parked ? park[((it + k) * 2 + 1) * kBnThreads + threadIdx.x]
+                       : (ok ? __ldg(reinterpret_cast<const uint4*>(p.dz.ptr + qq * p.dz.ps + cg * 8)) : zero);
+        uz[k] = (!parked && ok && p.relu) ? __ldg(reinterpret_cast<const uint4*>(p.z.ptr + qq * p.z.ps + cg * 8)) : zero;
+        ur[k] = (ok && p.dres.ptr && p.acc_dres) ? *reinterpret_cast<const uint4*>(p.dres.ptr + qq * p.dres.ps + cg * 8) : zero;
+        uo[k] = (ok && p.dx.ptr && p.acc_dx) ? *reinterpret_cast<const uint4*>(p.dx.ptr + qq * p.dx.ps + cg * 8) : zero;
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const long qq = q + static_cast<long>(k) * lanes;
+        if (qq >= p1) break;
+        const F8 xv = unpack8(ux[k]);
+        F8 g = unpack8(ug[k]);
+        if (p.relu && !(it + k < p.stage_iters)) {   // parked gradients are already masked
+          const F8 zv = unpack8(uz[k]);
 #pragma unroll
           for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
         }
-      }
-      if (p.dres.ptr) {
-        F8 r = g;
-        if (p.acc_dres) {
-          const F8 o = ld8(p.dres.ptr + q * p.dres.ps + cg * 8);
+        if (p.dres.ptr) {
+          const F8 old = unpack8(ur[k]);
+          F8 r;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) r.v[e] += o.v[e];
+          for (int e = 0; e < 8; ++e) r.v[e] = g.v[e] + old.v[e];
+          st8(p.dres.ptr + qq * p.dres.ps + cg * 8, r);
         }
-        st8(p.dres.ptr + q * p.dres.ps + cg * 8, r);
-      }
-      if (p.dx.ptr) {
-        F8 o;
+        if (p.dx.ptr) {
+          const F8 old = unpack8(uo[k]);
+          F8 o;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o.v[e] = fmaf(cA[e], g.v[e], fmaf(cB[e], xv.v[e], cD[e]));
-        if (p.acc_dx) {
-          const F8 old = ld8(p.dx.ptr + q * p.dx.ps + cg * 8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o.v[e] += old.v[e];
+          for (int e = 0; e < 8; ++e) o.v[e] = fmaf(cA[e], g.v[e], fmaf(cB[e], xv.v[e], cD[e])) + old.v[e];
+          st8(p.dx.ptr + qq * p.dx.ps + cg * 8, o);
         }
-        st8(p.dx.ptr + q * p.dx.ps + cg * 8, o);
       }
     }
   }
