@@ -175,6 +175,9 @@ int pidnet_train_plan(pidnet_trainer* h, int N, int H, int W, size_t* arena_byte
 int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x_nchw, const int64_t* labels, const float* bd_gt,
                       const float* class_weights, const pidnet_criterion_cfg* cfg, int backward, float* out12,
                       float* out_main, float* out_p, float* out_d);
+/* PIDNet.forward in train mode (models/pidnet.py:136-182 with nn.BatchNorm2d in training mode): batch statistics, running
+ * statistics updated, the three low-res outputs copied to the optional device buffers; no criterion, no backward */
+int pidnet_train_forward(pidnet_trainer* h, void* stream, const float* x_nchw, float* out_main, float* out_p, float* out_d);
 int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd);
 /* options: "use_graph" 1 (default: the step replays two CUDA graphs after one eager step) | 0 (eager launches);
  *          "overlap_wgrad" 1 (default: weight-gradient GEMMs run on a side stream next to the dgrad chain) | 0;

@@ -59,6 +59,7 @@ SIGNATURES = {
     'pidnet_train_profile': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(CriterionCfg), C.c_char_p, C.c_size_t, C.POINTER(C.c_float)]),
     'pidnet_train_debug_tensor': (_i, [_vp, C.c_char_p, _i, _vp, _i64p]),
     'pidnet_train_num_launches': (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    'pidnet_train_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     'pidnet_train_set_option': (_i, [_vp, C.c_char_p, _i]),
     'pidnet_postprocess': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_int64, _vp, _vp]),
     'pidnet_sgd_step': (_i, [_vp, _vp, _vp, _vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, _i, _i, C.c_float]),

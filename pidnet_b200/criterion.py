@@ -127,12 +127,11 @@ class FullModel(nn.Module):
         from .pidnet import PIDNet
         if not isinstance(self.model, PIDNet):
             raise TypeError('pidnet_b200.FullModel trains pidnet_b200.PIDNet models only (call .eval() for loss evaluation)')
-        if getattr(self, '_trainer', None) is None:
-            self._trainer = EngineTrainer(self.model)
+        trainer = self.model.engine_trainer()
         names = [k for k, _ in self.model.named_parameters()]
         params = [p for _, p in self.model.named_parameters()]
         wt = self.sem_loss.criterion.weight
-        res = _TrainStepFn.apply(self._trainer, inputs, labels, bd_gt, wt, self._crit.cfg, names, *params)
+        res = _TrainStepFn.apply(trainer, inputs, labels, bd_gt, wt, self._crit.cfg, names, *params)
         loss, out12, x_p, x_m, x_d = res
         h, w = labels.size(1), labels.size(2)
         ups = [upsample_align_corners(o, (h, w)) for o in (x_p, x_m)] if self.return_outputs else []
@@ -141,10 +140,7 @@ class FullModel(nn.Module):
     @property
     def trainer(self):
         """The `EngineTrainer` behind the train-mode forward (created on first use)."""
-        from .train import EngineTrainer
-        if getattr(self, '_trainer', None) is None:
-            self._trainer = EngineTrainer(self.model)
-        return self._trainer
+        return self.model.engine_trainer()
 
     def check_valid(self, out):
         """The reference raises IndexError when an OHEM set has no valid pixel (criterion.py:73)."""

@@ -1612,6 +1612,20 @@ int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x, const int
     if (out_d) CK(cudaMemcpyAsync(out_d, t.logits[2], lp * 4, cudaMemcpyDeviceToDevice, st));
   });
 }
+/* train-mode forward only (batch statistics, running-stat update), no criterion / backward */
+int pidnet_train_forward(pidnet_trainer* h, void* stream, const float* x, float* out_main, float* out_p, float* out_d) {
+  return guard([&] {
+    if (!h || !x) fail("null argument");
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    pidnet_criterion_cfg none{};
+    t.step(st, x, nullptr, nullptr, nullptr, none, false);
+    const size_t lp = static_cast<size_t>(t.N) * t.h8 * t.w8;
+    if (out_main) CK(cudaMemcpyAsync(out_main, t.logits[0], lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
+    if (out_p) CK(cudaMemcpyAsync(out_p, t.logits[1], lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
+    if (out_d) CK(cudaMemcpyAsync(out_d, t.logits[2], lp * 4, cudaMemcpyDeviceToDevice, st));
+  });
+}
 /* measurement: per-launch device times of one training step.  Writes a text table (one line per launch:
  * "F|B <ms> <kernel> <name>") into buf; returns the criterion time separately. */
 int pidnet_train_profile(pidnet_trainer* h, void* stream, const float* x, const int64_t* labels, const float* bd_gt,

@@ -221,8 +221,17 @@ class PIDNet(nn.Module):
     # ----------------------------------------------------------------------- forward
     def forward(self, x):
         if self.training:
-            raise NotImplementedError('pidnet_b200: train-mode steps run through pidnet_b200.FullModel (forward + loss + '
-                                      'backward in one engine call); call .eval() for inference')
+            # train-mode forward (batch statistics + running-stat update).  Gradients only exist through
+            # pidnet_b200.FullModel, which runs forward + loss + backward as ONE engine step.
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                raise NotImplementedError('pidnet_b200: a differentiable train-mode forward runs through pidnet_b200.FullModel '
+                                          '(forward + loss + backward in one engine call); wrap the call in torch.no_grad() for a '
+                                          'statistics-only forward, or call .eval() for inference')
+            if not self.augment:
+                raise NotImplementedError('pidnet_b200: the train-mode engine needs augment=True (three outputs)')
+            if not x.is_cuda:
+                raise RuntimeError('pidnet_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback')
+            return self.engine_trainer().forward_train(x)
         if not x.is_cuda:
             raise RuntimeError('pidnet_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback')
         if x.dim() != 4 or x.shape[1] != 3:
@@ -244,6 +253,14 @@ class PIDNet(nn.Module):
                 C.c_void_p(outs[0].data_ptr()) if self.augment else None,
                 C.c_void_p(outs[2].data_ptr()) if self.augment else None, int(self.use_graph)))
         return outs if self.augment else out
+
+    def engine_trainer(self):
+        """The ONE `EngineTrainer` of this model (it owns the flat parameter / gradient buffers the parameters point into),
+        shared by `FullModel`, the train-mode forward and `FusedSGD`."""
+        from .train import EngineTrainer
+        if getattr(self, '_engine_trainer', None) is None:
+            object.__setattr__(self, '_engine_trainer', EngineTrainer(self))
+        return self._engine_trainer
 
     # ----------------------------------------------------------------------- camera-frame input (SURVEY 8 row f2)
     IMAGENET_MEAN = (0.485, 0.456, 0.406)      # datasets/base_dataset.py:27-28, tools/custom.py:18-19 (RGB order)

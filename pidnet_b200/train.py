@@ -102,6 +102,24 @@ class EngineTrainer:
         self.flat_nbt += 1                                      # nn.BatchNorm2d.num_batches_tracked of every layer
         return self.out12, outs
 
+    def forward_train(self, x):
+        """Train-mode forward only (batch statistics, running-stat update): [x_extra_p, x_, x_extra_d], no autograd graph."""
+        x = x.contiguous().float()
+        N, _, H, W = x.shape
+        with torch.cuda.device(self.device):
+            if self.planned != (N, H, W):
+                _lib.check(self.lib.pidnet_train_plan(self.h, N, H, W, None))
+                self.planned = (N, H, W)
+            ncls = self.model._cfg['num_classes']
+            outs = [torch.empty(N, ncls, H // 8, W // 8, device=self.device), torch.empty(N, ncls, H // 8, W // 8, device=self.device),
+                    torch.empty(N, 1, H // 8, W // 8, device=self.device)]
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.pidnet_train_forward(self.h, C.c_void_p(stream), C.c_void_p(x.data_ptr()),
+                                                     C.c_void_p(outs[1].data_ptr()), C.c_void_p(outs[0].data_ptr()),
+                                                     C.c_void_p(outs[2].data_ptr())))
+        self.flat_nbt += 1
+        return outs
+
     def set_option(self, name, value):
         """Engine option of the training path: "use_graph" (1 = replay CUDA graphs after the first step)."""
         _lib.check(self.lib.pidnet_train_set_option(self.h, name.encode(), int(value)))
