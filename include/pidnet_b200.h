@@ -181,7 +181,8 @@ int pidnet_train_forward(pidnet_trainer* h, void* stream, const float* x_nchw, f
 int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd);
 /* options: "use_graph" 1 (default: the step replays two CUDA graphs after one eager step) | 0 (eager launches);
  *          "overlap_wgrad" 1 (default: weight-gradient GEMMs run on a side stream next to the dgrad chain) | 0;
- *          "fused_bn" 1 (default: single-launch BatchNorm kernels with a grid barrier) | 0 (3-kernel form; re-plan) */
+ *          "fused_bn" 1 (default: single-launch BatchNorm kernels with a grid barrier) | 0 (3-kernel form; re-plan);
+ *          "wgrad_halo" 1 (default: halo-patch weight-gradient kernel for 3x3 stride-1 convs) | 0 (tap-by-tap; re-plan) */
 int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value);
 int pidnet_train_profile(pidnet_trainer* h, void* stream, const float* x_nchw, const int64_t* labels, const float* bd_gt,
                          const float* class_weights, const pidnet_criterion_cfg* cfg, char* buf, size_t cap, float* crit_ms);

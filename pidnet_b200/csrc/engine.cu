@@ -1679,6 +1679,10 @@ int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value) {
     if (std::string(name) == "use_graph") {
       t.use_graph = value != 0;
       t.drop_graphs();
+    } else if (std::string(name) == "wgrad_halo") {
+      t.wgrad_halo = value != 0;
+      t.planned = false;   // needs a re-plan
+      t.drop_graphs();
     } else if (std::string(name) == "fused_bn") {
       t.fused_bn = value != 0;
       t.planned = false;   // needs a re-plan

@@ -86,6 +86,8 @@ struct WgradParams {
   int Cout, Cin, Cin_total, ci_off, k;
   float* dW;                       // [Cout][Cin_total][k][k] fp32
   float* ws;                       // split-K partials: [split][co tile][z][128 rows][T taps][64 ci] fp32
+  int halo;                        // 1: 3x3 stride-1 halo-patch kernel (16x8-pixel tiles: tmY box {64,16,8,1}, tmX[0] box {64,18,10,1},
+                                   //    5 taps per CTA, grid.z = ci tiles * 2)
 };
 constexpr int kWgradTileFloats = 128 * 64;   // per tap
 struct WgradLaunch {

@@ -142,6 +142,136 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   if (warp == 1) tmem_dealloc<kCols>(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 stride-1 variant with a HALO patch: per 16x8-pixel output tile the CTA loads dY once and ONE 18x10-pixel box of X;
+// the B operand of tap (r, s) and pixel row k is the 16 consecutive patch rows starting at ((k + r) * 18 + s) -- a
+// descriptor start shifted by whole 128-byte rows inside the TMA-written patch (the swizzle is a function of absolute
+// smem address bits, same trick as conv3_ws.cu).  Five taps per CTA (groups {0..4}, {5..8}: 5 x 64 fp32 TMEM columns), so X
+// is read twice per ci tile instead of nine times and dY twice instead of three times: the tap-by-tap form above is
+// L2->SM bandwidth bound on these layers, this one is bound by the MMA smem-operand rate.
+constexpr int kHT = 5;
+constexpr int kHStages = 3;
+constexpr int kHABytes = 2 * 16384;                 // dY: two 64-co blocks of [128 px][128 B]
+constexpr int kHPatchBytes = 18 * 10 * 128;         // 23040
+constexpr int kHBBytes = 23552;                     // padded to a 1 KB multiple
+constexpr int kHStageBytes = kHABytes + kHBBytes;   // 56320
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + kHStages * kHStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kHStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kHStages);
+  const uint32_t tmem_slot = done_bar + 8u;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + kHStages * kHStageBytes + 8 * (2 * kHStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci_tile = blockIdx.z >> 1, grp = blockIdx.z & 1;
+  const int co0 = blockIdx.y * 128, ci0 = ci_tile * 64;
+  const int tap0 = grp * kHT;
+  const int ntap = min(kHT, 9 - tap0);
+  const int per_img = p.tiles_w * p.tiles_h;
+  const int m_tiles = p.N * per_img;
+  const bool second_a = co0 + 64 < p.Cout;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kHStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+
+  int my_tiles = 0;
+  for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) ++my_tiles;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+        const int n = tile / per_img;
+        const int rem = tile - n * per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        const int w0 = tw * 16, h0 = th * 8;
+        const int st = it % kHStages;
+        const uint32_t ph = (it / kHStages) & 1;
+        mbar_wait(empty_bar(st), ph ^ 1);
+        mbar_arrive_expect_tx(full_bar(st), (second_a ? 2 : 1) * 16384 + kHPatchBytes);
+        const uint32_t sb = base + st * kHStageBytes;
+        tma_load_4d(sb, &p.tmY, full_bar(st), co0, w0, h0, n);
+        if (second_a) tma_load_4d(sb + 16384, &p.tmY, full_bar(st), co0 + 64, w0, h0, n);
+        tma_load_4d(sb + kHABytes, &p.tmX[0], full_bar(st), ci0, w0 - 1, h0 - 1, n);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+    // A: 64-co blocks 16384 B apart (LBO), 8-pixel atoms 1024 B apart (SBO); B: one 64-ci block
+    constexpr uint64_t a_hi = (static_cast<uint64_t>(16384 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                              (1ull << 46) | (2ull << 61);
+    constexpr uint64_t b_hi = (static_cast<uint64_t>(8192 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                              (1ull << 46) | (2ull << 61);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int st = it % kHStages;
+      const uint32_t ph = (it / kHStages) & 1;
+      mbar_wait(full_bar(st), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sb = base + st * kHStageBytes;
+#pragma unroll
+        for (int j = 0; j < kHT; ++j) {
+          if (j < ntap) {
+            const int tap = tap0 + j, r = tap / 3, s = tap - 3 * r;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {   // k = pixel row of the tile = 16 pixels = one K16 step
+              const uint64_t a_desc = a_hi | static_cast<uint64_t>(((sb + k * 2048) & 0x3FFFF) >> 4);
+              const uint64_t b_desc = b_hi | static_cast<uint64_t>(((sb + kHABytes + ((k + r) * 18 + s) * 128) & 0x3FFFF) >> 4);
+              umma_bf16(tmem + j * 64, a_desc, b_desc, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(empty_bar(st));
+        if (it == my_tiles - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+    }
+  } else if (my_tiles > 0) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* tile = p.ws + ((static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * gridDim.z + blockIdx.z) *
+                             (static_cast<size_t>(kHT) * kWgradTileFloats);
+    const int nci = min(64, p.Cin - ci0);
+    for (int j = 0; j < ntap; ++j) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (g * 32 >= nci) break;   // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem + j * 64 + g * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          float4* dst = reinterpret_cast<float4*>(tile + (static_cast<size_t>(q * 32 + lane) * kHT + j) * 64 + g * 32);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                 __uint_as_float(v[4 * e + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+constexpr size_t kHSmem = static_cast<size_t>(kHStages) * kHStageBytes + 256 + 1024;
+
 // dW[co][ci_off + ci][r][s] += sum over splits of the partial tiles (one thread per gradient element)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(WgradParams p, int T, int splits, int co_tiles, int nz) {
   const long total = static_cast<long>(p.Cout) * p.ntaps * p.Cin;
@@ -177,11 +307,16 @@ cudaError_t wgrad_tc_init() {
   cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(wg_smem<1>()));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wg_smem<3>()));
+  e = cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wg_smem<3>()));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHSmem));
 }
 
 cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
-  if (L.taps_per_group == 1) wgrad_tc_kernel<1><<<L.grid, kWgThreads, wg_smem<1>(), st>>>(L.p);
+  if (L.p.halo) {
+    if (L.taps_per_group != kHT || L.p.ntaps != 9 || (L.grid.z & 1)) return cudaErrorInvalidValue;
+    wgrad_halo_kernel<<<L.grid, kWgThreads, kHSmem, st>>>(L.p);
+  } else if (L.taps_per_group == 1) wgrad_tc_kernel<1><<<L.grid, kWgThreads, wg_smem<1>(), st>>>(L.p);
   else if (L.taps_per_group == 3) wgrad_tc_kernel<3><<<L.grid, kWgThreads, wg_smem<3>(), st>>>(L.p);
   else return cudaErrorInvalidValue;
   cudaError_t e = cudaGetLastError();
