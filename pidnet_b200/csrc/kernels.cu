@@ -61,6 +61,19 @@ __device__ __forceinline__ F8 sample8(const View& b, int n, const Lerp& lh, cons
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// thread index -> (channel group, w, h, n, pixel) with 32-bit unsigned divisions (three instead of the six 64-bit div/mod
+// of the naive form: these elementwise kernels are instruction-issue bound, and 64-bit division was a third of their
+// instructions).  Launchers reject tensors with >= 2^32 (pixel, channel-group) items.
+__device__ __forceinline__ void decode_idx(unsigned idx, unsigned groups, unsigned W, unsigned H, int& cg, int& w, int& h,
+                                           int& n, unsigned& pix) {
+  pix = idx / groups;
+  cg = static_cast<int>(idx - pix * groups);
+  const unsigned t1 = pix / W;
+  w = static_cast<int>(pix - t1 * W);
+  const unsigned nn = t1 / H;
+  h = static_cast<int>(t1 - nn * H);
+  n = static_cast<int>(nn);
+}
 
 // --------------------------------------------------------------------------- stem
 // Register-tiled direct conv: one thread = 2 horizontally adjacent output pixels x 32 output channels
@@ -138,16 +151,13 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
 // --------------------------------------------------------------------------- PagFM fuse
 template <int LP>  // lanes per pixel = C/8
 __global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View out, int relu) {
-  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long npix = static_cast<long>(x.N) * x.H * x.W;
-  long pix = gid / LP;
-  const int cg = static_cast<int>(gid % LP);
-  const bool valid = pix < npix;
-  if (!valid) pix = npix - 1;
-  const int w = static_cast<int>(pix % x.W);
-  const long t1 = pix / x.W;
-  const int h = static_cast<int>(t1 % x.H);
-  const int n = static_cast<int>(t1 / x.H);
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned npix = static_cast<unsigned>(x.N) * x.H * x.W;
+  const bool valid = gid / LP < npix;
+  int cg, w, h, n;
+  unsigned pixu;
+  decode_idx(valid ? gid : (npix - 1) * LP + gid % LP, LP, x.W, x.H, cg, w, h, n, pixu);   // LP is a compile-time power of two
+  const long pix = pixu;
   const int C = x.C;
   const Lerp lh = lerp_of(h, low.H, x.H), lw = lerp_of(w, low.W, x.W);
   const F8 xv = ld8(x.ptr + pix * x.ps + cg * 8);
@@ -179,15 +189,13 @@ __global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View ou
 __global__ void __launch_bounds__(256) upadd_kernel(View a, View b, View r, View out, const float* __restrict__ s,
                                                     const float* __restrict__ t, int relu) {
   const int groups = out.C >> 3;
-  const long total = static_cast<long>(out.N) * out.H * out.W * groups;
-  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned total = static_cast<unsigned>(out.N) * out.H * out.W * groups;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int cg = static_cast<int>(idx % groups);
-  const long pix = idx / groups;
-  const int w = static_cast<int>(pix % out.W);
-  const long t1 = pix / out.W;
-  const int h = static_cast<int>(t1 % out.H);
-  const int n = static_cast<int>(t1 / out.H);
+  int cg, w, h, n;
+  unsigned pixu;
+  decode_idx(idx, groups, out.W, out.H, cg, w, h, n, pixu);
+  const long pix = pixu;
   F8 v;
 #pragma unroll
   for (int e = 0; e < 8; ++e) v.v[e] = 0.f;
@@ -274,14 +282,12 @@ __global__ void __launch_bounds__(256) pool_affine_kernel(View x, View out, int 
 __global__ void __launch_bounds__(256) lightbag_uv_kernel(View p, View il, View d, View out) {
   const int groups = p.C >> 3;
   const long total = static_cast<long>(p.N) * p.H * p.W * groups;
-  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int cg = static_cast<int>(idx % groups);
-  const long pix = idx / groups;
-  const int w = static_cast<int>(pix % p.W);
-  const long t1 = pix / p.W;
-  const int h = static_cast<int>(t1 % p.H);
-  const int n = static_cast<int>(t1 / p.H);
+  int cg, w, h, n;
+  unsigned pixu;
+  decode_idx(idx, groups, p.W, p.H, cg, w, h, n, pixu);
+  const long pix = pixu;
   const Lerp lh = lerp_of(h, il.H, p.H), lw = lerp_of(w, il.W, p.W);
   const F8 iv = sample8(il, n, lh, lw, cg * 8);
   const F8 pv = ld8(p.ptr + pix * p.ps + cg * 8);
@@ -301,14 +307,12 @@ __global__ void __launch_bounds__(256) bag_blend_kernel(View p, View il, View d,
                                                         const float* __restrict__ t) {
   const int groups = p.C >> 3;
   const long total = static_cast<long>(p.N) * p.H * p.W * groups;
-  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int cg = static_cast<int>(idx % groups);
-  const long pix = idx / groups;
-  const int w = static_cast<int>(pix % p.W);
-  const long t1 = pix / p.W;
-  const int h = static_cast<int>(t1 % p.H);
-  const int n = static_cast<int>(t1 / p.H);
+  int cg, w, h, n;
+  unsigned pixu;
+  decode_idx(idx, groups, p.W, p.H, cg, w, h, n, pixu);
+  const long pix = pixu;
   const Lerp lh = lerp_of(h, il.H, p.H), lw = lerp_of(w, il.W, p.W);
   const F8 iv = sample8(il, n, lh, lw, cg * 8);
   const F8 pv = ld8(p.ptr + pix * p.ps + cg * 8);
@@ -382,6 +386,7 @@ cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, cons
 cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t st) {
   const int LP = x.C / 8;
   const long total = static_cast<long>(x.N) * x.H * x.W * LP;
+  if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
   const unsigned nb = blocks_for(total, 256);
   switch (LP) {
     case 1: pag_fuse_kernel<1><<<nb, 256, 0, st>>>(x, low, out, relu); break;
@@ -401,6 +406,7 @@ cudaError_t upadd_launch(View a, View b, View out, const float* s, const float* 
 
 cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, const float* t, int relu, cudaStream_t st) {
   const long total = static_cast<long>(out.N) * out.H * out.W * (out.C / 8);
+  if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
   upadd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, b, r, out, s, t, relu);
   return cudaGetLastError();
 }
@@ -418,12 +424,14 @@ cudaError_t pool_affine_launch(View x, View out, int k, int stride, int pad, con
 
 cudaError_t lightbag_uv_launch(View p, View i_low, View d, View out, cudaStream_t st) {
   const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
+  if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
   lightbag_uv_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out);
   return cudaGetLastError();
 }
 
 cudaError_t bag_blend_launch(View p, View i_low, View d, View out, const float* s, const float* t, cudaStream_t st) {
   const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
+  if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
   bag_blend_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out, s, t);
   return cudaGetLastError();
 }
