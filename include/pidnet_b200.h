@@ -216,6 +216,9 @@ int pidnet_probe_halo(void* stream, const void* x_18x10x64_bf16, const void* w_6
 
 int pidnet_probe_mn(void* stream, const void* a_64x128_bf16, const void* b_64x64_bf16, int lbo, int sbo, float* out_128x64);
 int pidnet_probe_mma_rate(void* stream, int N, int iters, int distinct, int blocks, long long* out_cycles_dev);
+/* CTA-pair (tcgen05 cta_group::2, M = 256) probes: operand-split convention and MMA rate (tools/probe_pair.py). */
+int pidnet_probe_pair(void* stream, const void* a_256x64_bf16, const void* b_64x64_bf16, int swap_b, float* out_256x64);
+int pidnet_probe_mma_rate_pair(void* stream, int N, int iters, int distinct, int pairs, long long* out_cycles_dev);
 
 #ifdef __cplusplus
 }

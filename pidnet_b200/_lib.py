@@ -65,6 +65,8 @@ SIGNATURES = {
     'pidnet_sgd_step': (_i, [_vp, _vp, _vp, _vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, _i, _i, C.c_float]),
     'pidnet_probe_mn': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     'pidnet_probe_mma_rate': (_i, [_vp, _i, _i, _i, _i, _vp]),
+    'pidnet_probe_pair': (_i, [_vp, _vp, _vp, _i, _vp]),
+    'pidnet_probe_mma_rate_pair': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'pidnet_probe_halo': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'pidnet_op_bag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }

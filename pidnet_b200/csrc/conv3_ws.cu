@@ -22,11 +22,24 @@
 // Warp roles: 0 = TMA producer, 1 and 10 = MMA issuers (lane 0 / 1; warp 1 also owns the TMEM allocation),
 // 2..5 and 6..9 = epilogue groups (lane 0 / 1), 11 = TMA store.
 //
+// PAIR = true runs the same pipeline on a CTA PAIR (2-CTA cluster = the two SMs of a TPC) with tcgen05 cta_group::2: one
+// M = 256 MMA covers the 128-pixel tiles of BOTH CTAs; each CTA keeps only HALF of the Cout tile's weights (B is split
+// across the pair), loads its own halo patches and runs its own epilogue / stores.  Only the leader (cluster rank 0) issues
+// MMAs; its patch_full / w_full / tmem_empty barriers collect arrivals from both CTAs, and tcgen05.commit multicasts the
+// patch_empty / tmem_full arrivals to both.  Measured (tools/probe_pair.py): M256 x N64 x K16 costs 43 cycles against 48 for
+// M128 x N64 on each SM alone (the B operand is fetched once per pair), and -- what matters more for the Cin = 128 layers
+// -- halving the resident weights (147 -> 74 KB) makes room for a patch ring that can actually prefetch.
+//
+// Staging buffers rotate over `nstage` (2 or 3) tiles independent of the two lanes: with 3, the residual tile of tile i+3 is
+// requested as soon as tile i's store has been read out, a full tile period earlier than with one buffer per lane (the
+// residual load latency used to sit on the critical path of every `+res` layer: 95 us against 72 us without residual).
+//
 // MODE 1 is the same persistent, weight-stationary pipeline for 1x1 stride-1 convs over the flattened
 // pixel dimension (tile = 128 consecutive pixels, one tap, up to two K-concatenated sources): these
 // layers have K of only 64..512, so they are pure streaming and live or die by the per-tile overhead.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
+#include <cstring>
 
 namespace pidnet {
 
@@ -53,15 +66,16 @@ struct WsGeom {
   static constexpr int kSboBytes = MODE == 0 ? kPW * kRowBytes : 8 * kRowBytes;
 };
 
-template <int BN, int CK, int MODE>
+template <int BN, int CK, int MODE, bool PAIR>
 __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_constant__ Conv3Params p) {
   using G = WsGeom<CK, MODE>;
+  constexpr int kWRows = PAIR ? BN / 2 : BN;   // weight rows (output channels) resident in THIS CTA
   constexpr int kSlabC = BN < 64 ? BN : 64;
   constexpr int kSlabRowBytes = kSlabC * 2;
   constexpr int kSlabBytes = 128 * kSlabRowBytes;
   constexpr int kNumSlabs = BN / kSlabC;
   constexpr int kStageBytes = 128 * BN * 2;
-  constexpr int kWTileBytes = BN * CK * 2;
+  constexpr int kWTileBytes = kWRows * CK * 2;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -69,36 +83,47 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
 
   const int chunks = p.chunks;
   const int npatch = p.npatch;
+  const int nstage = p.nstage;   // staging buffers (2: one per lane, 3: rotating)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const uint32_t w_base = smem_base;
   const uint32_t w_bytes = static_cast<uint32_t>(G::kTaps) * chunks * kWTileBytes;
   const uint32_t patch_base = w_base + w_bytes;
   const uint32_t stage_base = patch_base + npatch * G::kPatchStride;
   uint8_t* stage_gen = smem_gen + w_bytes + npatch * G::kPatchStride;
-  const uint32_t bar_base = stage_base + 2 * kStageBytes;
+  const uint32_t bar_base = stage_base + nstage * kStageBytes;
   // barriers (8 B each): w_full | patch_full[kMaxPatch] | patch_empty[kMaxPatch] | tmem_full[4] | tmem_empty[4] |
-  //                      res_full[2] | stage_free[2] | stage_ready[2] | tmem slot  -- 8 * (16 + 2 * kMaxPatch) <= 512 bytes
+  //                      res_full[3][2] | stage_free[3][2] | stage_ready[3] | tmem slot  -- 8 * (25 + 2 * kMaxPatch) <= 512 bytes
+  // res_full / stage_free are indexed by (staging buffer, lane): each is waited on by ONE epilogue group, which therefore
+  // observes every phase (a barrier shared by both groups would alias parities when the lanes drift apart).
   const uint32_t w_full = bar_base;
   auto patch_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto patch_empty = [&](int s) { return bar_base + 8u * (1 + kMaxPatch + s); };
   auto tmem_full = [&](int b) { return bar_base + 8u * (1 + 2 * kMaxPatch + b); };
   auto tmem_empty = [&](int b) { return bar_base + 8u * (5 + 2 * kMaxPatch + b); };
-  auto res_full = [&](int b) { return bar_base + 8u * (9 + 2 * kMaxPatch + b); };
-  auto stage_free = [&](int b) { return bar_base + 8u * (11 + 2 * kMaxPatch + b); };
-  auto stage_ready = [&](int b) { return bar_base + 8u * (13 + 2 * kMaxPatch + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (15 + 2 * kMaxPatch);
-  static_assert(8 * (16 + 2 * kMaxPatch) <= 512, "barrier block overlaps the bias table");
-  float* bias_s = reinterpret_cast<float*>(stage_gen + 2 * kStageBytes + 512);   // BN floats (<= 512 B) after the barriers
+  auto res_full = [&](int sb, int g) { return bar_base + 8u * (9 + 2 * kMaxPatch + 2 * sb + g); };
+  auto stage_free = [&](int sb, int g) { return bar_base + 8u * (15 + 2 * kMaxPatch + 2 * sb + g); };
+  auto stage_ready = [&](int sb) { return bar_base + 8u * (21 + 2 * kMaxPatch + sb); };
+  const uint32_t tmem_slot = bar_base + 8u * (24 + 2 * kMaxPatch);
+  static_assert(8 * (25 + 2 * kMaxPatch) <= 512, "barrier block overlaps the bias table");
+  float* bias_s = reinterpret_cast<float*>(stage_gen + nstage * kStageBytes + 512);   // BN floats (<= 512 B) after the barriers
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-      stage_gen + 2 * kStageBytes + 8 * (15 + 2 * kMaxPatch));
-
+      stage_gen + nstage * kStageBytes + 8 * (24 + 2 * kMaxPatch));
+  // staging-buffer rotation: tile iteration i uses buffer i % nstage; the (buffer, lane) pair recurs every 2 or 6 iterations
+  auto stage_of = [&](int i) { return nstage == 3 ? i % 3 : (i & 1); };
+  auto stage_use = [&](int i) { return static_cast<uint32_t>(nstage == 3 ? i / 6 : (i >> 1)); };
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tile = blockIdx.y;
   const int c_out0 = n_tile * BN;
   const int per_img = p.tiles_w * p.tiles_h;
   const int m_tiles = MODE == 0 ? p.N * per_img : p.tiles_w;   // MODE 1: tiles_w = ceil(rows / 128)
+  // iteration i of this CTA works on tile blockIdx.x + i * gridDim.x; a pair iterates while its FIRST tile exists (the
+  // second CTA of the last pair may run past the end: its loads are zero-filled and its stores clipped by TMA)
+  auto tile_of = [&](int i) { return static_cast<long>(blockIdx.x) + static_cast<long>(i) * gridDim.x; };
+  auto in_range = [&](int i) { return tile_of(i) - static_cast<long>(rank) < static_cast<long>(m_tiles); };
   // tile -> TMA coordinates (w, h, n) of its first output pixel
-  auto tile_coord = [&](int tile, int& w0, int& h0, int& n) {
+  auto tile_coord = [&](long tile_l, int& w0, int& h0, int& n) {
+    const int tile = static_cast<int>(tile_l);
     if (MODE == 0) {
       n = tile / per_img;
       const int rem = tile - n * per_img;
@@ -111,100 +136,111 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   };
 
   if (threadIdx.x == 0) {
-    mbar_init(w_full, 1);
+    mbar_init(w_full, PAIR ? 2 : 1);
     for (int s = 0; s < kMaxPatch; ++s) {
-      mbar_init(patch_full(s), 1);
+      mbar_init(patch_full(s), PAIR ? 2 : 1);
       mbar_init(patch_empty(s), 1);
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(tmem_full(b), 1);
-      mbar_init(tmem_empty(b), 4);
+      mbar_init(tmem_empty(b), PAIR ? 8 : 4);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(res_full(b), 1);
-      mbar_init(stage_free(b), 1);
-      mbar_init(stage_ready(b), 4);
+    for (int sb = 0; sb < 3; ++sb) {
+      for (int g = 0; g < 2; ++g) {
+        mbar_init(res_full(sb, g), 1);
+        mbar_init(stage_free(sb, g), 1);
+      }
+      mbar_init(stage_ready(sb), 4);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<4 * BN>(tmem_slot);   // four accumulators: two per tile-parity lane
+  if (warp == 1) {   // four accumulators: two per tile-parity lane
+    if (PAIR) tmem_alloc_pair<4 * BN>(tmem_slot);
+    else tmem_alloc<4 * BN>(tmem_slot);
+  }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) bias_s[threadIdx.x - 64] = p.bias[c_out0 + threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();   // both CTAs' barriers are initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_gen;
+  // barriers that collect arrivals from both CTAs live in the leader (cluster rank 0)
+  auto leader = [&](uint32_t bar) { return PAIR ? mapa_u32(bar, 0) : bar; };
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (elect_one()) {
       tma_prefetch_desc(&p.tmA);
       tma_prefetch_desc(&p.tmW);
-      mbar_arrive_expect_tx(w_full, w_bytes);
-      for (int t = 0; t < G::kTaps * chunks; ++t)
-        tma_load_2d(w_base + t * kWTileBytes, &p.tmW, w_full, t * CK, c_out0);
+      if (PAIR) {
+        const uint32_t wf = leader(w_full);
+        mbar_arrive_expect_tx_cluster(wf, w_bytes);
+        for (int t = 0; t < G::kTaps * chunks; ++t)
+          tma_load_2d_pair(w_base + t * kWTileBytes, &p.tmW, wf, t * CK, c_out0 + static_cast<int>(rank) * kWRows);
+      } else {
+        mbar_arrive_expect_tx(w_full, w_bytes);
+        for (int t = 0; t < G::kTaps * chunks; ++t)
+          tma_load_2d(w_base + t * kWTileBytes, &p.tmW, w_full, t * CK, c_out0);
+      }
       // The patch ring is partitioned per lane (even slots: even tiles, odd slots: odd tiles) so that every
       // waiter observes EVERY phase of the barriers it uses (a shared ring would alias mbarrier parities).
       const int np_lane = npatch >> 1;
-      int i = 0;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
+      for (int i = 0; in_range(i); ++i) {
         int w0, h0, n;
-        tile_coord(tile, w0, h0, n);
+        tile_coord(tile_of(i), w0, h0, n);
         const int ln = i & 1;
         int j = (i >> 1) * chunks;   // lane-local item index
         for (int c = 0; c < chunks; ++c, ++j) {
           const int slot = ln + 2 * (j % np_lane);
           const uint32_t ph = (j / np_lane) & 1;
           mbar_wait(patch_empty(slot), ph ^ 1);
-          mbar_arrive_expect_tx(patch_full(slot), G::kPatchBytes);
-          if (MODE == 0) {
-            tma_load_4d(patch_base + slot * G::kPatchStride, &p.tmA, patch_full(slot), c * CK, w0 - 1, h0 - 1, n);
-          } else {
+          const uint32_t dst = patch_base + slot * G::kPatchStride;
+          const CUtensorMap* map = &p.tmA;
+          int c0 = c * CK, c1 = w0 - 1, c2 = h0 - 1, c3 = n;
+          if (MODE == 1) {
             const bool first = c < p.chunks0;
-            tma_load_4d(patch_base + slot * G::kPatchStride, first ? &p.tmA : &p.tmA2, patch_full(slot),
-                        (first ? c : c - p.chunks0) * CK, w0, 0, 0);
+            map = first ? &p.tmA : &p.tmA2;
+            c0 = (first ? c : c - p.chunks0) * CK; c1 = w0; c2 = 0; c3 = 0;
           }
-        }
-        if (p.has_res && p.out_mode != kOutNHWCbf16) {   // (bf16 outputs: the store warp prefetches residuals, see below)
-          const int b = i & 1;
-          const uint32_t u = static_cast<uint32_t>(i >> 1);
-          mbar_wait(stage_free(b), (u & 1) ^ 1);
-          mbar_arrive_expect_tx(res_full(b), kStageBytes);
-          for (int sl = 0; sl < kNumSlabs; ++sl)
-            tma_load_4d(stage_base + b * kStageBytes + sl * kSlabBytes, &p.tmR, res_full(b), c_out0 + sl * kSlabC, w0,
-                        h0, n);
+          if (PAIR) {
+            const uint32_t pf = leader(patch_full(slot));
+            mbar_arrive_expect_tx_cluster(pf, G::kPatchBytes);
+            tma_load_4d_pair(dst, map, pf, c0, c1, c2, c3);
+          } else {
+            mbar_arrive_expect_tx(patch_full(slot), G::kPatchBytes);
+            tma_load_4d(dst, map, patch_full(slot), c0, c1, c2, c3);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1 || warp == 10) {
-    // ============================== MMA issuers (one per tile parity) ==============================
+    // ============================== MMA issuers (one per tile parity; leader CTA only in PAIR mode) ==============================
     // The whole warp runs the loop converged (waits included); one ELECTED lane issues tcgen05.mma / commit
     // (elect.sync lets ptxas keep descriptors in uniform registers without per-MMA uniformisation loops).
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+    if (!PAIR || rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN);
       constexpr uint64_t kLayout = (CK == 64) ? 2ull : 4ull;  // SWIZZLE_128B / SWIZZLE_64B
       // descriptor high words are constant: SBO (A: tile rows are kPW patch pixels apart), version, layout
       constexpr uint64_t a_hi = (static_cast<uint64_t>(G::kSboBytes >> 4) << 32) | (1ull << 46) | (kLayout << 61) |
                                 (1ull << 16);
       constexpr uint64_t b_hi = (static_cast<uint64_t>((8 * G::kRowBytes) >> 4) << 32) | (1ull << 46) |
                                 (kLayout << 61) | (1ull << 16);
-      mbar_wait(w_full, 0);
+      if (PAIR) mbar_wait_cluster(w_full, 0); else mbar_wait(w_full, 0);
       tc_fence_after();
       const int ab = warp == 1 ? 0 : 1;   // this warp's tile parity (lane); each lane alternates two accumulators
-      for (int i = ab;; i += 2) {
-        const long tile = static_cast<long>(blockIdx.x) + static_cast<long>(i) * gridDim.x;
-        if (tile >= m_tiles) break;
+      for (int i = ab; in_range(i); i += 2) {
         const uint32_t u = static_cast<uint32_t>(i >> 1);      // lane-local tile counter
         const int ai = ab + 2 * static_cast<int>(u & 1);       // accumulator index 0..3
         const uint32_t acc = tmem_acc + ai * BN;
-        mbar_wait(tmem_empty(ai), ((u >> 1) & 1) ^ 1);
+        if (PAIR) mbar_wait_cluster(tmem_empty(ai), ((u >> 1) & 1) ^ 1); else mbar_wait(tmem_empty(ai), ((u >> 1) & 1) ^ 1);
         tc_fence_after();
         const int np_lane = npatch >> 1;
         int j = (i >> 1) * chunks;   // lane-local item index (see the producer)
         for (int c = 0; c < chunks; ++c, ++j) {
           const int slot = ab + 2 * (j % np_lane);
           const uint32_t ph = (j / np_lane) & 1;
-          mbar_wait(patch_full(slot), ph);
+          if (PAIR) mbar_wait_cluster(patch_full(slot), ph); else mbar_wait(patch_full(slot), ph);
           tc_fence_after();
           const uint32_t pbase = patch_base + slot * G::kPatchStride;
           const uint32_t wbase = w_base + c * kWTileBytes;
@@ -217,11 +253,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
               const uint64_t b_desc =
                   b_hi | static_cast<uint64_t>(((wbase + tap * chunks * kWTileBytes) & 0x3FFFF) >> 4);
 #pragma unroll
-              for (int k = 0; k < CK / 16; ++k)
-                umma_bf16(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < CK / 16; ++k) {
+                if (PAIR) umma_bf16_pair(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+                else umma_bf16(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+              }
             }
-            umma_commit(patch_empty(slot));
-            if (c == chunks - 1) umma_commit(tmem_full(ai));
+            if (PAIR) {
+              umma_commit_pair(patch_empty(slot), 3);
+              if (c == chunks - 1) umma_commit_pair(tmem_full(ai), 3);
+            } else {
+              umma_commit(patch_empty(slot));
+              if (c == chunks - 1) umma_commit(tmem_full(ai));
+            }
           }
           __syncwarp();
         }
@@ -231,38 +274,36 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   } else if (warp == 11) {
     // ============================== TMA store warp ==============================
     if (p.out_mode == kOutNHWCbf16 && elect_one()) {
-      // This thread also prefetches the residual tiles: the staging buffer of lane b is free exactly when this thread has
-      // seen its store read the buffer out, so the residual of the lane's NEXT tile is requested right there (the TMA
+      // This thread also prefetches the residual tiles: staging buffer sb is free exactly when this thread has seen tile i's
+      // store read it out, so the residual of the buffer's NEXT tile (i + nstage) is requested right there (the TMA
       // producer never blocks on a staging buffer, which used to serialise its patch loads behind the epilogue).
-      auto load_residual = [&](int tile, int b) {
+      auto load_residual = [&](int i) {
         int w0, h0, n;
-        tile_coord(tile, w0, h0, n);
-        mbar_arrive_expect_tx(res_full(b), kStageBytes);
+        tile_coord(tile_of(i), w0, h0, n);
+        const int sb = stage_of(i);
+        const uint32_t bar = res_full(sb, i & 1);
+        mbar_arrive_expect_tx(bar, kStageBytes);
         for (int sl = 0; sl < kNumSlabs; ++sl)
-          tma_load_4d(stage_base + b * kStageBytes + sl * kSlabBytes, &p.tmR, res_full(b), c_out0 + sl * kSlabC, w0, h0, n);
+          tma_load_4d(stage_base + sb * kStageBytes + sl * kSlabBytes, &p.tmR, bar, c_out0 + sl * kSlabC, w0, h0, n);
       };
       if (p.has_res) {
         tma_prefetch_desc(&p.tmR);
-        for (int b = 0; b < 2; ++b) {
-          const long t0 = static_cast<long>(blockIdx.x) + static_cast<long>(b) * gridDim.x;
-          if (t0 < m_tiles) load_residual(static_cast<int>(t0), b);
-        }
+        for (int i = 0; i < nstage; ++i)
+          if (in_range(i)) load_residual(i);
       }
-      int i = 0;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++i) {
+      for (int i = 0; in_range(i); ++i) {
         int w0, h0, n;
-        tile_coord(tile, w0, h0, n);
-        const int b = i & 1;
-        const uint32_t u = static_cast<uint32_t>(i >> 1);
-        mbar_wait(stage_ready(b), u & 1);
+        tile_coord(tile_of(i), w0, h0, n);
+        const int sb = stage_of(i);
+        mbar_wait(stage_ready(sb), static_cast<uint32_t>(i / nstage) & 1);
         for (int sl = 0; sl < kNumSlabs; ++sl)
           if (c_out0 + sl * kSlabC < p.Cout)
-            tma_store_4d(&p.tmD, stage_base + b * kStageBytes + sl * kSlabBytes, c_out0 + sl * kSlabC, w0, h0, n);
+            tma_store_4d(&p.tmD, stage_base + sb * kStageBytes + sl * kSlabBytes, c_out0 + sl * kSlabC, w0, h0, n);
         tma_store_commit();
         tma_store_wait_read();       // smem of this buffer has been read out
-        const long next = static_cast<long>(tile) + 2L * gridDim.x;
-        if (p.has_res) { if (next < m_tiles) load_residual(static_cast<int>(next), b); }
-        else mbar_arrive(stage_free(b));
+        const int nxt = i + nstage;  // next user of the buffer (lane nxt & 1)
+        if (p.has_res) { if (in_range(nxt)) load_residual(nxt); }
+        else mbar_arrive(stage_free(sb, nxt & 1));
       }
       tma_store_wait_all();
     }
@@ -272,22 +313,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;        // tile row == TMEM lane
     const uint32_t swz = (kSlabRowBytes == 128) ? (row & 7) : (kSlabRowBytes == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
-    const int b = warp >= 6 ? 1 : 0;   // lane == tile parity == accumulator == staging buffer
-    for (int i = b;; i += 2) {
-      const long tile_l = static_cast<long>(blockIdx.x) + static_cast<long>(i) * gridDim.x;
-      if (tile_l >= m_tiles) break;
-      const int tile = static_cast<int>(tile_l);
+    const int b = warp >= 6 ? 1 : 0;   // lane == tile parity
+    for (int i = b; in_range(i); i += 2) {
       int w0, h0, n;
-      tile_coord(tile, w0, h0, n);
-      const uint32_t u = static_cast<uint32_t>(i >> 1);      // lane-local tile counter == staging-buffer use count
+      tile_coord(tile_of(i), w0, h0, n);
+      const uint32_t u = static_cast<uint32_t>(i >> 1);      // lane-local tile counter
       const int ai = b + 2 * static_cast<int>(u & 1);        // accumulator index 0..3
       mbar_wait(tmem_full(ai), (u >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_acc + ai * BN + (static_cast<uint32_t>(q * 32) << 16);
       if (p.out_mode == kOutNHWCbf16) {
-        if (p.has_res) mbar_wait(res_full(b), u & 1);
-        else mbar_wait(stage_free(b), (u & 1) ^ 1);
-        uint8_t* stage = stage_gen + b * kStageBytes;
+        const int sb = stage_of(i);
+        if (p.has_res) mbar_wait(res_full(sb, b), stage_use(i) & 1);
+        else if (i >= nstage) mbar_wait(stage_free(sb, b), stage_use(i - nstage) & 1);
+        uint8_t* stage = stage_gen + sb * kStageBytes;
 #pragma unroll
         for (int g2 = 0; g2 < BN / 32; g2 += 2) {
           // two 32-column TMEM loads in flight, one wait
@@ -334,8 +373,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(tmem_empty(ai));
-          mbar_arrive(stage_ready(b));
+          if (PAIR) mbar_arrive_cluster(leader(tmem_empty(ai))); else mbar_arrive(tmem_empty(ai));
+          mbar_arrive(stage_ready(sb));
         }
       } else {
         int w, h;
@@ -343,7 +382,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
         const size_t plane = static_cast<size_t>(p.Ho) * p.Wo;
         if (MODE == 0) {
           w = w0 + row % kTW; h = h0 + row / kTW;
-          ok = (w < p.Wo) && (h < p.Ho);
+          ok = (w < p.Wo) && (h < p.Ho) && (n < p.N);
         } else {
           const long pix = static_cast<long>(w0) + row;          // flat pixel index over (n, h, w)
           ok = pix < static_cast<long>(p.N) * static_cast<long>(plane);
@@ -371,33 +410,53 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty(ai));
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(leader(tmem_empty(ai))); else mbar_arrive(tmem_empty(ai)); }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<4 * BN>(tmem_acc);
+  if (PAIR) cluster_sync();   // no CTA leaves (or frees TMEM) while its peer may still signal it or read its smem
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair<4 * BN>(tmem_acc);
+    else tmem_dealloc<4 * BN>(tmem_acc);
+  }
 }
 
 template <int BN, int CK>
 cudaError_t ws_launch_inst(const Conv3Launch& L, cudaStream_t stream) {
-  if (L.mode == 0) conv3_ws_kernel<BN, CK, 0><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
-  else conv3_ws_kernel<BN, CK, 1><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
+  if (L.mode == 0) conv3_ws_kernel<BN, CK, 0, false><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
+  else conv3_ws_kernel<BN, CK, 1, false><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
   return cudaGetLastError();
+}
+// CTA-pair instance: launched as 2-CTA clusters along x
+template <int BN, int CK>
+cudaError_t ws_launch_pair(const Conv3Launch& L, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = L.grid; cfg.blockDim = dim3(kWsThreads, 1, 1); cfg.dynamicSmemBytes = L.smem_bytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv3_ws_kernel<BN, CK, 0, true>, L.p);
 }
 template <int BN, int CK>
 cudaError_t ws_init_inst() {
-  cudaError_t e = cudaFuncSetAttribute(conv3_ws_kernel<BN, CK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(conv3_ws_kernel<BN, CK, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kConv3MaxSmem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv3_ws_kernel<BN, CK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3MaxSmem);
+  return cudaFuncSetAttribute(conv3_ws_kernel<BN, CK, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3MaxSmem);
 }
 
 }  // namespace
 
 cudaError_t conv3_ws_launch(const Conv3Launch& L, cudaStream_t stream) {
   const int BN = L.BN, CK = L.CK;
+  if (L.pair) {
+    if (L.mode == 0 && BN == 64 && CK == 64 && L.grid.x % 2 == 0) return ws_launch_pair<64, 64>(L, stream);
+    return cudaErrorInvalidValue;
+  }
   if (BN == 32 && CK == 32) return ws_launch_inst<32, 32>(L, stream);
   if (BN == 32 && CK == 64) return ws_launch_inst<32, 64>(L, stream);
   if (BN == 64 && CK == 32) return ws_launch_inst<64, 32>(L, stream);
@@ -415,21 +474,34 @@ cudaError_t conv3_ws_init() {
   if ((e = ws_init_inst<64, 64>()) != cudaSuccess) return e;
   if ((e = ws_init_inst<128, 32>()) != cudaSuccess) return e;
   if ((e = ws_init_inst<128, 64>()) != cudaSuccess) return e;
-  return cudaSuccess;
+  return cudaFuncSetAttribute(conv3_ws_kernel<64, 64, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3MaxSmem);
 }
 
-// Shared-memory plan for (BN, CK, chunks): returns the number of patch buffers (0: does not fit) and the bytes.
-int conv3_ws_plan(int mode, int BN, int CK, int chunks, size_t* smem_bytes) {
-  const size_t w = static_cast<size_t>(mode == 0 ? 9 : 1) * chunks * BN * CK * 2;
-  const size_t stage = static_cast<size_t>(2) * 128 * BN * 2;
+// The CTA-pair instance exists for (mode 0, BN 64, CK 64): the 3x3 C >= 64 layers, which are the MMA-bound ones.
+bool conv3_ws_pair_available(int mode, int BN, int CK) { return mode == 0 && BN == 64 && CK == 64; }
+
+// Shared-memory plan for (BN, CK, chunks): returns the number of patch buffers (0: does not fit), the staging-buffer
+// count (3 when that costs no ring depth worth having, else 2) and the bytes.  pair: each CTA holds half of the weights.
+int conv3_ws_plan(int mode, int BN, int CK, int chunks, int pair, int want_stages, int* nstage, size_t* smem_bytes) {
+  const size_t w = static_cast<size_t>(mode == 0 ? 9 : 1) * chunks * (pair ? BN / 2 : BN) * CK * 2;
   const size_t patch = (static_cast<size_t>(mode == 0 ? kPH * kPW : 128) * CK * 2 + 1023) / 1024 * 1024;
-  const size_t fixed = w + stage + 1024 /*barriers + bias*/ + 1024 /*alignment slack*/;  // see kernel smem carve-up
-  if (fixed + 2 * patch > static_cast<size_t>(kConv3MaxSmem)) return 0;
-  size_t np = (kConv3MaxSmem - fixed) / patch;
-  if (np > static_cast<size_t>(kMaxPatch)) np = kMaxPatch;
-  np &= ~static_cast<size_t>(1);   // even: the ring is split between the two tile-parity lanes
-  if (smem_bytes) *smem_bytes = fixed + np * patch;
-  return static_cast<int>(np);
+  auto ring = [&](int stages, size_t* bytes) -> int {
+    const size_t fixed = w + static_cast<size_t>(stages) * 128 * BN * 2 + 1024 /*barriers + bias*/ + 1024 /*alignment slack*/;
+    if (fixed + 2 * patch > static_cast<size_t>(kConv3MaxSmem)) return 0;
+    size_t np = (kConv3MaxSmem - fixed) / patch;
+    if (np > static_cast<size_t>(kMaxPatch)) np = kMaxPatch;
+    np &= ~static_cast<size_t>(1);   // even: the ring is split between the two tile-parity lanes
+    *bytes = fixed + np * patch;
+    return static_cast<int>(np);
+  };
+  size_t b2 = 0, b3 = 0;
+  const int np2 = ring(2, &b2);
+  const int np3 = want_stages >= 3 ? ring(3, &b3) : 0;
+  const int need = 2 * (chunks < 2 ? 2 : chunks);   // per lane: a tile's chunks, at least two patches
+  const bool use3 = np3 > 0 && (np3 >= np2 || np3 >= need);
+  if (nstage) *nstage = use3 ? 3 : 2;
+  if (smem_bytes) *smem_bytes = use3 ? b3 : b2;
+  return use3 ? np3 : np2;
 }
 
 }  // namespace pidnet

@@ -56,12 +56,13 @@ constexpr int kConv3MaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 struct Conv3Params {
   CUtensorMap tmA;   // input  [N,H,W,C]  box {CK, 10, 18, 1}   (mode 1: flat [rows, C], box {CK, 128, 1, 1})
   CUtensorMap tmA2;  // mode 1: second K-concatenated source
-  CUtensorMap tmW;   // packed weights [Cout_pad][9*chunks*CK], box {CK, BN}
+  CUtensorMap tmW;   // packed weights [Cout_pad][9*chunks*CK], box {CK, BN} (CTA pairs: box {CK, BN/2})
   CUtensorMap tmR;   // residual, box {min(BN,64), 8, 16, 1}
   CUtensorMap tmD;   // output,   box {min(BN,64), 8, 16, 1}
   int chunks;        // ceil(Cin / CK), summed over the sources
   int chunks0;       // mode 1: chunks of the first source
   int npatch;        // halo patch ring depth
+  int nstage;        // output / residual staging buffers (2 or 3)
   int tiles_w, tiles_h, N;
   int Cout, Ho, Wo;
   int relu, has_res, out_mode;
@@ -75,11 +76,13 @@ struct Conv3Launch {
   int mode;           // 0: 3x3 stride-1 halo-patch   1: 1x1 stride-1 over flattened pixels
   dim3 grid;          // (persistent CTAs per Cout tile, Cout tiles)
   size_t smem_bytes;
+  int pair;           // 1: CTA pairs (2-CTA clusters along x, tcgen05 cta_group::2); grid.x is even
 };
 
 cudaError_t conv3_ws_launch(const Conv3Launch& L, cudaStream_t stream);
 cudaError_t conv3_ws_init();
-int conv3_ws_plan(int mode, int BN, int CK, int chunks, size_t* smem_bytes);
+int conv3_ws_plan(int mode, int BN, int CK, int chunks, int pair, int want_stages, int* nstage, size_t* smem_bytes);
+bool conv3_ws_pair_available(int mode, int BN, int CK);
 
 // Launches the kernel instance for (BN, BK); returns cudaError_t.
 cudaError_t conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -36,6 +37,13 @@ struct MnProbeParams {
   float* out;
 };
 cudaError_t mn_probe_launch(const MnProbeParams& p, cudaStream_t st);
+struct PairProbeParams {
+  CUtensorMap tmA, tmB;
+  int swap_b;
+  float* out;
+};
+cudaError_t pair_probe_launch(const PairProbeParams& p, cudaStream_t st);
+cudaError_t mma_rate_pair_launch(int N, int iters, int distinct, int pairs, long long* out, cudaStream_t st);
 }  // namespace pidnet
 
 namespace pidnet {
@@ -173,10 +181,17 @@ struct ConvSrcSpec {
 };
 
 // ----------------------------------------------------------------------------------------- builder
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v && *v ? std::atoi(v) : dflt;
+}
+
 struct Builder {
   bool dry = true;
   int conv_impl = 0;
   int use_ws = 1;   // weight-stationary halo-patch kernel for 3x3 stride-1 convs
+  int use_pair = env_int("PIDNET_WS_PAIR", 1);      // CTA pairs (tcgen05 cta_group::2) where conv3_ws has the instance
+  int ws_stages = env_int("PIDNET_WS_STAGES", 3);   // rotating staging buffers of the weight-stationary kernels (2 or 3)
   int num_sms = 148;
   size_t act_cur = 0, wt_cur = 0;
   uint8_t* act_base = nullptr;
@@ -274,7 +289,7 @@ struct Builder {
       if (bn > 32 && bn / 2 >= Cout) continue;
       if (bn == 32 && Cout > 32) continue;
       size_t smem = 0;
-      if (conv3_ws_plan(0, bn, BK, chunks, &smem) >= 2) return true;
+      if (conv3_ws_plan(0, bn, BK, chunks, 0, ws_stages, nullptr, &smem) >= 2) return true;
     }
     return false;
   }
@@ -321,9 +336,9 @@ struct Builder {
     // persistent weight-stationary kernels (conv3_ws.cu): mode 0 = single-source 3x3 stride-1 (halo patch),
     // mode 1 = 1x1 stride-1 (<= 2 sources) over flattened pixels; used when the Cout tile's weights fit in smem
     bool ws = false;
-    int ws_mode = 0, ws_np = 0, ws_chunks = 0;
+    int ws_mode = 0, ws_np = 0, ws_chunks = 0, ws_nstage = 2, ws_pair = 0;
     size_t ws_smem = 0;
-    if (conv_impl == 0 && use_ws) {
+    if (conv_impl == 0 && use_ws && !(res && out_slot >= 0)) {
       bool all1x1 = true;
       for (const auto& sp : srcs) {
         ws_chunks += cdiv(sp.in.C, BK);
@@ -337,13 +352,31 @@ struct Builder {
         for (int bn = 128; bn >= 32 && !ws; bn >>= 1) {
           if (bn > 32 && bn / 2 >= Cout) continue;      // tile wider than needed
           if (m0 && bn == 32 && Cout > 32) continue;    // N=32 MMAs re-reading the patch per Cout tile lose to the generic kernel
-          const int np = conv3_ws_plan(ws_mode, bn, BK, ws_chunks, &ws_smem);
+          const int np = conv3_ws_plan(ws_mode, bn, BK, ws_chunks, 0, ws_stages, &ws_nstage, &ws_smem);
           if (np >= (m0 ? 2 : 4)) {
             ws = true;
             ws_np = np;
             BN = bn;
           }
         }
+      }
+    }
+    // CTA pairs (conv3_ws PAIR instance): half of the weights per CTA and M = 256 MMAs.  Used where the layer is MMA-bound
+    // and the single-CTA ring cannot prefetch, i.e. Cin >= 128 (two or more chunks): measured 0.098 -> 0.069 ms (C = 128
+    // @64x128) and 0.348 -> 0.238 ms (final_layer.conv1, 1.30 PFLOP/s).  The Cin = 64 layers stream more than they compute
+    // and lose ~10-20 % to the pair's lock step (either CTA's memory stall holds both), so they stay single-CTA
+    // (use_pair = 2 forces pairs wherever the instance exists; it also admits layers whose weights only fit when halved).
+    if (conv_impl == 0 && use_ws && use_pair && ws_mode == 0 && !(res && out_slot >= 0) && srcs.size() == 1 &&
+        srcs[0].k == 3 && srcs[0].stride == 1 && Cout > 32 && conv3_ws_pair_available(0, 64, BK) &&
+        (ws ? BN == 64 : use_pair >= 2) && (ws_chunks >= 2 || use_pair >= 2)) {
+      const bool strided_io = xt || (out_view && !out_view->dense()) || (res && !res->dense());
+      const long mt = static_cast<long>(N) * cdiv(Wo, 8) * cdiv(Ho, 16);
+      int nst = 2;
+      size_t sm = 0;
+      const int np = strided_io ? 0 : conv3_ws_plan(0, 64, BK, ws_chunks, 1, ws_stages, &nst, &sm);
+      if (np >= 2 && mt >= 2 && num_sms / cdiv(Cout, 64) >= 2) {
+        ws = true; BN = 64;
+        ws_pair = 1; ws_np = np; ws_nstage = nst; ws_smem = sm;
       }
     }
     const int n_tiles = cdiv(Cout, BN);
@@ -524,7 +557,8 @@ struct Builder {
     std::memset(&L3, 0, sizeof(L3));
     if (ws) {
       Conv3Params& q = L3.p;
-      L3.BN = BN; L3.CK = BK; L3.mode = ws_mode; L3.smem_bytes = ws_smem;
+      L3.BN = BN; L3.CK = BK; L3.mode = ws_mode; L3.smem_bytes = ws_smem; L3.pair = ws_pair;
+      q.nstage = ws_nstage;
       q.chunks = ws_chunks;
       q.chunks0 = cdiv(in0.C, BK);
       q.npatch = ws_np;
@@ -542,6 +576,7 @@ struct Builder {
       }
       long gx = std::max<long>(1, num_sms / n_tiles);
       if (gx > mt) gx = mt;
+      if (ws_pair) gx = std::max<long>(2, gx & ~1L);   // whole pairs (the last pair's second CTA may get a tile past the end)
       L3.grid = dim3(static_cast<unsigned>(gx), n_tiles, 1);
       if (!dry) {
         auto nhwc_map = [&](const T& t, int boxc, int bw, int bh) {
@@ -561,6 +596,12 @@ struct Builder {
         };
         const int SC = BN < 64 ? BN : 64;
         q.tmW = p.tmB;
+        if (ws_pair) {   // each CTA of a pair loads its half of the Cout tile's rows
+          uint64_t wd[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(Cout_pad)};
+          uint64_t wst[1] = {static_cast<uint64_t>(Ktot) * 2};
+          uint32_t wbox[2] = {static_cast<uint32_t>(BK), static_cast<uint32_t>(BN / 2)};
+          q.tmW = encode_map(wdev, 2, wd, wst, wbox, BK * 2);
+        }
         if (ws_mode == 0) {
           q.tmA = nhwc_map(in0, BK, 10, 18);
           if (out_slot < 0) q.tmD = nhwc_map(out, SC, 8, 16);
@@ -607,7 +648,7 @@ struct Builder {
     {
       Op& op = ops[idx];
       char lab[64];
-      if (impl == 0 && ws) std::snprintf(lab, sizeof(lab), "%s<BN=%d,CK=%d>", ws_mode == 0 ? "conv3_ws" : "conv1_ws", BN, BK);
+      if (impl == 0 && ws) std::snprintf(lab, sizeof(lab), "%s<BN=%d,CK=%d>", ws_mode == 0 ? (ws_pair ? "conv3_ws_pair" : "conv3_ws") : "conv1_ws", BN, BK);
       else if (impl == 0) std::snprintf(lab, sizeof(lab), "conv_tc<BN=%d,BK=%d>", BN, BK);
       else std::snprintf(lab, sizeof(lab), "conv_ref");
       op.kernel = lab;
@@ -639,6 +680,7 @@ struct Engine {
   int lanes = 3;
   int conv_impl = 0;
   int use_ws = 1;
+  int use_pair = -1, ws_stages = -1;   // -1: builder default (environment / built-in)
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;  // capture origin (the caller's stream may be the legacy default stream)
   // uint8 input path: per-channel table of the reference's input_transform (datasets/base_dataset.py:36-44), evaluated
@@ -1172,6 +1214,8 @@ struct Engine {
       CK(conv3_ws_init());
     }
     b.use_ws = use_ws;
+    if (use_pair >= 0) b.use_pair = use_pair;
+    if (ws_stages >= 0) b.ws_stages = ws_stages;
     b.reset(true);
     build();  // dry pass: sizes only
     const size_t act_bytes = b.act_cur, wt_bytes = b.wt_cur;
@@ -1352,6 +1396,8 @@ int pidnet_set_option(pidnet_engine* h, const char* name, int value) {
     if (k == "conv_impl") h->e.conv_impl = value;
     else if (k == "lanes") h->e.lanes = value == 3 ? 3 : 1;
     else if (k == "use_ws") h->e.use_ws = value ? 1 : 0;
+    else if (k == "use_pair") h->e.use_pair = value ? 1 : 0;
+    else if (k == "ws_stages") h->e.ws_stages = value == 2 ? 2 : 3;
     else fail("unknown option '" + k + "'");
     h->e.planned = false;
   });
@@ -1455,6 +1501,8 @@ int pidnet_op_conv2d(void* stream, const void* x, int N, int H, int W, int Cin, 
     b.num_sms = prop.multiProcessorCount;
     b.conv_impl = impl == 1 ? 1 : 0;
     b.use_ws = impl == 2 ? 0 : 1;
+    if (impl == 3) { b.use_pair = 0; b.ws_stages = 2; }   // weight-stationary kernels without CTA pairs / rotating stages
+    if (impl == 4) b.use_pair = 0;
     T xin = ext_tensor(x, N, H, W, Cin);
     T rt, ot;
     if (res) rt = ext_tensor(res, N, Ho, Wo, Cout);
@@ -1781,6 +1829,28 @@ int pidnet_probe_mn(void* stream, const void* a, const void* b, int lbo, int sbo
 int pidnet_probe_mma_rate(void* stream, int N, int iters, int distinct, int blocks, long long* out) {
   return guard([&] {
     CK(mma_rate_launch(N, iters, distinct, blocks, out, reinterpret_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
+
+// hardware probes for CTA pairs (cta_group::2): a [256][64] bf16, b [64][64] bf16 (device), out [256][64] fp32; rate as above
+int pidnet_probe_pair(void* stream, const void* a, const void* b, int swap_b, float* out) {
+  return guard([&] {
+    PairProbeParams p;
+    std::memset(&p, 0, sizeof(p));
+    uint64_t da[2] = {64, 256}, sa[1] = {128};
+    uint64_t db[2] = {64, 64}, sb[1] = {128};
+    uint32_t boxa[2] = {64, 128}, boxb[2] = {64, 32};
+    p.tmA = encode_map(a, 2, da, sa, boxa, 128);
+    p.tmB = encode_map(b, 2, db, sb, boxb, 128);
+    p.swap_b = swap_b; p.out = out;
+    CK(pair_probe_launch(p, reinterpret_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  });
+}
+int pidnet_probe_mma_rate_pair(void* stream, int N, int iters, int distinct, int pairs, long long* out) {
+  return guard([&] {
+    CK(mma_rate_pair_launch(N, iters, distinct, pairs, out, reinterpret_cast<cudaStream_t>(stream)));
     CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
   });
 }

@@ -1,5 +1,6 @@
 // HBM-bound fused kernels: 128-bit vectorised NHWC bf16 access, fp32 math.
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace pidnet {
 
@@ -73,6 +74,52 @@ __device__ __forceinline__ void decode_idx(unsigned idx, unsigned groups, unsign
   const unsigned nn = t1 / H;
   h = static_cast<int>(t1 - nn * H);
   n = static_cast<int>(nn);
+}
+
+// --------------------------------------------------------------------------- vertical strip walk
+// The upsampling kernels below give one thread a STRIP of kStrip vertically adjacent hi-res pixels of one (n, w, 8-channel
+// group).  The horizontal interpolation weights are fixed for the strip and consecutive rows share their two low-res source
+// rows (or advance by one), so the thread keeps the two horizontally-interpolated low-res rows in registers and gathers a
+// new one only when the source row changes: 2/scale row gathers per pixel instead of 4 corner gathers (x2: 10 instead of 32
+// 16-byte gathers per 8 pixels; x8: 4 instead of 32), and the index arithmetic is paid once per strip.  Consecutive threads
+// still map to consecutive (w, channel group), so every hi-res access stays a fully coalesced 128-bit access.
+constexpr int kStrip = 8;
+
+struct StripIdx {
+  int cg, w, n, h0;
+  bool valid;
+};
+// item index -> (channel group, w, strip, n); invalid tail threads are redirected to the last item (they still take part
+// in warp shuffles) and must not store
+__device__ __forceinline__ StripIdx strip_decode(unsigned gid, unsigned groups, unsigned W, unsigned H, unsigned N) {
+  const unsigned strips = (H + kStrip - 1) / kStrip;
+  const unsigned total = N * strips * W * groups;
+  StripIdx r;
+  r.valid = gid < total;
+  if (!r.valid) gid = total - groups + gid % groups;
+  const unsigned t0 = gid / groups;
+  r.cg = static_cast<int>(gid - t0 * groups);
+  const unsigned t1 = t0 / W;
+  r.w = static_cast<int>(t0 - t1 * W);
+  const unsigned nn = t1 / strips;
+  r.h0 = static_cast<int>(t1 - nn * strips) * kStrip;
+  r.n = static_cast<int>(nn);
+  return r;
+}
+// horizontally interpolated 8 channels of low-res row `row` (o0 / o1: element offsets of the two source columns)
+__device__ __forceinline__ F8 hsample8(const bf16* img, int row, int Wl, long ps, long o0, long o1, float l) {
+  const bf16* r = img + static_cast<long>(row) * Wl * ps;
+  const F8 a = ld8(r + o0), b = ld8(r + o1);
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = (1.f - l) * a.v[e] + l * b.v[e];
+  return o;
+}
+__device__ __forceinline__ F8 vlerp8(const F8& a, const F8& b, float l) {
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = (1.f - l) * a.v[e] + l * b.v[e];
+  return o;
 }
 
 // --------------------------------------------------------------------------- stem
@@ -151,38 +198,62 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
 // --------------------------------------------------------------------------- PagFM fuse
 template <int LP>  // lanes per pixel = C/8
 __global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View out, int relu) {
-  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned npix = static_cast<unsigned>(x.N) * x.H * x.W;
-  const bool valid = gid / LP < npix;
-  int cg, w, h, n;
-  unsigned pixu;
-  decode_idx(valid ? gid : (npix - 1) * LP + gid % LP, LP, x.W, x.H, cg, w, h, n, pixu);   // LP is a compile-time power of two
-  const long pix = pixu;
-  const int C = x.C;
-  const Lerp lh = lerp_of(h, low.H, x.H), lw = lerp_of(w, low.W, x.W);
-  const F8 xv = ld8(x.ptr + pix * x.ps + cg * 8);
-  const F8 yv = sample8(low, n, lh, lw, cg * 8);
-  const F8 zv = sample8(low, n, lh, lw, C + cg * 8);
-  float dot = 0.f;
+  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, LP, x.W, x.H, x.N);
+  const int C = x.C, cg = ix.cg;
+  const Lerp lw = lerp_of(ix.w, low.W, x.W);
+  const bf16* limg = low.ptr + static_cast<long>(ix.n) * low.H * low.W * low.ps;
+  const long o0 = static_cast<long>(lw.i0) * low.ps, o1 = static_cast<long>(lw.i1) * low.ps;
+  // one low-res row, horizontally interpolated: y (channels cg*8..), z (C + cg*8..) and the scalar t (channel 2C)
+  auto hrow = [&](int row, F8& y, F8& z, float& t) {
+    y = hsample8(limg, row, low.W, low.ps, o0 + cg * 8, o1 + cg * 8, lw.l);
+    z = hsample8(limg, row, low.W, low.ps, o0 + C + cg * 8, o1 + C + cg * 8, lw.l);
+    const bf16* r = limg + static_cast<long>(row) * low.W * low.ps + 2 * C;
+    t = (1.f - lw.l) * __bfloat162float(r[o0]) + lw.l * __bfloat162float(r[o1]);
+  };
+  // rows past the image bottom (partial last strip) are clamped, computed redundantly and not stored: every lane runs
+  // all kStrip iterations, so the full-mask shuffles below are always convergent
+  const long pixn = static_cast<long>(ix.n) * x.H * x.W + ix.w;
+  uint4 xr[kStrip];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) dot += xv.v[e] * zv.v[e];
+  for (int r = 0; r < kStrip; ++r)
+    xr[r] = __ldg(reinterpret_cast<const uint4*>(x.ptr + (pixn + static_cast<long>(min(ix.h0 + r, x.H - 1)) * x.W) * x.ps + cg * 8));
+  F8 y0, z0, y1, z1;
+  float t0 = 0.f, t1 = 0.f;
+  int r0 = -1, r1 = -1;
 #pragma unroll
-  for (int o = LP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  // scalar term t (channel 2C of `low`)
-  const bf16* tb = low.ptr + static_cast<long>(n) * low.H * low.W * low.ps + 2 * C;
-  const float t00 = __bfloat162float(tb[(static_cast<long>(lh.i0) * low.W + lw.i0) * low.ps]);
-  const float t01 = __bfloat162float(tb[(static_cast<long>(lh.i0) * low.W + lw.i1) * low.ps]);
-  const float t10 = __bfloat162float(tb[(static_cast<long>(lh.i1) * low.W + lw.i0) * low.ps]);
-  const float t11 = __bfloat162float(tb[(static_cast<long>(lh.i1) * low.W + lw.i1) * low.ps]);
-  const float tt = (1.f - lh.l) * ((1.f - lw.l) * t00 + lw.l * t01) + lh.l * ((1.f - lw.l) * t10 + lw.l * t11);
-  const float g = sigmoidf_(dot + tt);
-  F8 o;
+  for (int r = 0; r < kStrip; ++r) {
+    const int h = min(ix.h0 + r, x.H - 1);
+    const Lerp lh = lerp_of(h, low.H, x.H);
+    if (lh.i0 != r0) {
+      if (lh.i0 == r1) { y0 = y1; z0 = z1; t0 = t1; }
+      else hrow(lh.i0, y0, z0, t0);
+      r0 = lh.i0;
+    }
+    if (lh.i1 != r1) {
+      if (lh.i1 == r0) { y1 = y0; z1 = z0; t1 = t0; }
+      else hrow(lh.i1, y1, z1, t1);
+      r1 = lh.i1;
+    }
+    F8 xv;
+    xv.v[0] = __uint_as_float(xr[r].x << 16); xv.v[1] = __uint_as_float(xr[r].x & 0xFFFF0000u);
+    xv.v[2] = __uint_as_float(xr[r].y << 16); xv.v[3] = __uint_as_float(xr[r].y & 0xFFFF0000u);
+    xv.v[4] = __uint_as_float(xr[r].z << 16); xv.v[5] = __uint_as_float(xr[r].z & 0xFFFF0000u);
+    xv.v[6] = __uint_as_float(xr[r].w << 16); xv.v[7] = __uint_as_float(xr[r].w & 0xFFFF0000u);
+    const F8 yv = vlerp8(y0, y1, lh.l), zv = vlerp8(z0, z1, lh.l);
+    float dot = 0.f;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    float v = (1.f - g) * xv.v[e] + g * yv.v[e];
-    o.v[e] = relu ? fmaxf(v, 0.f) : v;
+    for (int e = 0; e < 8; ++e) dot += xv.v[e] * zv.v[e];
+#pragma unroll
+    for (int o = LP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float g = sigmoidf_(dot + (1.f - lh.l) * t0 + lh.l * t1);
+    F8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = (1.f - g) * xv.v[e] + g * yv.v[e];
+      o.v[e] = relu ? fmaxf(v, 0.f) : v;
+    }
+    if (ix.valid && ix.h0 + r < x.H) st8(out.ptr + (pixn + static_cast<long>(h) * x.W) * out.ps + cg * 8, o);
   }
-  if (valid) st8(out.ptr + pix * out.ps + cg * 8, o);
 }
 
 // --------------------------------------------------------------------------- upadd / affine
@@ -220,6 +291,86 @@ __global__ void __launch_bounds__(256) upadd_kernel(View a, View b, View r, View
     for (int e = 0; e < 8; ++e) v.v[e] = fmaxf(v.v[e], 0.f);
   }
   st8(out.ptr + pix * out.ps + cg * 8, v);
+}
+
+// strip form of upadd_kernel for the upsampling case (b != null): out = act(s * (a + U(b)) + t (+ r))
+__device__ __forceinline__ F8 cvt8(const uint4& u) {
+  F8 r;
+  r.v[0] = __uint_as_float(u.x << 16); r.v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  r.v[2] = __uint_as_float(u.y << 16); r.v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  r.v[4] = __uint_as_float(u.z << 16); r.v[5] = __uint_as_float(u.z & 0xFFFF0000u);
+  r.v[6] = __uint_as_float(u.w << 16); r.v[7] = __uint_as_float(u.w & 0xFFFF0000u);
+  return r;
+}
+// the two low-res source rows of hi-res row h, kept across the strip (see "vertical strip walk")
+struct RowPair {
+  F8 a, b;
+  int ra = -1, rb = -1;
+  template <class Load>
+  __device__ __forceinline__ void advance(const Lerp& lh, Load&& load) {
+    if (lh.i0 != ra) {
+      if (lh.i0 == rb) a = b; else a = load(lh.i0);
+      ra = lh.i0;
+    }
+    if (lh.i1 != rb) {
+      if (lh.i1 == ra) b = a; else b = load(lh.i1);
+      rb = lh.i1;
+    }
+  }
+};
+__global__ void __launch_bounds__(256) upadd_strip_kernel(View a, View b, View r, View out, const float* __restrict__ s,
+                                                          const float* __restrict__ t, int relu) {
+  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, out.C >> 3, out.W, out.H, out.N);
+  if (!ix.valid) return;
+  const int cg = ix.cg;
+  const Lerp lw = lerp_of(ix.w, b.W, out.W);
+  const bf16* limg = b.ptr + static_cast<long>(ix.n) * b.H * b.W * b.ps;
+  const long o0 = static_cast<long>(lw.i0) * b.ps + cg * 8, o1 = static_cast<long>(lw.i1) * b.ps + cg * 8;
+  const long pixn = static_cast<long>(ix.n) * out.H * out.W + ix.w;
+  const int rows = min(kStrip, out.H - ix.h0);
+  uint4 ar[kStrip], rr[kStrip];
+#pragma unroll
+  for (int k = 0; k < kStrip; ++k) {
+    if (k < rows) {
+      const long pix = pixn + static_cast<long>(ix.h0 + k) * out.W;
+      if (a.ptr) ar[k] = __ldg(reinterpret_cast<const uint4*>(a.ptr + pix * a.ps + cg * 8));
+      if (r.ptr) rr[k] = __ldg(reinterpret_cast<const uint4*>(r.ptr + pix * r.ps + cg * 8));
+    }
+  }
+  F8 sc, sh;
+  if (s) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc.v[e] = __ldg(s + cg * 8 + e); sh.v[e] = __ldg(t + cg * 8 + e); }
+  }
+  RowPair rp;
+#pragma unroll
+  for (int k = 0; k < kStrip; ++k) {
+    if (k < rows) {
+      const int h = ix.h0 + k;
+      const Lerp lh = lerp_of(h, b.H, out.H);
+      rp.advance(lh, [&](int row) { return hsample8(limg, row, b.W, b.ps, o0, o1, lw.l); });
+      F8 v = vlerp8(rp.a, rp.b, lh.l);
+      if (a.ptr) {
+        const F8 av = cvt8(ar[k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] += av.v[e];
+      }
+      if (s) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = v.v[e] * sc.v[e] + sh.v[e];
+      }
+      if (r.ptr) {
+        const F8 rv = cvt8(rr[k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] += rv.v[e];
+      }
+      if (relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = fmaxf(v.v[e], 0.f);
+      }
+      st8(out.ptr + (pixn + static_cast<long>(h) * out.W) * out.ps + cg * 8, v);
+    }
+  }
 }
 
 // --------------------------------------------------------------------------- avg pool + affine
@@ -279,7 +430,104 @@ __global__ void __launch_bounds__(256) pool_affine_kernel(View x, View out, int 
 }
 
 // --------------------------------------------------------------------------- Light_Bag / Bag
-__global__ void __launch_bounds__(256) lightbag_uv_kernel(View p, View il, View d, View out) {
+// (strip walk: the x8 upsample of the PPM output costs 4 row gathers per 8 pixels instead of 32 corner gathers)
+template <bool kBag>
+__global__ void __launch_bounds__(256) bag_strip_kernel(View p, View il, View d, View out, const float* __restrict__ s,
+                                                        const float* __restrict__ t) {
+  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, p.C >> 3, p.W, p.H, p.N);
+  if (!ix.valid) return;
+  const int cg = ix.cg;
+  const Lerp lw = lerp_of(ix.w, il.W, p.W);
+  const bf16* limg = il.ptr + static_cast<long>(ix.n) * il.H * il.W * il.ps;
+  const long o0 = static_cast<long>(lw.i0) * il.ps + cg * 8, o1 = static_cast<long>(lw.i1) * il.ps + cg * 8;
+  const long pixn = static_cast<long>(ix.n) * p.H * p.W + ix.w;
+  const int rows = min(kStrip, p.H - ix.h0);
+  uint4 pr[kStrip], dr[kStrip];
+#pragma unroll
+  for (int k = 0; k < kStrip; ++k) {
+    if (k < rows) {
+      const long pix = pixn + static_cast<long>(ix.h0 + k) * p.W;
+      pr[k] = __ldg(reinterpret_cast<const uint4*>(p.ptr + pix * p.ps + cg * 8));
+      dr[k] = __ldg(reinterpret_cast<const uint4*>(d.ptr + pix * d.ps + cg * 8));
+    }
+  }
+  F8 sc, sh;
+  if (kBag) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc.v[e] = __ldg(s + cg * 8 + e); sh.v[e] = __ldg(t + cg * 8 + e); }
+  }
+  RowPair rp;
+#pragma unroll
+  for (int k = 0; k < kStrip; ++k) {
+    if (k < rows) {
+      const int h = ix.h0 + k;
+      const Lerp lh = lerp_of(h, il.H, p.H);
+      rp.advance(lh, [&](int row) { return hsample8(limg, row, il.W, il.ps, o0, o1, lw.l); });
+      const F8 iv = vlerp8(rp.a, rp.b, lh.l);
+      const F8 pv = cvt8(pr[k]), dv = cvt8(dr[k]);
+      bf16* op = out.ptr + (pixn + static_cast<long>(h) * p.W) * out.ps + cg * 8;
+      if (kBag) {
+        F8 o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float g = sigmoidf_(dv.v[e]);
+          const float a = g * pv.v[e] + (1.f - g) * iv.v[e];
+          o.v[e] = fmaxf(a * sc.v[e] + sh.v[e], 0.f);
+        }
+        st8(op, o);
+      } else {
+        F8 u, v;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float g = sigmoidf_(dv.v[e]);
+          u.v[e] = (1.f - g) * iv.v[e] + pv.v[e];
+          v.v[e] = iv.v[e] + g * pv.v[e];
+        }
+        st8(op, u);
+        st8(op + p.C, v);
+      }
+    }
+  }
+}
+
+// ---- flat (one thread per pixel x 8 channels) forms, the default for PagFM / Light_Bag: measured faster than their strip forms, which need 152 registers (PIDNET_ELTWISE_STRIP=1 selects those)
+template <int LP>  // lanes per pixel = C/8
+__global__ void __launch_bounds__(256) pag_fuse_flat_kernel(View x, View low, View out, int relu) {
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned npix = static_cast<unsigned>(x.N) * x.H * x.W;
+  const bool valid = gid / LP < npix;
+  int cg, w, h, n;
+  unsigned pixu;
+  decode_idx(valid ? gid : (npix - 1) * LP + gid % LP, LP, x.W, x.H, cg, w, h, n, pixu);   // LP is a compile-time power of two
+  const long pix = pixu;
+  const int C = x.C;
+  const Lerp lh = lerp_of(h, low.H, x.H), lw = lerp_of(w, low.W, x.W);
+  const F8 xv = ld8(x.ptr + pix * x.ps + cg * 8);
+  const F8 yv = sample8(low, n, lh, lw, cg * 8);
+  const F8 zv = sample8(low, n, lh, lw, C + cg * 8);
+  float dot = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dot += xv.v[e] * zv.v[e];
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  // scalar term t (channel 2C of `low`)
+  const bf16* tb = low.ptr + static_cast<long>(n) * low.H * low.W * low.ps + 2 * C;
+  const float t00 = __bfloat162float(tb[(static_cast<long>(lh.i0) * low.W + lw.i0) * low.ps]);
+  const float t01 = __bfloat162float(tb[(static_cast<long>(lh.i0) * low.W + lw.i1) * low.ps]);
+  const float t10 = __bfloat162float(tb[(static_cast<long>(lh.i1) * low.W + lw.i0) * low.ps]);
+  const float t11 = __bfloat162float(tb[(static_cast<long>(lh.i1) * low.W + lw.i1) * low.ps]);
+  const float tt = (1.f - lh.l) * ((1.f - lw.l) * t00 + lw.l * t01) + lh.l * ((1.f - lw.l) * t10 + lw.l * t11);
+  const float g = sigmoidf_(dot + tt);
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float v = (1.f - g) * xv.v[e] + g * yv.v[e];
+    o.v[e] = relu ? fmaxf(v, 0.f) : v;
+  }
+  if (valid) st8(out.ptr + pix * out.ps + cg * 8, o);
+}
+
+__global__ void __launch_bounds__(256) lightbag_uv_flat_kernel(View p, View il, View d, View out) {
   const int groups = p.C >> 3;
   const long total = static_cast<long>(p.N) * p.H * p.W * groups;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -303,29 +551,6 @@ __global__ void __launch_bounds__(256) lightbag_uv_kernel(View p, View il, View 
   st8(out.ptr + pix * out.ps + p.C + cg * 8, v);
 }
 
-__global__ void __launch_bounds__(256) bag_blend_kernel(View p, View il, View d, View out, const float* __restrict__ s,
-                                                        const float* __restrict__ t) {
-  const int groups = p.C >> 3;
-  const long total = static_cast<long>(p.N) * p.H * p.W * groups;
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  int cg, w, h, n;
-  unsigned pixu;
-  decode_idx(idx, groups, p.W, p.H, cg, w, h, n, pixu);
-  const long pix = pixu;
-  const Lerp lh = lerp_of(h, il.H, p.H), lw = lerp_of(w, il.W, p.W);
-  const F8 iv = sample8(il, n, lh, lw, cg * 8);
-  const F8 pv = ld8(p.ptr + pix * p.ps + cg * 8);
-  const F8 dv = ld8(d.ptr + pix * d.ps + cg * 8);
-  F8 o;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const float g = sigmoidf_(dv.v[e]);
-    const float a = g * pv.v[e] + (1.f - g) * iv.v[e];
-    o.v[e] = fmaxf(a * __ldg(s + cg * 8 + e) + __ldg(t + cg * 8 + e), 0.f);
-  }
-  st8(out.ptr + pix * out.ps + cg * 8, o);
-}
 
 // --------------------------------------------------------------------------- SIMT reference conv
 __global__ void __launch_bounds__(128) conv_ref_kernel(const ConvRefParams p) {
@@ -385,8 +610,22 @@ cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, cons
 
 cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t st) {
   const int LP = x.C / 8;
-  const long total = static_cast<long>(x.N) * x.H * x.W * LP;
-  if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
+  if (static_cast<long>(x.N) * x.H * x.W * LP + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic
+  static const bool flat = getenv("PIDNET_ELTWISE_STRIP") == nullptr;
+  if (flat) {
+    const unsigned nbf = blocks_for(static_cast<long>(x.N) * x.H * x.W * LP, 256);
+    switch (LP) {
+      case 1: pag_fuse_flat_kernel<1><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
+      case 2: pag_fuse_flat_kernel<2><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
+      case 4: pag_fuse_flat_kernel<4><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
+      case 8: pag_fuse_flat_kernel<8><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
+      case 16: pag_fuse_flat_kernel<16><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
+      case 32: pag_fuse_flat_kernel<32><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
+  const long total = static_cast<long>(x.N) * ((x.H + kStrip - 1) / kStrip) * x.W * LP;   // one thread per strip
   const unsigned nb = blocks_for(total, 256);
   switch (LP) {
     case 1: pag_fuse_kernel<1><<<nb, 256, 0, st>>>(x, low, out, relu); break;
@@ -407,7 +646,12 @@ cudaError_t upadd_launch(View a, View b, View out, const float* s, const float* 
 cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, const float* t, int relu, cudaStream_t st) {
   const long total = static_cast<long>(out.N) * out.H * out.W * (out.C / 8);
   if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
-  upadd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, b, r, out, s, t, relu);
+  if (b.ptr) {
+    const long strips = static_cast<long>(out.N) * ((out.H + kStrip - 1) / kStrip) * out.W * (out.C / 8);
+    upadd_strip_kernel<<<blocks_for(strips, 256), 256, 0, st>>>(a, b, r, out, s, t, relu);
+  } else {
+    upadd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, b, r, out, s, t, relu);
+  }
   return cudaGetLastError();
 }
 
@@ -425,14 +669,21 @@ cudaError_t pool_affine_launch(View x, View out, int k, int stride, int pad, con
 cudaError_t lightbag_uv_launch(View p, View i_low, View d, View out, cudaStream_t st) {
   const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
   if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
-  lightbag_uv_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out);
+  static const bool flat = getenv("PIDNET_ELTWISE_STRIP") == nullptr;
+  if (flat) {
+    lightbag_uv_flat_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out);
+    return cudaGetLastError();
+  }
+  const long strips = static_cast<long>(p.N) * ((p.H + kStrip - 1) / kStrip) * p.W * (p.C / 8);
+  bag_strip_kernel<false><<<blocks_for(strips, 256), 256, 0, st>>>(p, i_low, d, out, nullptr, nullptr);
   return cudaGetLastError();
 }
 
 cudaError_t bag_blend_launch(View p, View i_low, View d, View out, const float* s, const float* t, cudaStream_t st) {
   const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
   if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
-  bag_blend_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out, s, t);
+  const long strips = static_cast<long>(p.N) * ((p.H + kStrip - 1) / kStrip) * p.W * (p.C / 8);
+  bag_strip_kernel<true><<<blocks_for(strips, 256), 256, 0, st>>>(p, i_low, d, out, s, t);
   return cudaGetLastError();
 }
 

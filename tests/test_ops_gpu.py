@@ -51,10 +51,17 @@ CONV_CASES = [
     (1, 128, 256, 128, 128, 3, 1, 1, False, True, False), # final_layer.conv1 (many tiles per CTA)
     (4, 16, 32, 112, 112, 3, 1, 1, False, False, False),  # DAPPM process conv (K tail 112 = 64 + 48)
     (1, 40, 24, 64, 19, 3, 1, 1, False, False, True),     # 3x3 with fp32 NCHW output
+    # CTA-pair instance (cta_group::2, BN = CK = 64): odd tile counts (the last pair's second CTA runs past the end),
+    # many iterations per pair with the three rotating staging buffers, residual on and off
+    (1, 48, 8, 64, 64, 3, 1, 1, True, True, False),       # 3 tiles
+    (3, 80, 40, 64, 64, 3, 1, 1, True, True, False),      # 75 tiles: odd, one per CTA
+    (5, 112, 136, 64, 64, 3, 1, 1, False, True, False),   # 595 tiles: odd, ~8 iterations per pair
+    (6, 112, 136, 128, 64, 3, 1, 1, True, False, False),  # two chunks, residual, ~10 iterations per pair
+    (1, 16, 8, 64, 64, 3, 1, 1, False, False, False),     # a single tile (no pair possible)
 ]
 
 
-@pytest.mark.parametrize('impl', [1, 2, 0], ids=['simt', 'tcgen05-generic', 'tcgen05-default'])
+@pytest.mark.parametrize('impl', [1, 2, 3, 0], ids=['simt', 'tcgen05-generic', 'tcgen05-ws-single-cta', 'tcgen05-default'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: 'x'.join(map(str, c)))
 def test_conv2d(case, impl):
     dev = _dev()
