@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libpidnet_b200.so')
-SOURCES = ['conv_tc.cu', 'conv3_ws.cu', 'stem_tc.cu', 'criterion.cu', 'train_kernels.cu', 'wgrad_tc.cu', 'kernels.cu', 'engine.cu', 'probe.cu']
+SOURCES = ['conv_tc.cu', 'conv3_ws.cu', 'stem_tc.cu', 'stem2_tc.cu', 'criterion.cu', 'train_kernels.cu', 'wgrad_tc.cu', 'kernels.cu', 'engine.cu', 'probe.cu']
 HEADERS = ['conv_tc.cuh', 'kernels.cuh', 'ptx.cuh', 'criterion.cuh', 'train_kernels.cuh', 'train.inc', os.path.join('..', '..', 'include', 'pidnet_b200.h')]
 
 

@@ -16,14 +16,21 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   // pipeline depth: keep >= 2 CTAs per SM where the tile allows it (epilogue of one overlaps the
   // main loop of the other); the 128-wide tile takes the SM alone with a deeper ring.
-  static constexpr int kStages = (BN == 128) ? 4 : ((BN == 64 && BK == 64) ? 3 : 4);
+  // The 128-wide tile used to take the SM alone (4 stages + staging = 162 KB): with one non-persistent CTA per SM nothing
+  // overlapped its prologue (TMEM alloc, first TMA round trip) and epilogue.  It now runs 3 stages and ALIASES the output
+  // staging tile onto the (by then drained) stage ring, which fits two CTAs per SM.
+  static constexpr bool kAliasOut = (BN == 128 && BK == 64);
+  static constexpr int kStages = kAliasOut ? 3 : ((BN == 128) ? 4 : ((BN == 64 && BK == 64) ? 3 : 4));
   static constexpr int kSlabC = BN < 64 ? BN : 64;  // channels per staged output slab
   static constexpr int kSlabRowBytes = kSlabC * 2;  // == swizzle span of tmD / tmR
   static constexpr int kSlabBytes = kTileM * kSlabRowBytes;
   static constexpr int kNumSlabs = BN / kSlabC;
   static constexpr int kOutBytes = kTileM * BN * 2;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmem = kStages * kStageBytes + kOutBytes + BN * 4 + kBarBytes + 1024 /*align slack*/;
+  static constexpr int kOutOffset = kAliasOut ? 0 : kStages * kStageBytes;
+  static constexpr int kTailOffset = kAliasOut ? kStages * kStageBytes : kStages * kStageBytes + kOutBytes;   // bias, barriers
+  static_assert(!kAliasOut || kStages * kStageBytes >= kOutBytes, "staging tile must fit in the stage ring");
+  static constexpr int kSmem = kTailOffset + BN * 4 + kBarBytes + 1024 /*align slack*/;
 };
 
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
@@ -34,17 +41,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 template <int BN, int BK>
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kThreads, Cfg<BN, BK>::kAliasOut ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using C = Cfg<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const uint32_t stage_base = smem_base;
-  const uint32_t out_base = smem_base + C::kStages * C::kStageBytes;
-  uint8_t* out_gen = smem_gen + C::kStages * C::kStageBytes;
-  float* bias_s = reinterpret_cast<float*>(out_gen + C::kOutBytes);
-  const uint32_t bar_base = out_base + C::kOutBytes + BN * 4;
+  const uint32_t out_base = smem_base + C::kOutOffset;
+  uint8_t* out_gen = smem_gen + C::kOutOffset;
+  float* bias_s = reinterpret_cast<float*>(smem_gen + C::kTailOffset);
+  const uint32_t bar_base = smem_base + C::kTailOffset + BN * 4;
   // barriers: full[kStages], empty[kStages], acc_full, res_full ; then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
@@ -52,7 +59,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   const uint32_t res_bar = acc_bar + 8u;
   const uint32_t tmem_slot = res_bar + 8u;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(out_gen + C::kOutBytes + BN * 4 + 8 * (2 * C::kStages + 2));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::kTailOffset + BN * 4 + 8 * (2 * C::kStages + 2));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,11 +99,12 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     // ======================= TMA producer =======================
     if (elect_one()) {
       tma_prefetch_desc(&p.tmB);
-      if (p.has_res) {
+      auto load_residual = [&] {
         mbar_arrive_expect_tx(res_bar, C::kOutBytes);
         for (int sl = 0; sl < C::kNumSlabs; ++sl)
           tma_load_4d(out_base + sl * C::kSlabBytes, &p.tmR, res_bar, c_out0 + sl * C::kSlabC, w0, h0, n0);
-      }
+      };
+      if (p.has_res && !C::kAliasOut) load_residual();
       int ks = 0;
       for (int s = 0; s < p.nsrc; ++s) {
         const ConvSrc& src = p.src[s];
@@ -115,6 +123,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             tma_load_2d(a_dst + C::kABytes, &p.tmB, full_bar(st), ks * BK, c_out0);
           }
         }
+      }
+      if (p.has_res && C::kAliasOut) {   // the staging tile aliases the ring: wait until every MMA has read its stage
+        mbar_wait(acc_bar, 0);
+        load_residual();
       }
     }
     __syncwarp();

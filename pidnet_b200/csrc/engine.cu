@@ -190,6 +190,7 @@ struct Builder {
   bool dry = true;
   int conv_impl = 0;
   int use_ws = 1;   // weight-stationary halo-patch kernel for 3x3 stride-1 convs
+  int use_stem2 = env_int("PIDNET_STEM2", 1);       // fused conv1.0 -> conv1.3 kernel (stem2_tc.cu)
   int use_pair = env_int("PIDNET_WS_PAIR", 1);      // CTA pairs (tcgen05 cta_group::2) where conv3_ws has the instance
   int ws_stages = env_int("PIDNET_WS_STAGES", 3);   // rotating staging buffers of the weight-stationary kernels (2 or 3)
   int num_sms = 148;
@@ -680,7 +681,7 @@ struct Engine {
   int lanes = 3;
   int conv_impl = 0;
   int use_ws = 1;
-  int use_pair = -1, ws_stages = -1;   // -1: builder default (environment / built-in)
+  int use_pair = -1, ws_stages = -1, use_stem2 = -1;   // -1: builder default (environment / built-in)
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;  // capture origin (the caller's stream may be the legacy default stream)
   // uint8 input path: per-channel table of the reference's input_transform (datasets/base_dataset.py:36-44), evaluated
@@ -1040,59 +1041,119 @@ struct Engine {
     if (H % 8 || W % 8) fail("H and W must be multiples of 8");
     b.conv_impl = conv_impl;
 
-    // stem conv1.0 + BN + ReLU : fp32 NCHW -> bf16 NHWC
+    // stem: conv1.0 + BN + ReLU -> conv1.3 + BN + ReLU
     b.lane = L0;
-    T x1 = b.new_tensor(N, cdiv(H, 2), cdiv(W, 2), Pn);
-    {
-      Affine a = bn("conv1.1");
-      std::vector<float> w, bias;
-      fold("conv1.0", &a, w, bias);  // [P][3][3][3]
+    T x;
+    const bool stem2 = conv_impl == 0 && b.use_stem2 && (Pn == 32 || Pn == 64) &&
+                       P("conv1.3.weight").shape[0] == Pn && P("conv1.3.weight").shape[1] == Pn;
+    if (stem2) {
+      // ONE kernel; the half-resolution conv1.0 output (the largest tensor of the net) never reaches HBM
+      const int H1 = cdiv(H, 2), W1 = cdiv(W, 2), H2 = cdiv(H1, 2), W2 = cdiv(W1, 2);
+      x = b.new_tensor(N, H2, W2, Pn);
+      Affine a1 = bn("conv1.1"), a2 = bn("conv1.4");
+      std::vector<float> w1, bias1, w2, bias2;
+      fold("conv1.0", &a1, w1, bias1);   // [P][3][3][3]
+      fold("conv1.3", &a2, w2, bias2);   // [P][P][3][3]
       if (P("conv1.0.weight").shape[1] != 3) fail("conv1.0 must have 3 input channels");
-      std::vector<float> wt(static_cast<size_t>(27) * Pn);
+      std::vector<uint16_t> w1s(static_cast<size_t>(Pn) * 32, 0);
       for (int co = 0; co < Pn; ++co)
-        for (int k = 0; k < 27; ++k) wt[static_cast<size_t>(k) * Pn + co] = w[static_cast<size_t>(co) * 27 + k];
-      const float* wd = b.upload_f32(wt);
-      const float* bd = b.upload_f32(bias);
-      View ov = x1.view();
-      const int n_ = N, h_ = H, w_ = W;
-      b.flops += 2.0 * N * x1.H * x1.W * Pn * 27;
-      const bool stem_tc = conv_impl == 0 && (Pn == 32 || Pn == 64);
-      // tcgen05 stem: weights [Cout][32] bf16 K-major, pre-swizzled the way a SWIZZLE_64B tile sits in smem
-      std::vector<uint16_t> wsw(static_cast<size_t>(Pn) * 32, 0);
-      for (int co = 0; co < Pn; ++co)
-        for (int k = 0; k < 27; ++k) {
-          const int chunk = k / 8, within = k % 8;
-          const int pos = co * 32 + ((chunk ^ ((co >> 1) & 3)) * 8) + within;
-          wsw[pos] = f2bf(w[static_cast<size_t>(co) * 27 + k]);
-        }
-      const uint8_t* wswd = reinterpret_cast<const uint8_t*>(b.alloc_wt(wsw.data(), wsw.size() * 2));
-      StemParams sp;
+        for (int k = 0; k < 27; ++k)
+          w1s[co * 32 + (((k / 8) ^ ((co >> 1) & 3)) * 8) + k % 8] = f2bf(w1[static_cast<size_t>(co) * 27 + k]);
+      for (int co = 0; co < Pn; ++co) {   // K columns 27 / 28 (the im2col rows hold 1.0 there): bias as bf16 hi + lo
+        const uint16_t hi = f2bf(bias1[co]);
+        uint32_t hb = static_cast<uint32_t>(hi) << 16;
+        float hf;
+        std::memcpy(&hf, &hb, 4);
+        w1s[co * 32 + ((3 ^ ((co >> 1) & 3)) * 8) + 3] = hi;
+        w1s[co * 32 + ((3 ^ ((co >> 1) & 3)) * 8) + 4] = f2bf(bias1[co] - hf);
+      }
+      // conv1.3 tap tiles [tap][co][ci], rows of Pn*2 bytes, 16-byte chunks XOR-swizzled the way tcgen05 reads them
+      std::vector<uint16_t> w2s(static_cast<size_t>(9) * Pn * Pn, 0);
+      const int cmask = Pn == 32 ? 3 : 7;
+      for (int tap = 0; tap < 9; ++tap)
+        for (int co = 0; co < Pn; ++co)
+          for (int ci = 0; ci < Pn; ++ci) {
+            const int sw = Pn == 32 ? ((co >> 1) & 3) : (co & 7);
+            const size_t pos = (static_cast<size_t>(tap) * Pn + co) * Pn + ((((ci >> 3) ^ sw) & cmask) << 3) + (ci & 7);
+            w2s[pos] = f2bf(w2[(static_cast<size_t>(co) * Pn + ci) * 9 + tap]);
+          }
+      Stem2Params sp;
       std::memset(&sp, 0, sizeof(sp));
-      sp.w_swz = wswd; sp.bias = bd; sp.H = H; sp.W = W; sp.Ho = x1.H; sp.Wo = x1.W; sp.relu = 1;
-      sp.rows = static_cast<long>(N) * x1.H * x1.W;
-      sp.tiles = (sp.rows + 127) / 128;
-      if (stem_tc && !b.dry) {
-        uint64_t dims4[4] = {static_cast<uint64_t>(Pn), static_cast<uint64_t>(sp.rows), 1, 1};
-        uint64_t str[3] = {static_cast<uint64_t>(Pn) * 2, static_cast<uint64_t>(sp.rows) * Pn * 2,
-                           static_cast<uint64_t>(sp.rows) * Pn * 2};
-        uint32_t box4[4] = {static_cast<uint32_t>(Pn), 128, 1, 1};
-        sp.tmD = encode_map(x1.ptr, 4, dims4, str, box4, Pn * 2);
+      sp.w1_swz = reinterpret_cast<const uint8_t*>(b.alloc_wt(w1s.data(), w1s.size() * 2));
+      sp.w2_swz = reinterpret_cast<const uint8_t*>(b.alloc_wt(w2s.data(), w2s.size() * 2));
+      sp.bias1 = b.upload_f32(bias1);
+      sp.bias2 = b.upload_f32(bias2);
+      sp.H = H; sp.W = W; sp.H1 = H1; sp.W1 = W1; sp.H2 = H2; sp.W2 = W2;
+      sp.tiles_w = cdiv(W2, 8); sp.tiles_h = cdiv(H2, 16); sp.N = N;
+      if (!b.dry) {
+        uint64_t dims4[4] = {static_cast<uint64_t>(Pn), static_cast<uint64_t>(W2), static_cast<uint64_t>(H2),
+                             static_cast<uint64_t>(N)};
+        uint64_t str[3] = {static_cast<uint64_t>(x.ps) * 2, static_cast<uint64_t>(W2) * x.ps * 2,
+                           static_cast<uint64_t>(H2) * W2 * x.ps * 2};
+        uint32_t box4[4] = {static_cast<uint32_t>(Pn), 8, 16, 1};
+        sp.tmD = encode_map(x.ptr, 4, dims4, str, box4, Pn * 2);
       }
       const int sms = b.num_sms;
-      x1.prod = b.add_op("conv1.0", {}, [ov, wd, bd, n_, h_, w_, sp, stem_tc, Pn, sms](cudaStream_t st, const RunArgs& a) mutable {
-        if (stem_tc) {
-          sp.x = a.x;
-          sp.x_u8 = a.x_u8;
-          sp.lut = a.lut;
-          return stem_tc_launch(sp, Pn, sms, st);
-        }
-        if (a.x_u8) return cudaErrorNotSupported;   // the uint8 path exists in the tcgen05 stem only
-        return stem_conv_launch(a.x, n_, h_, w_, ov, wd, bd, st);
+      const double fl = 2.0 * N * H1 * W1 * Pn * 27 + 2.0 * N * H2 * W2 * Pn * Pn * 9;
+      b.flops += fl;
+      x.prod = b.add_op("conv1.0+conv1.3", {}, [sp, Pn, sms](cudaStream_t st, const RunArgs& a) mutable {
+        sp.x = a.x; sp.x_u8 = a.x_u8; sp.lut = a.lut;
+        return stem2_tc_launch(sp, Pn, sms, st);
       });
-      b.label(x1.prod, stem_tc ? "stem_tc" : "stem_conv", 4.0 * N * 3 * H * W + Builder::tbytes(x1),
-              2.0 * N * x1.H * x1.W * Pn * 27);
+      b.label(x.prod, "stem2_tc", 4.0 * N * 3 * H * W + Builder::tbytes(x), fl);
+    } else {
+      T x1 = b.new_tensor(N, cdiv(H, 2), cdiv(W, 2), Pn);
+      {
+        Affine a = bn("conv1.1");
+        std::vector<float> w, bias;
+        fold("conv1.0", &a, w, bias);  // [P][3][3][3]
+        if (P("conv1.0.weight").shape[1] != 3) fail("conv1.0 must have 3 input channels");
+        std::vector<float> wt(static_cast<size_t>(27) * Pn);
+        for (int co = 0; co < Pn; ++co)
+          for (int k = 0; k < 27; ++k) wt[static_cast<size_t>(k) * Pn + co] = w[static_cast<size_t>(co) * 27 + k];
+        const float* wd = b.upload_f32(wt);
+        const float* bd = b.upload_f32(bias);
+        View ov = x1.view();
+        const int n_ = N, h_ = H, w_ = W;
+        b.flops += 2.0 * N * x1.H * x1.W * Pn * 27;
+        const bool stem_tc = conv_impl == 0 && (Pn == 32 || Pn == 64);
+        // tcgen05 stem: weights [Cout][32] bf16 K-major, pre-swizzled the way a SWIZZLE_64B tile sits in smem
+        std::vector<uint16_t> wsw(static_cast<size_t>(Pn) * 32, 0);
+        for (int co = 0; co < Pn; ++co)
+          for (int k = 0; k < 27; ++k) {
+            const int chunk = k / 8, within = k % 8;
+            const int pos = co * 32 + ((chunk ^ ((co >> 1) & 3)) * 8) + within;
+            wsw[pos] = f2bf(w[static_cast<size_t>(co) * 27 + k]);
+          }
+        const uint8_t* wswd = reinterpret_cast<const uint8_t*>(b.alloc_wt(wsw.data(), wsw.size() * 2));
+        StemParams sp;
+        std::memset(&sp, 0, sizeof(sp));
+        sp.w_swz = wswd; sp.bias = bd; sp.H = H; sp.W = W; sp.Ho = x1.H; sp.Wo = x1.W; sp.relu = 1;
+        sp.rows = static_cast<long>(N) * x1.H * x1.W;
+        sp.tiles = (sp.rows + 127) / 128;
+        if (stem_tc && !b.dry) {
+          uint64_t dims4[4] = {static_cast<uint64_t>(Pn), static_cast<uint64_t>(sp.rows), 1, 1};
+          uint64_t str[3] = {static_cast<uint64_t>(Pn) * 2, static_cast<uint64_t>(sp.rows) * Pn * 2,
+                             static_cast<uint64_t>(sp.rows) * Pn * 2};
+          uint32_t box4[4] = {static_cast<uint32_t>(Pn), 128, 1, 1};
+          sp.tmD = encode_map(x1.ptr, 4, dims4, str, box4, Pn * 2);
+        }
+        const int sms = b.num_sms;
+        x1.prod = b.add_op("conv1.0", {}, [ov, wd, bd, n_, h_, w_, sp, stem_tc, Pn, sms](cudaStream_t st, const RunArgs& a) mutable {
+          if (stem_tc) {
+            sp.x = a.x;
+            sp.x_u8 = a.x_u8;
+            sp.lut = a.lut;
+            return stem_tc_launch(sp, Pn, sms, st);
+          }
+          if (a.x_u8) return cudaErrorNotSupported;   // the uint8 path exists in the tcgen05 stem only
+          return stem_conv_launch(a.x, n_, h_, w_, ov, wd, bd, st);
+        });
+        b.label(x1.prod, stem_tc ? "stem_tc" : "stem_conv", 4.0 * N * 3 * H * W + Builder::tbytes(x1),
+                2.0 * N * x1.H * x1.W * Pn * 27);
+      }
+      x = conv_bn("conv1.3", x1, "conv1.3", "conv1.4", 3, 2, true);
     }
-    T x = conv_bn("conv1.3", x1, "conv1.3", "conv1.4", 3, 2, true);
     b.named["conv1"] = x;
     x = layer("layer1", x, false, m, 1, true);
     b.named["layer1"] = x;
@@ -1216,6 +1277,7 @@ struct Engine {
     b.use_ws = use_ws;
     if (use_pair >= 0) b.use_pair = use_pair;
     if (ws_stages >= 0) b.ws_stages = ws_stages;
+    if (use_stem2 >= 0) b.use_stem2 = use_stem2;
     b.reset(true);
     build();  // dry pass: sizes only
     const size_t act_bytes = b.act_cur, wt_bytes = b.wt_cur;
@@ -1397,6 +1459,7 @@ int pidnet_set_option(pidnet_engine* h, const char* name, int value) {
     else if (k == "lanes") h->e.lanes = value == 3 ? 3 : 1;
     else if (k == "use_ws") h->e.use_ws = value ? 1 : 0;
     else if (k == "use_pair") h->e.use_pair = value ? 1 : 0;
+    else if (k == "use_stem2") h->e.use_stem2 = value ? 1 : 0;
     else if (k == "ws_stages") h->e.ws_stages = value == 2 ? 2 : 3;
     else fail("unknown option '" + k + "'");
     h->e.planned = false;

@@ -39,6 +39,22 @@ struct StemParams {
   int relu;             // 1: inference (bias + ReLU); 0: training (raw conv output, BatchNorm follows)
 };
 cudaError_t stem_tc_launch(const StemParams& p, int Cout, int num_sms, cudaStream_t st);
+// ---- fused stem (stem2_tc.cu): conv1.0+BN+ReLU -> conv1.3+BN+ReLU, the C-channel half-resolution intermediate stays in smem
+struct Stem2Params {
+  CUtensorMap tmD;        // conv1.3 output [N,H2,W2,C] bf16 NHWC, box {C, 8, 16, 1}, swizzle = C*2 bytes
+  const float* x;         // fp32 NCHW image (or null)
+  const uint8_t* x_u8;    // uint8 HWC BGR frames (or null), normalised through `lut` as in StemParams
+  const float* lut;
+  const uint8_t* w1_swz;  // conv1.0: [C][32] bf16 K-major, pre-swizzled SWIZZLE_64B (== StemParams::w_swz)
+  const float* bias1;     // [C]
+  const uint8_t* w2_swz;  // conv1.3: [9 taps][C out][C in] bf16 K-major tiles, pre-swizzled (C*2-byte rows)
+  const float* bias2;     // [C]
+  int H, W;               // image
+  int H1, W1;             // conv1.0 output (ceil(H/2), ceil(W/2))
+  int H2, W2;             // conv1.3 output
+  int tiles_w, tiles_h, N;  // 16 x 8 output tiles
+};
+cudaError_t stem2_tc_launch(const Stem2Params& p, int C, int num_sms, cudaStream_t st);
 // training: fp32 [Cout][3][3][3] master weights -> the pre-swizzled bf16 [Cout][32] tile of the kernel above
 cudaError_t stem_pack_launch(const float* w, uint8_t* w_swz, int Cout, cudaStream_t st);
 
