@@ -1057,8 +1057,11 @@ struct Engine {
       if (P("conv1.0.weight").shape[1] != 3) fail("conv1.0 must have 3 input channels");
       std::vector<uint16_t> w1s(static_cast<size_t>(Pn) * 32, 0);
       for (int co = 0; co < Pn; ++co)
-        for (int k = 0; k < 27; ++k)
-          w1s[co * 32 + (((k / 8) ^ ((co >> 1) & 3)) * 8) + k % 8] = f2bf(w1[static_cast<size_t>(co) * 27 + k]);
+        for (int m = 0; m < 9; ++m)        // m = ci * 3 + r; kernel K order (stem2_tc.cu P1): taps s = 1, 2 at 2m, 2m+1; s = 0 at 18 + m
+          for (int sx = 0; sx < 3; ++sx) {
+            const int k = sx == 0 ? 18 + m : 2 * m + (sx - 1);
+            w1s[co * 32 + (((k / 8) ^ ((co >> 1) & 3)) * 8) + k % 8] = f2bf(w1[static_cast<size_t>(co) * 27 + m * 3 + sx]);
+          }
       for (int co = 0; co < Pn; ++co) {   // K columns 27 / 28 (the im2col rows hold 1.0 there): bias as bf16 hi + lo
         const uint16_t hi = f2bf(bias1[co]);
         uint32_t hb = static_cast<uint32_t>(hi) << 16;

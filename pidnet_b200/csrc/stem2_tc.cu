@@ -36,6 +36,13 @@ __device__ __forceinline__ uint32_t pk2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// {lo, hi} -> bf16x2 with ReLU folded into the conversion (one instruction for two channels)
+__device__ __forceinline__ uint32_t pk2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 template <int C>
 struct S2Geom {
   static constexpr int kRowB = C * 2;
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(kS2Threads, C == 32 ? 2 : 1) stem2_tc_kernel(c
 #pragma unroll
       for (int k = 0; k < kLdRounds; ++k) {
         const int idx = threadIdx.x + k * kS2Threads;
-        if (idx < kLdItems) {
+        if (k < kLdRounds - 1 || idx < kLdItems) {   // (only the last round is partial)
           uint2 o;
           o.x = pk2(pre[k].x, pre[k].y); o.y = pk2(pre[k].z, pre[k].w);
           *reinterpret_cast<uint2*>(patch_gen + idx * 4) = o;   // idx == (ci * 67 + row) * 9 + g  ->  element (..) * 36 + 4 g
@@ -183,7 +190,6 @@ __global__ void __launch_bounds__(kS2Threads, C == 32 ? 2 : 1) stem2_tc_kernel(c
       const int j = idx / kPosW, i = idx - j * kPosW;
       const int pi = i & 1, pj = j & 1;
       const int prow = (pj ? (pi ? kPl3 : kPl2) : (pi ? kPl1 : kPl0)) + (j >> 1) * (pi ? 8 : 9) + (i >> 1);
-      const uint16_t* pp = reinterpret_cast<const uint16_t*>(patch_gen) + (2 * j) * 36 + 2 * i + 1;
       const int swz = (prow >> 1) & 3;
       const int y = y0 + j, x = x0 + i;
       if (y < 0 || y >= p.H1 || x < 0 || x >= p.W1) {
@@ -192,23 +198,26 @@ __global__ void __launch_bounds__(kS2Threads, C == 32 ? 2 : 1) stem2_tc_kernel(c
         for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(a1_gen + prow * 64 + (ch << 4)) = make_uint4(0u, 0u, 0u, 0u);
         continue;
       }
-      uint32_t h[28];
+      // The taps of (ci, r) are patch columns 2i+1 .. 2i+3 = the high half of 32-bit word i and both halves of word i+1, so
+      // the K order is chosen to need no per-element shuffling: k = 2m, 2m+1: taps s = 1, 2 of m = ci*3 + r (word i+1 as
+      // is); k = 18 + m: tap s = 0; k = 27, 28: 1.0 (the weight tile carries bias_hi / bias_lo there).
+      const uint32_t* pw = reinterpret_cast<const uint32_t*>(patch_gen) + (2 * j) * 18 + i;
+      uint32_t wa[9], w[16];
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r) {
+          wa[ci * 3 + r] = pw[(ci * kPatH + r) * 18];
+          w[ci * 3 + r] = pw[(ci * kPatH + r) * 18 + 1];
+        }
 #pragma unroll
-          for (int s2 = 0; s2 < 3; ++s2) h[(ci * 3 + r) * 3 + s2] = pp[(ci * kPatH + r) * 36 + s2];
-      h[27] = 0x3F80u;   // K columns 27 and 28 are 1.0: the weight tile carries the bias there (bf16 hi + lo parts)
+      for (int m = 0; m < 4; ++m) w[9 + m] = __byte_perm(wa[2 * m], wa[2 * m + 1], 0x7632);
+      w[13] = (wa[8] >> 16) | 0x3F800000u;
+      w[14] = 0x00003F80u;
+      w[15] = 0u;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint4 q;
-        q.x = h[ch * 8 + 0] | (h[ch * 8 + 1] << 16);
-        q.y = h[ch * 8 + 2] | (h[ch * 8 + 3] << 16);
-        q.z = ch < 3 ? (h[ch * 8 + 4] | (h[ch * 8 + 5] << 16)) : 0x3F80u;
-        q.w = ch < 3 ? (h[ch * 8 + 6] | (h[ch * 8 + 7] << 16)) : 0u;
-        *reinterpret_cast<uint4*>(a1_gen + prow * 64 + ((ch ^ swz) << 4)) = q;
-      }
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(a1_gen + prow * 64 + ((ch ^ swz) << 4)) = make_uint4(w[ch * 4], w[ch * 4 + 1], w[ch * 4 + 2], w[ch * 4 + 3]);
     }
     if (threadIdx.x == 0) tma_store_wait_read();   // the previous tile's store has read the staging buffer out
     fence_proxy_async_smem();
@@ -255,11 +264,12 @@ __global__ void __launch_bounds__(kS2Threads, C == 32 ? 2 : 1) stem2_tc_kernel(c
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int c = g * 32 + jj * 8;
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(acc[jj * 8 + e]), 0.f);   // bias came through the MMA
+              const uint32_t* av = acc + jj * 8;   // bias came through the MMA; ReLU rides in the conversion
               uint4 o;
-              o.x = pk2(f[0], f[1]); o.y = pk2(f[2], f[3]); o.z = pk2(f[4], f[5]); o.w = pk2(f[6], f[7]);
+              o.x = pk2_relu(__uint_as_float(av[0]), __uint_as_float(av[1]));
+              o.y = pk2_relu(__uint_as_float(av[2]), __uint_as_float(av[3]));
+              o.z = pk2_relu(__uint_as_float(av[4]), __uint_as_float(av[5]));
+              o.w = pk2_relu(__uint_as_float(av[6]), __uint_as_float(av[7]));
               *reinterpret_cast<uint4*>(gen + roff + (((c >> 3) ^ swz) << 4)) = o;
             }
           }
@@ -314,9 +324,9 @@ __global__ void __launch_bounds__(kS2Threads, C == 32 ? 2 : 1) stem2_tc_kernel(c
           const int c = g * 32 + jj * 8;
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(acc[jj * 8 + e]) + bias2_s[c + e], 0.f);
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[jj * 8 + e]) + bias2_s[c + e];
           uint4 o;
-          o.x = pk2(f[0], f[1]); o.y = pk2(f[2], f[3]); o.z = pk2(f[4], f[5]); o.w = pk2(f[6], f[7]);
+          o.x = pk2_relu(f[0], f[1]); o.y = pk2_relu(f[2], f[3]); o.z = pk2_relu(f[4], f[5]); o.w = pk2_relu(f[6], f[7]);
           *reinterpret_cast<uint4*>(st_gen + row * kRowB + (((c >> 3) ^ swz) << 4)) = o;
         }
       }
