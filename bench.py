@@ -120,7 +120,7 @@ def run_reference(a):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
     NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -130,11 +130,27 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                       '-lms', '50', '-i', str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       '-lms', '20', '-i', str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    def wait_ready(self, timeout=3.0):
+        """Block until nvidia-smi has written its first sample (so the loop is running before the timed region)."""
+        t_end = time.time() + timeout
+        while self.p is not None and time.time() < t_end:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return True
+            except OSError:
+                pass
+            time.sleep(0.01)
+        return False
+
+    def stop(self, t0=None, t1=None):
+        """Samples whose nvidia-smi timestamp lies inside the timed region [t0, t1] (host epoch seconds); the sampler is
+        started before the warm-up so that it is already running when the region begins.  If the region was too short to
+        catch one, the samples taken under load just before it (warm-up) are reported and `window` says so."""
+        import datetime
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.p is None:
             return out
@@ -145,23 +161,31 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, pw, reasons = [], [], [], set()
+        rows = []
         for line in self.f.read().splitlines():
             parts = [p.strip() for p in line.split(',')]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]),
+                             [nm for nm, v in zip(self.NAMES, parts[4:8]) if v.lower().startswith('active')]))
             except ValueError:
                 continue
-            for nm, v in zip(self.NAMES, parts[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(nm)
         self.f.close()
         os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), reasons=sorted(reasons),
-                       samples=len(sm))
+        window = 'all'
+        sel = rows
+        if t0 is not None and t1 is not None:
+            inside = [r for r in rows if t0 <= r[0] <= t1]
+            if inside:
+                sel, window = inside, 'timed region'
+            else:   # the last samples before the region ended (GPU already under the warm-up load)
+                sel, window = [r for r in rows if r[0] <= t1][-3:], 'warm-up + timed region (region shorter than the sampling period)'
+        if sel:
+            out.update(sm_mhz=statistics.median(r[1] for r in sel), sm_max_mhz=max(r[2] for r in sel),
+                       power_w_max=max(r[3] for r in sel), reasons=sorted({n for r in sel for n in r[4]}),
+                       samples=len(sel), window=window)
         return out
 
 
@@ -225,18 +249,22 @@ def run_ours(a):
     x = x_host.to(dev, non_blocking=True)
     out = torch.empty(B, a.classes, H // 8, W // 8, device=dev)
     with torch.no_grad():
+        sampler = ClockSampler(local) if rank == 0 else None   # started early: nvidia-smi takes ~0.1 s to deliver its first line
+        if sampler:
+            sampler.wait_ready()
         for _ in range(max(a.warmup, 3)):
             model.forward_into(x, out, use_graph=use_graph)
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host0 = time.time()
         e0.record()
         for _ in range(a.steps):
             model.forward_into(x, out, use_graph=use_graph)
         e1.record()
         barrier()
+        t_host1 = time.time()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_host0, t_host1) if sampler else None
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -34,8 +34,37 @@ struct Lerp {
   int i0, i1;
   float l;
 };
-__device__ __forceinline__ Lerp lerp_of(int dst, int in, int out) {
-  const float scale = static_cast<float>(in) / static_cast<float>(out);
+// Exact unsigned division by a launch-time constant (Granlund-Montgomery round-up): umulhi + 4 ALU ops instead of the
+// ~20-instruction runtime division; the elementwise kernels are instruction-issue bound and decode three of them per thread.
+struct FastDiv {
+  uint32_t mul, sh1, sh2;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{0u, 0u, 0u};   // d == 1: q = n
+  if (d > 1) {
+    const uint32_t l = 32u - static_cast<uint32_t>(__builtin_clz(d - 1));   // ceil(log2 d)
+    f.mul = static_cast<uint32_t>((((1ull << l) - d) << 32) / d + 1);
+    f.sh1 = 1; f.sh2 = l - 1;
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.mul, n);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+// launch-time decode constants of an elementwise kernel: divisors (channel groups, W, H or strips) and the two bilinear scales
+struct Dec {
+  FastDiv g, w, h;
+  float sh, sw;   // low-res / hi-res size ratios (torch: scale = in / out in fp32)
+};
+inline Dec make_dec(int groups, int W, int Hdiv, int in_h, int out_h, int in_w, int out_w) {
+  Dec d;
+  d.g = make_fastdiv(groups); d.w = make_fastdiv(W); d.h = make_fastdiv(Hdiv);
+  d.sh = out_h ? static_cast<float>(in_h) / static_cast<float>(out_h) : 1.f;
+  d.sw = out_w ? static_cast<float>(in_w) / static_cast<float>(out_w) : 1.f;
+  return d;
+}
+__device__ __forceinline__ Lerp lerp_of(int dst, int in, float scale) {
   float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
   src = src < 0.f ? 0.f : src;
   Lerp r;
@@ -47,12 +76,15 @@ __device__ __forceinline__ Lerp lerp_of(int dst, int in, int out) {
 }
 
 // bilinear sample of 8 channels of a low-res view at hi-res pixel (h, w) of an (H, W) grid
+// (32-bit element offsets inside one image: the launchers reject low-res images of 2^31 elements or more)
 __device__ __forceinline__ F8 sample8(const View& b, int n, const Lerp& lh, const Lerp& lw, int c) {
-  const bf16* base = b.ptr + static_cast<long>(n) * b.H * b.W * b.ps + c;
-  const F8 v00 = ld8(base + (static_cast<long>(lh.i0) * b.W + lw.i0) * b.ps);
-  const F8 v01 = ld8(base + (static_cast<long>(lh.i0) * b.W + lw.i1) * b.ps);
-  const F8 v10 = ld8(base + (static_cast<long>(lh.i1) * b.W + lw.i0) * b.ps);
-  const F8 v11 = ld8(base + (static_cast<long>(lh.i1) * b.W + lw.i1) * b.ps);
+  const int ps = static_cast<int>(b.ps);
+  const bf16* base = b.ptr + static_cast<long>(n) * (b.H * b.W * ps) + c;
+  const int r0 = lh.i0 * b.W, r1 = lh.i1 * b.W;
+  const F8 v00 = ld8(base + (r0 + lw.i0) * ps);
+  const F8 v01 = ld8(base + (r0 + lw.i1) * ps);
+  const F8 v10 = ld8(base + (r1 + lw.i0) * ps);
+  const F8 v11 = ld8(base + (r1 + lw.i1) * ps);
   const float w00 = (1.f - lh.l) * (1.f - lw.l), w01 = (1.f - lh.l) * lw.l;
   const float w10 = lh.l * (1.f - lw.l), w11 = lh.l * lw.l;
   F8 r;
@@ -65,13 +97,13 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 // thread index -> (channel group, w, h, n, pixel) with 32-bit unsigned divisions (three instead of the six 64-bit div/mod
 // of the naive form: these elementwise kernels are instruction-issue bound, and 64-bit division was a third of their
 // instructions).  Launchers reject tensors with >= 2^32 (pixel, channel-group) items.
-__device__ __forceinline__ void decode_idx(unsigned idx, unsigned groups, unsigned W, unsigned H, int& cg, int& w, int& h,
-                                           int& n, unsigned& pix) {
-  pix = idx / groups;
+__device__ __forceinline__ void decode_idx(unsigned idx, const Dec& d, unsigned groups, unsigned W, unsigned H, int& cg,
+                                           int& w, int& h, int& n, unsigned& pix) {
+  pix = fdiv(idx, d.g);
   cg = static_cast<int>(idx - pix * groups);
-  const unsigned t1 = pix / W;
+  const unsigned t1 = fdiv(pix, d.w);
   w = static_cast<int>(pix - t1 * W);
-  const unsigned nn = t1 / H;
+  const unsigned nn = fdiv(t1, d.h);
   h = static_cast<int>(t1 - nn * H);
   n = static_cast<int>(nn);
 }
@@ -91,24 +123,25 @@ struct StripIdx {
 };
 // item index -> (channel group, w, strip, n); invalid tail threads are redirected to the last item (they still take part
 // in warp shuffles) and must not store
-__device__ __forceinline__ StripIdx strip_decode(unsigned gid, unsigned groups, unsigned W, unsigned H, unsigned N) {
+// (d.h divides by the number of strips per image)
+__device__ __forceinline__ StripIdx strip_decode(unsigned gid, const Dec& d, unsigned groups, unsigned W, unsigned H, unsigned N) {
   const unsigned strips = (H + kStrip - 1) / kStrip;
   const unsigned total = N * strips * W * groups;
   StripIdx r;
   r.valid = gid < total;
   if (!r.valid) gid = total - groups + gid % groups;
-  const unsigned t0 = gid / groups;
+  const unsigned t0 = fdiv(gid, d.g);
   r.cg = static_cast<int>(gid - t0 * groups);
-  const unsigned t1 = t0 / W;
+  const unsigned t1 = fdiv(t0, d.w);
   r.w = static_cast<int>(t0 - t1 * W);
-  const unsigned nn = t1 / strips;
+  const unsigned nn = fdiv(t1, d.h);
   r.h0 = static_cast<int>(t1 - nn * strips) * kStrip;
   r.n = static_cast<int>(nn);
   return r;
 }
 // horizontally interpolated 8 channels of low-res row `row` (o0 / o1: element offsets of the two source columns)
 __device__ __forceinline__ F8 hsample8(const bf16* img, int row, int Wl, long ps, long o0, long o1, float l) {
-  const bf16* r = img + static_cast<long>(row) * Wl * ps;
+  const bf16* r = img + row * (Wl * static_cast<int>(ps));
   const F8 a = ld8(r + o0), b = ld8(r + o1);
   F8 o;
 #pragma unroll
@@ -197,10 +230,10 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
 
 // --------------------------------------------------------------------------- PagFM fuse
 template <int LP>  // lanes per pixel = C/8
-__global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View out, int relu) {
-  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, LP, x.W, x.H, x.N);
+__global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View out, int relu, Dec dec) {
+  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, dec, LP, x.W, x.H, x.N);
   const int C = x.C, cg = ix.cg;
-  const Lerp lw = lerp_of(ix.w, low.W, x.W);
+  const Lerp lw = lerp_of(ix.w, low.W, dec.sw);
   const bf16* limg = low.ptr + static_cast<long>(ix.n) * low.H * low.W * low.ps;
   const long o0 = static_cast<long>(lw.i0) * low.ps, o1 = static_cast<long>(lw.i1) * low.ps;
   // one low-res row, horizontally interpolated: y (channels cg*8..), z (C + cg*8..) and the scalar t (channel 2C)
@@ -223,7 +256,7 @@ __global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View ou
 #pragma unroll
   for (int r = 0; r < kStrip; ++r) {
     const int h = min(ix.h0 + r, x.H - 1);
-    const Lerp lh = lerp_of(h, low.H, x.H);
+    const Lerp lh = lerp_of(h, low.H, dec.sh);
     if (lh.i0 != r0) {
       if (lh.i0 == r1) { y0 = y1; z0 = z1; t0 = t1; }
       else hrow(lh.i0, y0, z0, t0);
@@ -258,21 +291,21 @@ __global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View ou
 
 // --------------------------------------------------------------------------- upadd / affine
 __global__ void __launch_bounds__(256) upadd_kernel(View a, View b, View r, View out, const float* __restrict__ s,
-                                                    const float* __restrict__ t, int relu) {
+                                                    const float* __restrict__ t, int relu, Dec dec) {
   const int groups = out.C >> 3;
   const unsigned total = static_cast<unsigned>(out.N) * out.H * out.W * groups;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   int cg, w, h, n;
   unsigned pixu;
-  decode_idx(idx, groups, out.W, out.H, cg, w, h, n, pixu);
+  decode_idx(idx, dec, groups, out.W, out.H, cg, w, h, n, pixu);
   const long pix = pixu;
   F8 v;
 #pragma unroll
   for (int e = 0; e < 8; ++e) v.v[e] = 0.f;
   if (a.ptr) v = ld8(a.ptr + pix * a.ps + cg * 8);
   if (b.ptr) {
-    const Lerp lh = lerp_of(h, b.H, out.H), lw = lerp_of(w, b.W, out.W);
+    const Lerp lh = lerp_of(h, b.H, dec.sh), lw = lerp_of(w, b.W, dec.sw);
     const F8 u = sample8(b, n, lh, lw, cg * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) v.v[e] += u.v[e];
@@ -319,11 +352,11 @@ struct RowPair {
   }
 };
 __global__ void __launch_bounds__(256) upadd_strip_kernel(View a, View b, View r, View out, const float* __restrict__ s,
-                                                          const float* __restrict__ t, int relu) {
-  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, out.C >> 3, out.W, out.H, out.N);
+                                                          const float* __restrict__ t, int relu, Dec dec) {
+  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, dec, out.C >> 3, out.W, out.H, out.N);
   if (!ix.valid) return;
   const int cg = ix.cg;
-  const Lerp lw = lerp_of(ix.w, b.W, out.W);
+  const Lerp lw = lerp_of(ix.w, b.W, dec.sw);
   const bf16* limg = b.ptr + static_cast<long>(ix.n) * b.H * b.W * b.ps;
   const long o0 = static_cast<long>(lw.i0) * b.ps + cg * 8, o1 = static_cast<long>(lw.i1) * b.ps + cg * 8;
   const long pixn = static_cast<long>(ix.n) * out.H * out.W + ix.w;
@@ -347,7 +380,7 @@ __global__ void __launch_bounds__(256) upadd_strip_kernel(View a, View b, View r
   for (int k = 0; k < kStrip; ++k) {
     if (k < rows) {
       const int h = ix.h0 + k;
-      const Lerp lh = lerp_of(h, b.H, out.H);
+      const Lerp lh = lerp_of(h, b.H, dec.sh);
       rp.advance(lh, [&](int row) { return hsample8(limg, row, b.W, b.ps, o0, o1, lw.l); });
       F8 v = vlerp8(rp.a, rp.b, lh.l);
       if (a.ptr) {
@@ -433,11 +466,11 @@ __global__ void __launch_bounds__(256) pool_affine_kernel(View x, View out, int 
 // (strip walk: the x8 upsample of the PPM output costs 4 row gathers per 8 pixels instead of 32 corner gathers)
 template <bool kBag>
 __global__ void __launch_bounds__(256) bag_strip_kernel(View p, View il, View d, View out, const float* __restrict__ s,
-                                                        const float* __restrict__ t) {
-  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, p.C >> 3, p.W, p.H, p.N);
+                                                        const float* __restrict__ t, Dec dec) {
+  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, dec, p.C >> 3, p.W, p.H, p.N);
   if (!ix.valid) return;
   const int cg = ix.cg;
-  const Lerp lw = lerp_of(ix.w, il.W, p.W);
+  const Lerp lw = lerp_of(ix.w, il.W, dec.sw);
   const bf16* limg = il.ptr + static_cast<long>(ix.n) * il.H * il.W * il.ps;
   const long o0 = static_cast<long>(lw.i0) * il.ps + cg * 8, o1 = static_cast<long>(lw.i1) * il.ps + cg * 8;
   const long pixn = static_cast<long>(ix.n) * p.H * p.W + ix.w;
@@ -461,7 +494,7 @@ __global__ void __launch_bounds__(256) bag_strip_kernel(View p, View il, View d,
   for (int k = 0; k < kStrip; ++k) {
     if (k < rows) {
       const int h = ix.h0 + k;
-      const Lerp lh = lerp_of(h, il.H, p.H);
+      const Lerp lh = lerp_of(h, il.H, dec.sh);
       rp.advance(lh, [&](int row) { return hsample8(limg, row, il.W, il.ps, o0, o1, lw.l); });
       const F8 iv = vlerp8(rp.a, rp.b, lh.l);
       const F8 pv = cvt8(pr[k]), dv = cvt8(dr[k]);
@@ -492,16 +525,16 @@ __global__ void __launch_bounds__(256) bag_strip_kernel(View p, View il, View d,
 
 // ---- flat (one thread per pixel x 8 channels) forms, the default for PagFM / Light_Bag: measured faster than their strip forms, which need 152 registers (PIDNET_ELTWISE_STRIP=1 selects those)
 template <int LP>  // lanes per pixel = C/8
-__global__ void __launch_bounds__(256) pag_fuse_flat_kernel(View x, View low, View out, int relu) {
+__global__ void __launch_bounds__(256) pag_fuse_flat_kernel(View x, View low, View out, int relu, Dec dec) {
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned npix = static_cast<unsigned>(x.N) * x.H * x.W;
   const bool valid = gid / LP < npix;
   int cg, w, h, n;
   unsigned pixu;
-  decode_idx(valid ? gid : (npix - 1) * LP + gid % LP, LP, x.W, x.H, cg, w, h, n, pixu);   // LP is a compile-time power of two
+  decode_idx(valid ? gid : (npix - 1) * LP + gid % LP, dec, LP, x.W, x.H, cg, w, h, n, pixu);   // LP is a compile-time power of two
   const long pix = pixu;
   const int C = x.C;
-  const Lerp lh = lerp_of(h, low.H, x.H), lw = lerp_of(w, low.W, x.W);
+  const Lerp lh = lerp_of(h, low.H, dec.sh), lw = lerp_of(w, low.W, dec.sw);
   const F8 xv = ld8(x.ptr + pix * x.ps + cg * 8);
   const F8 yv = sample8(low, n, lh, lw, cg * 8);
   const F8 zv = sample8(low, n, lh, lw, C + cg * 8);
@@ -527,16 +560,16 @@ __global__ void __launch_bounds__(256) pag_fuse_flat_kernel(View x, View low, Vi
   if (valid) st8(out.ptr + pix * out.ps + cg * 8, o);
 }
 
-__global__ void __launch_bounds__(256) lightbag_uv_flat_kernel(View p, View il, View d, View out) {
+__global__ void __launch_bounds__(256) lightbag_uv_flat_kernel(View p, View il, View d, View out, Dec dec) {
   const int groups = p.C >> 3;
   const long total = static_cast<long>(p.N) * p.H * p.W * groups;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   int cg, w, h, n;
   unsigned pixu;
-  decode_idx(idx, groups, p.W, p.H, cg, w, h, n, pixu);
+  decode_idx(idx, dec, groups, p.W, p.H, cg, w, h, n, pixu);
   const long pix = pixu;
-  const Lerp lh = lerp_of(h, il.H, p.H), lw = lerp_of(w, il.W, p.W);
+  const Lerp lh = lerp_of(h, il.H, dec.sh), lw = lerp_of(w, il.W, dec.sw);
   const F8 iv = sample8(il, n, lh, lw, cg * 8);
   const F8 pv = ld8(p.ptr + pix * p.ps + cg * 8);
   const F8 dv = ld8(d.ptr + pix * d.ps + cg * 8);
@@ -612,15 +645,18 @@ cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t s
   const int LP = x.C / 8;
   if (static_cast<long>(x.N) * x.H * x.W * LP + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic
   static const bool flat = getenv("PIDNET_ELTWISE_STRIP") == nullptr;
+  if (static_cast<long>(low.H) * low.W * low.ps >= (1L << 31)) return cudaErrorInvalidValue;   // 32-bit offsets inside an image
+  const Dec dflat = make_dec(LP, x.W, x.H, low.H, x.H, low.W, x.W);
+  const Dec dstrip = make_dec(LP, x.W, (x.H + kStrip - 1) / kStrip, low.H, x.H, low.W, x.W);
   if (flat) {
     const unsigned nbf = blocks_for(static_cast<long>(x.N) * x.H * x.W * LP, 256);
     switch (LP) {
-      case 1: pag_fuse_flat_kernel<1><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
-      case 2: pag_fuse_flat_kernel<2><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
-      case 4: pag_fuse_flat_kernel<4><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
-      case 8: pag_fuse_flat_kernel<8><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
-      case 16: pag_fuse_flat_kernel<16><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
-      case 32: pag_fuse_flat_kernel<32><<<nbf, 256, 0, st>>>(x, low, out, relu); break;
+      case 1: pag_fuse_flat_kernel<1><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
+      case 2: pag_fuse_flat_kernel<2><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
+      case 4: pag_fuse_flat_kernel<4><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
+      case 8: pag_fuse_flat_kernel<8><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
+      case 16: pag_fuse_flat_kernel<16><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
+      case 32: pag_fuse_flat_kernel<32><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
       default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -628,12 +664,12 @@ cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t s
   const long total = static_cast<long>(x.N) * ((x.H + kStrip - 1) / kStrip) * x.W * LP;   // one thread per strip
   const unsigned nb = blocks_for(total, 256);
   switch (LP) {
-    case 1: pag_fuse_kernel<1><<<nb, 256, 0, st>>>(x, low, out, relu); break;
-    case 2: pag_fuse_kernel<2><<<nb, 256, 0, st>>>(x, low, out, relu); break;
-    case 4: pag_fuse_kernel<4><<<nb, 256, 0, st>>>(x, low, out, relu); break;
-    case 8: pag_fuse_kernel<8><<<nb, 256, 0, st>>>(x, low, out, relu); break;
-    case 16: pag_fuse_kernel<16><<<nb, 256, 0, st>>>(x, low, out, relu); break;
-    case 32: pag_fuse_kernel<32><<<nb, 256, 0, st>>>(x, low, out, relu); break;
+    case 1: pag_fuse_kernel<1><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
+    case 2: pag_fuse_kernel<2><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
+    case 4: pag_fuse_kernel<4><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
+    case 8: pag_fuse_kernel<8><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
+    case 16: pag_fuse_kernel<16><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
+    case 32: pag_fuse_kernel<32><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -648,9 +684,12 @@ cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, c
   if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
   if (b.ptr) {
     const long strips = static_cast<long>(out.N) * ((out.H + kStrip - 1) / kStrip) * out.W * (out.C / 8);
-    upadd_strip_kernel<<<blocks_for(strips, 256), 256, 0, st>>>(a, b, r, out, s, t, relu);
+    if (static_cast<long>(b.H) * b.W * b.ps >= (1L << 31)) return cudaErrorInvalidValue;   // 32-bit offsets inside an image
+    upadd_strip_kernel<<<blocks_for(strips, 256), 256, 0, st>>>(
+        a, b, r, out, s, t, relu, make_dec(out.C / 8, out.W, (out.H + kStrip - 1) / kStrip, b.H, out.H, b.W, out.W));
   } else {
-    upadd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, b, r, out, s, t, relu);
+    upadd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, b, r, out, s, t, relu,
+                                                          make_dec(out.C / 8, out.W, out.H, 0, 0, 0, 0));
   }
   return cudaGetLastError();
 }
@@ -671,11 +710,13 @@ cudaError_t lightbag_uv_launch(View p, View i_low, View d, View out, cudaStream_
   if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
   static const bool flat = getenv("PIDNET_ELTWISE_STRIP") == nullptr;
   if (flat) {
-    lightbag_uv_flat_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out);
+    lightbag_uv_flat_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out,
+                                                                     make_dec(p.C / 8, p.W, p.H, i_low.H, p.H, i_low.W, p.W));
     return cudaGetLastError();
   }
   const long strips = static_cast<long>(p.N) * ((p.H + kStrip - 1) / kStrip) * p.W * (p.C / 8);
-  bag_strip_kernel<false><<<blocks_for(strips, 256), 256, 0, st>>>(p, i_low, d, out, nullptr, nullptr);
+  bag_strip_kernel<false><<<blocks_for(strips, 256), 256, 0, st>>>(
+      p, i_low, d, out, nullptr, nullptr, make_dec(p.C / 8, p.W, (p.H + kStrip - 1) / kStrip, i_low.H, p.H, i_low.W, p.W));
   return cudaGetLastError();
 }
 
@@ -683,7 +724,8 @@ cudaError_t bag_blend_launch(View p, View i_low, View d, View out, const float* 
   const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
   if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
   const long strips = static_cast<long>(p.N) * ((p.H + kStrip - 1) / kStrip) * p.W * (p.C / 8);
-  bag_strip_kernel<true><<<blocks_for(strips, 256), 256, 0, st>>>(p, i_low, d, out, s, t);
+  bag_strip_kernel<true><<<blocks_for(strips, 256), 256, 0, st>>>(
+      p, i_low, d, out, s, t, make_dec(p.C / 8, p.W, (p.H + kStrip - 1) / kStrip, i_low.H, p.H, i_low.W, p.W));
   return cudaGetLastError();
 }
 
