@@ -94,7 +94,11 @@ int pidnet_op_info(pidnet_engine* h, int i, char* name, int name_cap, char* kern
 
 /* Options (set before pidnet_plan): "conv_impl" = 0 tcgen05 (default) | 1 SIMT restatement (debug
  * cross-check); "lanes" = 1 | 3 concurrent branch streams (default 3); "use_ws" = 1 (default) | 0: use
- * the weight-stationary halo-patch kernel for 3x3 stride-1 convs. */
+ * the weight-stationary halo-patch kernel for 3x3 stride-1 convs; "use_pair" = 1 (default: CTA pairs /
+ * tcgen05 cta_group::2 for 3x3 layers with Cin >= 128) | 0 | 2 (wherever the pair instance exists);
+ * "ws_stages" = 3 (default) | 2 staging buffers of the weight-stationary kernels; "use_stem2" = 1
+ * (default: conv1.0 -> conv1.3 fused in one kernel) | 0.  The same switches can be set for a whole
+ * process with PIDNET_WS_PAIR / PIDNET_WS_STAGES / PIDNET_STEM2 (A/B measurements). */
 int pidnet_set_option(pidnet_engine* h, const char* name, int value);
 
 /* Debug: copy a named intermediate (e.g. "layer3", "pag3", "spp"; see engine.cu) to the host as fp32
@@ -106,8 +110,9 @@ int pidnet_debug_tensor(pidnet_engine* h, const char* name, float* host_out, int
 /* nn.Conv2d (+folded affine, +residual, +ReLU) on one NHWC bf16 tensor.  w: host fp32 [Cout][Cin/groups][k][k]
  * (already BN-folded), bias: host fp32 [Cout] or NULL, res: device NHWC bf16 [N,Ho,Wo,Cout] or NULL.
  * out_nhwc (bf16) or out_nchw_f32 (exactly one non-NULL).  k in {1,3}, pad = k/2, stride in {1,2}.
- * impl: 0 tcgen05 (weight-stationary halo kernel where it applies, else the generic one), 1 SIMT restatement,
- * 2 generic tcgen05 kernel only. */
+ * impl: 0 tcgen05 (weight-stationary halo kernel -- CTA pairs for Cin >= 128 -- where it applies, else the generic one),
+ * 1 SIMT restatement, 2 generic tcgen05 kernel only, 3 weight-stationary kernels without CTA pairs and with two staging
+ * buffers, 4 without CTA pairs. */
 int pidnet_op_conv2d(void* stream, const void* x_nhwc, int N, int H, int W, int Cin, const float* w, const float* bias,
                      int Cout, int k, int stride, int groups, const void* res, int relu, void* out_nhwc,
                      float* out_nchw_f32, int impl);

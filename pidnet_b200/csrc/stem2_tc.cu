@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kS2Threads, C == 32 ? 2 : 1) stem2_tc_kernel(c
     // ---- P3: epilogue A -> parity planes (warp w reads TMEM lane quarter w & 3)
     {
       const int quarter = warp & 3;
-      const int stepq = quarter == 0 ? 3 : 2;   // quarter 0 is shared by warps 0, 4, 8; the others by two warps
+      const int stepq = (kS2Threads / 32 - quarter + 3) / 4;   // warps sharing this TMEM lane quarter split its five accumulators
       for (int q = warp >> 2; q < 5; q += stepq) {
         const int prow = q * 128 + quarter * 32 + lane;
         const uint32_t t_addr = tmem + q * C + (static_cast<uint32_t>(quarter * 32) << 16);

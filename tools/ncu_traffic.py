@@ -10,9 +10,10 @@ import sys
 
 
 def label(name):
-    m = re.search(r'conv3_ws_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+)>', name)
+    m = re.search(r'conv3_ws_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+)(?:, (?:\(bool\))?(\w+))?>', name)
     if m:
-        return ('conv3_ws' if m.group(3) == '0' else 'conv1_ws') + f'<BN={m.group(1)},CK={m.group(2)}>'
+        pair = m.group(4) in ('1', 'true')
+        return ('conv1_ws' if m.group(3) != '0' else ('conv3_ws_pair' if pair else 'conv3_ws')) + f'<BN={m.group(1)},CK={m.group(2)}>'
     m = re.search(r'conv_tc_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+)>', name)
     if m:
         return f'conv_tc<BN={m.group(1)},BK={m.group(2)}>'
