@@ -96,8 +96,9 @@ int pidnet_op_info(pidnet_engine* h, int i, char* name, int name_cap, char* kern
  * cross-check); "lanes" = 1 | 3 concurrent branch streams (default 3); "use_ws" = 1 (default) | 0: use
  * the weight-stationary halo-patch kernel for 3x3 stride-1 convs; "use_pair" = 1 (default: CTA pairs /
  * tcgen05 cta_group::2 for 3x3 layers with Cin >= 128) | 0 | 2 (wherever the pair instance exists);
- * "ws_stages" = 3 (default) | 2 staging buffers of the weight-stationary kernels; "use_stem2" = 1
- * (default: conv1.0 -> conv1.3 fused in one kernel) | 0.  The same switches can be set for a whole
+ * "ws_stages" = 3 (default) | 2 staging buffers of the weight-stationary kernels; "use_stem2" = 2
+ * (default: conv1.0 -> conv1.3 fused in one kernel, warp-specialised pipeline for 32-channel stems) | 1 (lock-step
+ * fused kernel) | 0 (two kernels).  The same switches can be set for a whole
  * process with PIDNET_WS_PAIR / PIDNET_WS_STAGES / PIDNET_STEM2 (A/B measurements). */
 int pidnet_set_option(pidnet_engine* h, const char* name, int value);
 

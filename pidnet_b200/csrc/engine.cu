@@ -80,12 +80,14 @@ static CUtensorMapSwizzle swizzle_for(int bytes) {
     case 128: return CU_TENSOR_MAP_SWIZZLE_128B;
     case 64: return CU_TENSOR_MAP_SWIZZLE_64B;
     case 32: return CU_TENSOR_MAP_SWIZZLE_32B;
+    case 0: return CU_TENSOR_MAP_SWIZZLE_NONE;
   }
   fail("bad swizzle span");
 }
 // bf16 tensor of rank `rank` (dims fastest first, strides in BYTES for dims 1..rank-1)
 static CUtensorMap encode_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                              const uint32_t* box, int swizzle_bytes) {
+                              const uint32_t* box, int swizzle_bytes,
+                              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   CUtensorMap m;
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
@@ -101,7 +103,7 @@ static CUtensorMap encode_map(const void* base, int rank, const uint64_t* dims, 
     if (gs[i] % 16 != 0) fail("tensor map: stride not multiple of 16 B");
   }
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) fail("tensor map: base not 16 B aligned");
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = get_encode()(&m, dtype, rank, const_cast<void*>(base), gd, gs, bx, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(swizzle_bytes),
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
@@ -190,7 +192,7 @@ struct Builder {
   bool dry = true;
   int conv_impl = 0;
   int use_ws = 1;   // weight-stationary halo-patch kernel for 3x3 stride-1 convs
-  int use_stem2 = env_int("PIDNET_STEM2", 1);       // fused conv1.0 -> conv1.3 kernel (stem2_tc.cu)
+  int use_stem2 = env_int("PIDNET_STEM2", 2);       // fused conv1.0 -> conv1.3 kernel (stem2_tc.cu): 1 lock-step, 2 pipelined (C = 32)
   int use_pair = env_int("PIDNET_WS_PAIR", 1);      // CTA pairs (tcgen05 cta_group::2) where conv3_ws has the instance
   int ws_stages = env_int("PIDNET_WS_STAGES", 3);   // rotating staging buffers of the weight-stationary kernels (2 or 3)
   int num_sms = 148;
@@ -1099,11 +1101,26 @@ struct Engine {
       const int sms = b.num_sms;
       const double fl = 2.0 * N * H1 * W1 * Pn * 27 + 2.0 * N * H2 * W2 * Pn * Pn * 9;
       b.flops += fl;
-      x.prod = b.add_op("conv1.0+conv1.3", {}, [sp, Pn, sms](cudaStream_t st, const RunArgs& a) mutable {
+      const int pipelined = b.use_stem2 >= 2 ? 1 : 0;
+      const float* mapped_x = nullptr;
+      x.prod = b.add_op("conv1.0+conv1.3", {}, [sp, Pn, sms, pipelined, mapped_x](cudaStream_t st, const RunArgs& a) mutable {
         sp.x = a.x; sp.x_u8 = a.x_u8; sp.lut = a.lut;
-        return stem2_tc_launch(sp, Pn, sms, st);
+        if (pipelined && Pn == 32 && a.x && a.x != mapped_x) {
+          // the pipelined kernel fetches the fp32 NCHW image with TMA: box {36 cols, 67 rows, 3 channels, 1 image}
+          try {
+            uint64_t dims4[4] = {static_cast<uint64_t>(sp.W), static_cast<uint64_t>(sp.H), 3, static_cast<uint64_t>(sp.N)};
+            uint64_t str[3] = {static_cast<uint64_t>(sp.W) * 4, static_cast<uint64_t>(sp.H) * sp.W * 4,
+                               static_cast<uint64_t>(sp.H) * sp.W * 12};
+            uint32_t box4[4] = {36, 67, 3, 1};
+            sp.tmX = encode_map(a.x, 4, dims4, str, box4, 0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+          } catch (const std::exception&) {
+            return cudaErrorMisalignedAddress;
+          }
+          mapped_x = a.x;
+        }
+        return stem2_tc_launch(sp, Pn, sms, pipelined, st);
       });
-      b.label(x.prod, "stem2_tc", 4.0 * N * 3 * H * W + Builder::tbytes(x), fl);
+      b.label(x.prod, pipelined && Pn == 32 ? "stem3_tc" : "stem2_tc", 4.0 * N * 3 * H * W + Builder::tbytes(x), fl);
     } else {
       T x1 = b.new_tensor(N, cdiv(H, 2), cdiv(W, 2), Pn);
       {
@@ -1462,7 +1479,7 @@ int pidnet_set_option(pidnet_engine* h, const char* name, int value) {
     else if (k == "lanes") h->e.lanes = value == 3 ? 3 : 1;
     else if (k == "use_ws") h->e.use_ws = value ? 1 : 0;
     else if (k == "use_pair") h->e.use_pair = value ? 1 : 0;
-    else if (k == "use_stem2") h->e.use_stem2 = value ? 1 : 0;
+    else if (k == "use_stem2") h->e.use_stem2 = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (k == "ws_stages") h->e.ws_stages = value == 2 ? 2 : 3;
     else fail("unknown option '" + k + "'");
     h->e.planned = false;

@@ -42,6 +42,7 @@ cudaError_t stem_tc_launch(const StemParams& p, int Cout, int num_sms, cudaStrea
 // ---- fused stem (stem2_tc.cu): conv1.0+BN+ReLU -> conv1.3+BN+ReLU, the C-channel half-resolution intermediate stays in smem
 struct Stem2Params {
   CUtensorMap tmD;        // conv1.3 output [N,H2,W2,C] bf16 NHWC, box {C, 8, 16, 1}, swizzle = C*2 bytes
+  CUtensorMap tmX;        // pipelined kernel: the fp32 NCHW image as [N,3,H,W], box {36, 67, 3, 1}, no swizzle
   const float* x;         // fp32 NCHW image (or null)
   const uint8_t* x_u8;    // uint8 HWC BGR frames (or null), normalised through `lut` as in StemParams
   const float* lut;
@@ -54,7 +55,7 @@ struct Stem2Params {
   int H2, W2;             // conv1.3 output
   int tiles_w, tiles_h, N;  // 16 x 8 output tiles
 };
-cudaError_t stem2_tc_launch(const Stem2Params& p, int C, int num_sms, cudaStream_t st);
+cudaError_t stem2_tc_launch(const Stem2Params& p, int C, int num_sms, int pipelined, cudaStream_t st);
 // training: fp32 [Cout][3][3][3] master weights -> the pre-swizzled bf16 [Cout][32] tile of the kernel above
 cudaError_t stem_pack_launch(const float* w, uint8_t* w_swz, int Cout, cudaStream_t st);
 

@@ -22,7 +22,7 @@
 namespace pidnet {
 namespace {
 
-constexpr int kS2Threads = 288;                 // 9 warps: 561 im2col rows in two rounds
+constexpr int kS2Threads = 288;                 // 9 warps: 561 im2col rows in two rounds (384 threads measured slower: 0.785 vs 0.72-0.75 ms)
 constexpr int kPosH = 33, kPosW = 17, kPos = kPosH * kPosW;   // conv1.0 positions per tile
 // plane (pj, pi): rows a = 0..16 (pj = 0) / 0..15 (pj = 1), pitch 9 (pi = 0) / 8 (pi = 1) pixels
 constexpr int kPl0 = 0, kPl1 = 17 * 9, kPl2 = kPl1 + 17 * 8, kPl3 = kPl2 + 16 * 9;
@@ -345,6 +345,360 @@ __global__ void __launch_bounds__(kS2Threads, C == 32 ? 2 : 1) stem2_tc_kernel(c
   if (warp == 0) tmem_dealloc<G::kTmemCols>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Pipelined form for C = 32 (one CTA per SM, three tiles in flight).  The lock-step kernel above keeps every warp of a CTA in
+// the same phase, so the SM idles through each MMA round trip and barrier (ncu: 40 % issue activity, 29 % of the samples in
+// barriers).  Here the phases are ROLES of different warps connected by mbarriers, and consecutive tiles occupy consecutive
+// pipeline stages at the same time:
+//   producer warps (12): tile i+2 -- image patch -> smem (16-byte loads issued a tile ahead), im2col -> A1
+//   MMA warp       (1): conv1.0 of tile i+1 (A1 -> acc1[slot]) and conv1.3 of tile i (parity planes -> acc2[slot])
+//   epilogue A     (8): tile i+1 -- acc1[slot] -> ReLU -> parity planes
+//   epilogue B     (4): tile i   -- acc2[slot] -> bias, ReLU -> staging tile -> TMA store
+// A1 and the planes are single buffers (the MMAs that read them are short); the TMEM accumulators are double-buffered
+// (2 x 160 + 2 x 32 = 384 columns).
+constexpr int kS3ProdWarps = 12, kS3Threads = (8 + 4 + 1 + kS3ProdWarps) * 32;   // 608
+constexpr int kS3ProdThreads = kS3ProdWarps * 32;
+constexpr int kS3LdRounds = (kLdItems + kS3ProdThreads - 1) / kS3ProdThreads;
+constexpr int kS3Ring = 3;                                     // fp32 image patches in flight (TMA)
+constexpr int kS3RingTx = 36 * kPatH * 3 * 4;                  // bytes of one box {36, 67, 3} fp32
+constexpr int kS3RingBytes = (kS3RingTx + 1023) / 1024 * 1024;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+template <bool U8>
+__global__ void __launch_bounds__(kS3Threads, 1) stem3_tc_kernel(const __grid_constant__ Stem2Params p) {
+  constexpr int C = 32, kRowB = 64;
+  using G = S2Geom<32>;
+  constexpr int kOffPatch = G::kOffPlanes + G::kPlanesBytes;                 // own buffer (the planes are live across tiles here)
+  constexpr int kPatchBytes = (3 * kPatH * 36 * 2 + 1023) / 1024 * 1024;
+  constexpr int kOffStage = kOffPatch + kPatchBytes;                         // two staging tiles
+  constexpr int kOffW2 = kOffStage + 2 * G::kStageBytes;
+  constexpr int kOffW1 = kOffW2 + G::kW2Bytes;
+  constexpr int kOffMisc = kOffW1 + G::kW1Bytes;
+  constexpr int kOffRing = kOffMisc + 1024;                                  // fp32 image patches as TMA delivers them
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* a1_gen = gen;
+  float* bias2_s = reinterpret_cast<float*>(gen + kOffMisc);
+  const uint32_t bars = base + kOffMisc + 512;
+  auto ring_full = [&](int s) { return bars + 104u + 8u * s; };
+  auto ring_empty = [&](int s) { return bars + 128u + 8u * s; };
+  const uint32_t a1_full = bars, a1_free = bars + 8, pl_full = bars + 16, pl_free = bars + 24;
+  auto acc1_full = [&](int s) { return bars + 32u + 8u * s; };
+  auto acc1_free = [&](int s) { return bars + 48u + 8u * s; };
+  auto acc2_full = [&](int s) { return bars + 64u + 8u * s; };
+  auto acc2_free = [&](int s) { return bars + 80u + 8u * s; };
+  const uint32_t slot = bars + 96;
+  volatile uint32_t* slot_gen = reinterpret_cast<volatile uint32_t*>(gen + kOffMisc + 512 + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < G::kW2Bytes / 16; i += kS3Threads)
+    reinterpret_cast<uint4*>(gen + kOffW2)[i] = reinterpret_cast<const uint4*>(p.w2_swz)[i];
+  for (int i = threadIdx.x; i < G::kW1Bytes / 16; i += kS3Threads)
+    reinterpret_cast<uint4*>(gen + kOffW1)[i] = reinterpret_cast<const uint4*>(p.w1_swz)[i];
+  if (threadIdx.x < C) bias2_s[threadIdx.x] = p.bias2[threadIdx.x];
+  if (threadIdx.x == 0) {
+    mbar_init(a1_full, kS3ProdWarps);
+    mbar_init(a1_free, 1);
+    mbar_init(pl_full, 8);
+    mbar_init(pl_free, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc1_full(s), 1);
+      mbar_init(acc1_free(s), 8);
+      mbar_init(acc2_full(s), 1);
+      mbar_init(acc2_free(s), 4);
+    }
+    for (int s = 0; s < kS3Ring; ++s) {
+      mbar_init(ring_full(s), 1);
+      mbar_init(ring_empty(s), kS3ProdWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc<512>(slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_gen;
+  const long plane_in = static_cast<long>(p.H) * p.W;
+  const int per_img = p.tiles_w * p.tiles_h;
+  const long tiles = static_cast<long>(p.N) * per_img;
+  const int n_it = static_cast<long>(blockIdx.x) < tiles ? static_cast<int>((tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  auto tile_of = [&](int i) { return static_cast<long>(blockIdx.x) + static_cast<long>(i) * gridDim.x; };
+  auto tile_origin = [&](long t, int& n, int& oh0, int& ow0) {
+    n = static_cast<int>(t / per_img);
+    const int rem_t = static_cast<int>(t - static_cast<long>(n) * per_img);
+    const int th = rem_t / p.tiles_w;
+    oh0 = th * 16; ow0 = (rem_t - th * p.tiles_w) * 8;
+  };
+
+  if (warp >= 13) {
+    // ============================== producers: patch -> smem, im2col -> A1 ==============================
+    const int ptid = threadIdx.x - 13 * 32;
+    __nv_bfloat16* patch_gen = reinterpret_cast<__nv_bfloat16*>(gen + kOffPatch);
+    // fp32 images: ONE TMA box load per tile ({36 columns, 67 rows, 3 channels} of the NCHW image, zero-filled outside
+    // == the conv padding) into a ring of kS3Ring fp32 patches, issued kS3Ring - 1 tiles ahead: the lock-step kernel and
+    // a register prefetch keep one 29 KB tile of loads in flight per SM, which caps it near 1.5 TB/s.
+    auto issue_tma = [&](int i) {
+      int tn, oh0, ow0;
+      tile_origin(tile_of(i), tn, oh0, ow0);
+      const int sl = i % kS3Ring;
+      mbar_arrive_expect_tx(ring_full(sl), kS3RingTx);
+      tma_load_4d(base + kOffRing + sl * kS3RingBytes, &p.tmX, ring_full(sl), 4 * ow0 - 4, 4 * oh0 - 3, 0, tn);
+    };
+    if (!U8 && ptid == 0) {
+      tma_prefetch_desc(&p.tmX);
+      for (int i = 0; i < kS3Ring - 1 && i < n_it; ++i) issue_tma(i);
+    }
+    for (int i = 0; i < n_it; ++i) {
+      int n, oh0, ow0;
+      tile_origin(tile_of(i), n, oh0, ow0);
+      const int y0 = 2 * oh0 - 1, x0 = 2 * ow0 - 1;
+      // P0: patch -> smem (bf16)
+      if (U8) {
+        const uint8_t* xn = p.x_u8 + static_cast<long>(n) * 3 * plane_in;
+        for (int idx = ptid; idx < kPatH * 36; idx += kS3ProdThreads) {
+          const int row = idx / 36, col = idx - row * 36;
+          const int ih = 4 * oh0 - 3 + row, iw = 4 * ow0 - 4 + col;
+          const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+          const uint8_t* px = xn + (static_cast<long>(ok ? ih : 0) * p.W + (ok ? iw : 0)) * 3;
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) {   // model channel ci (RGB) = byte 2 - ci of the BGR pixel
+            const float f = ok ? __ldg(p.lut + ci * 256 + __ldg(px + (2 - ci))) : 0.f;
+            patch_gen[(ci * kPatH + row) * 36 + col] = __float2bfloat16_rn(f);
+          }
+        }
+      } else {
+        const int nx = i + kS3Ring - 1;   // refill the slot tile i-1 has just released
+        if (ptid == 0 && nx < n_it) {
+          if (nx >= kS3Ring) mbar_wait(ring_empty(nx % kS3Ring), static_cast<uint32_t>(nx / kS3Ring - 1) & 1);
+          issue_tma(nx);
+        }
+        const int sl = i % kS3Ring;
+        mbar_wait(ring_full(sl), static_cast<uint32_t>(i / kS3Ring) & 1);
+        const float4* src = reinterpret_cast<const float4*>(gen + kOffRing + sl * kS3RingBytes);
+#pragma unroll
+        for (int k = 0; k < kS3LdRounds; ++k) {
+          const int idx = ptid + k * kS3ProdThreads;
+          if (k < kS3LdRounds - 1 || idx < kLdItems) {
+            const float4 v = src[idx];
+            uint2 o;
+            o.x = pk2(v.x, v.y); o.y = pk2(v.z, v.w);
+            *reinterpret_cast<uint2*>(patch_gen + idx * 4) = o;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ring_empty(sl));
+      }
+      named_bar_sync(2, kS3ProdThreads);
+      if (i >= 1) mbar_wait(a1_free, static_cast<uint32_t>(i - 1) & 1);   // conv1.0 of the previous tile has read A1
+      // P1: im2col (same row order / K order as the lock-step kernel)
+      for (int idx = ptid; idx < kPos; idx += kS3ProdThreads) {
+        const int j = idx / kPosW, ii = idx - j * kPosW;
+        const int pi = ii & 1, pj = j & 1;
+        const int prow = (pj ? (pi ? kPl3 : kPl2) : (pi ? kPl1 : kPl0)) + (j >> 1) * (pi ? 8 : 9) + (ii >> 1);
+        const int swz = (prow >> 1) & 3;
+        const int y = y0 + j, x = x0 + ii;
+        if (y < 0 || y >= p.H1 || x < 0 || x >= p.W1) {
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(a1_gen + prow * 64 + (ch << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          continue;
+        }
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(patch_gen) + (2 * j) * 18 + ii;
+        uint32_t wa[9], w[16];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            wa[ci * 3 + r] = pw[(ci * kPatH + r) * 18];
+            w[ci * 3 + r] = pw[(ci * kPatH + r) * 18 + 1];
+          }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) w[9 + m] = __byte_perm(wa[2 * m], wa[2 * m + 1], 0x7632);
+        w[13] = (wa[8] >> 16) | 0x3F800000u;
+        w[14] = 0x00003F80u;
+        w[15] = 0u;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          *reinterpret_cast<uint4*>(a1_gen + prow * 64 + ((ch ^ swz) << 4)) = make_uint4(w[ch * 4], w[ch * 4 + 1], w[ch * 4 + 2], w[ch * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a1_full);
+      named_bar_sync(2, kS3ProdThreads);   // every producer is done reading the patch before the next tile overwrites it
+    }
+  } else if (warp == 12) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc = make_idesc_bf16(128, C);
+    constexpr uint64_t kLayout = 4ull;   // SWIZZLE_64B
+    // The warp serves two independent queues -- conv1.0 of tile n1 (needs A1 and a free acc1 slot) and conv1.3 of tile n2
+    // (needs the planes of an already-converted tile and a free acc2 slot) -- and issues whichever is ready, the older
+    // tile first: a fixed order would hold conv1.3 of tile i-1 back until the producers have finished tile i.
+    int n1 = 0, n2 = 0;
+    uint32_t spins = 0;
+    while (n2 < n_it) {
+      bool did = false;
+      if (n2 < n1) {
+        const int j = n2, sl = j & 1;
+        bool ok = mbar_try_wait(pl_full, static_cast<uint32_t>(j) & 1);
+        if (ok && j >= 2) ok = mbar_try_wait(acc2_free(sl), static_cast<uint32_t>((j >> 1) - 1) & 1);
+        if (__all_sync(0xffffffffu, ok)) {
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t acc2 = tmem + 320 + sl * C;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int r = tap / 3, sx = tap % 3;
+              const int pl = (r & 1) * 2 + (sx & 1);
+              const int pitch = (sx & 1) ? 8 : 9;
+              const int ploff = pl == 0 ? G::kPlOff0 : (pl == 1 ? G::kPlOff1 : (pl == 2 ? G::kPlOff2 : G::kPlOff3));
+              const uint32_t a_start = base + G::kOffPlanes + ploff + ((r == 2 ? pitch : 0) + (sx == 2 ? 1 : 0)) * kRowB;
+              const uint64_t ad = static_cast<uint64_t>((a_start & 0x3FFFF) >> 4) | (1ull << 16) |
+                                  (static_cast<uint64_t>((pitch * kRowB) >> 4) << 32) | (1ull << 46) | (kLayout << 61);
+              const uint64_t bd = make_kmajor_desc(base + kOffW2 + tap * C * kRowB, kRowB);
+#pragma unroll
+              for (int k = 0; k < C / 16; ++k) umma_bf16(acc2, ad + 2 * k, bd + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(pl_free);
+            umma_commit(acc2_full(sl));
+          }
+          __syncwarp();
+          ++n2;
+          did = true;
+        }
+      }
+      if (!did && n1 < n_it) {
+        const int i = n1, sl = i & 1;
+        bool ok = mbar_try_wait(a1_full, static_cast<uint32_t>(i) & 1);
+        if (ok && i >= 2) ok = mbar_try_wait(acc1_free(sl), static_cast<uint32_t>((i >> 1) - 1) & 1);
+        if (__all_sync(0xffffffffu, ok)) {
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t bd = make_kmajor_desc(base + kOffW1, 64);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+              const uint64_t ad = make_kmajor_desc(base + q * 8192, 64);
+              umma_bf16(tmem + sl * 160 + q * C, ad, bd, idesc, 0u);
+              umma_bf16(tmem + sl * 160 + q * C, ad + 2, bd + 2, idesc, 1u);
+            }
+            umma_commit(a1_free);
+            umma_commit(acc1_full(sl));
+          }
+          __syncwarp();
+          ++n1;
+          did = true;
+        }
+      }
+      if (did) {
+        spins = 0;
+      } else if (++spins > (1u << 26)) {
+        if (lane == 0) printf("pidnet_b200: stem3 MMA scheduler timed out (block %d n1 %d n2 %d of %d)\n", blockIdx.x, n1, n2, n_it);
+        __trap();
+      }
+    }
+  } else if (warp < 8) {
+    // ============================== epilogue A: acc1 -> ReLU -> parity planes ==============================
+    const int quarter = warp & 3;
+    for (int i = 0; i < n_it; ++i) {
+      const int s = i & 1;
+      mbar_wait(acc1_full(s), static_cast<uint32_t>(i >> 1) & 1);
+      if (i >= 1) mbar_wait(pl_free, static_cast<uint32_t>(i - 1) & 1);   // conv1.3 of the previous tile has read the planes
+      tc_fence_after();
+      for (int q = warp >> 2; q < 5; q += 2) {
+        const int prow = q * 128 + quarter * 32 + lane;
+        const uint32_t t_addr = tmem + s * 160 + q * C + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int adj = prow >= kPl3 ? G::kPlOff3 - kPl3 * kRowB
+                                     : (prow >= kPl2 ? G::kPlOff2 - kPl2 * kRowB : (prow >= kPl1 ? G::kPlOff1 - kPl1 * kRowB : G::kPlOff0));
+        const uint32_t roff = static_cast<uint32_t>(G::kOffPlanes + adj + prow * kRowB);
+        const uint32_t swz = (roff >> 7) & 3u;
+        uint32_t acc[32];
+        tmem_ld32(t_addr, acc);
+        tmem_ld_wait();
+        if (prow < kPos) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t* av = acc + jj * 8;
+            uint4 o;
+            o.x = pk2_relu(__uint_as_float(av[0]), __uint_as_float(av[1]));
+            o.y = pk2_relu(__uint_as_float(av[2]), __uint_as_float(av[3]));
+            o.z = pk2_relu(__uint_as_float(av[4]), __uint_as_float(av[5]));
+            o.w = pk2_relu(__uint_as_float(av[6]), __uint_as_float(av[7]));
+            *reinterpret_cast<uint4*>(gen + roff + ((static_cast<uint32_t>(jj) ^ swz) << 4)) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc1_free(s));
+        mbar_arrive(pl_full);
+      }
+    }
+  } else {
+    // ============================== epilogue B (warps 8..11): acc2 -> bias, ReLU -> staging -> TMA store ==============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t swz = (row >> 1) & 3;
+    for (int i = 0; i < n_it; ++i) {
+      const int s = i & 1;
+      int n, oh0, ow0;
+      tile_origin(tile_of(i), n, oh0, ow0);
+      mbar_wait(acc2_full(s), static_cast<uint32_t>(i >> 1) & 1);
+      tc_fence_after();
+      uint32_t acc[32];
+      tmem_ld32(tmem + 320 + s * C + (static_cast<uint32_t>(q * 32) << 16), acc);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_free(s));
+      if (threadIdx.x == 8 * 32) tma_store_wait_read1();   // the store that used this staging buffer (tile i-2) has read it out
+      named_bar_sync(1, 128);
+      uint8_t* st = gen + kOffStage + s * G::kStageBytes;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[jj * 8 + e]) + bias2_s[jj * 8 + e];
+        uint4 o;
+        o.x = pk2_relu(f[0], f[1]); o.y = pk2_relu(f[2], f[3]); o.z = pk2_relu(f[4], f[5]); o.w = pk2_relu(f[6], f[7]);
+        *reinterpret_cast<uint4*>(st + row * kRowB + ((static_cast<uint32_t>(jj) ^ swz) << 4)) = o;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 8 * 32) {
+        tma_store_4d(&p.tmD, base + kOffStage + s * G::kStageBytes, 0, ow0, oh0, n);
+        tma_store_commit();
+      }
+    }
+    if (threadIdx.x == 8 * 32) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc<512>(tmem);
+}
+
+template <bool U8>
+cudaError_t stem3_launch_inst(const Stem2Params& p, int num_sms, cudaStream_t st) {
+  using G = S2Geom<32>;
+  constexpr int kSmem = G::kOffPlanes + G::kPlanesBytes + (3 * kPatH * 36 * 2 + 1023) / 1024 * 1024 + 2 * G::kStageBytes +
+                        G::kW2Bytes + G::kW1Bytes + 1024 + kS3Ring * kS3RingBytes + 1024;
+  static bool init = false;
+  if (!init) {
+    cudaError_t e = cudaFuncSetAttribute(stem3_tc_kernel<U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return e;
+    init = true;
+  }
+  long blocks = static_cast<long>(p.N) * p.tiles_w * p.tiles_h;
+  if (blocks > num_sms) blocks = num_sms;
+  stem3_tc_kernel<U8><<<static_cast<unsigned>(blocks), kS3Threads, kSmem, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <int C, bool U8>
 cudaError_t stem2_launch_inst(const Stem2Params& p, int num_sms, cudaStream_t st) {
   using G = S2Geom<C>;
@@ -363,9 +717,11 @@ cudaError_t stem2_launch_inst(const Stem2Params& p, int num_sms, cudaStream_t st
 
 }  // namespace
 
-cudaError_t stem2_tc_launch(const Stem2Params& p, int C, int num_sms, cudaStream_t st) {
+// pipelined: 1 = the warp-specialised three-tiles-in-flight kernel (C = 32 only), 0 = the lock-step kernel
+cudaError_t stem2_tc_launch(const Stem2Params& p, int C, int num_sms, int pipelined, cudaStream_t st) {
   // the fp32 path reads the image with 16-byte loads (W is a multiple of 8 by the engine's contract)
   if (!p.x_u8 && ((reinterpret_cast<uintptr_t>(p.x) & 15) != 0 || (p.W & 3) != 0)) return cudaErrorMisalignedAddress;
+  if (C == 32 && pipelined) return p.x_u8 ? stem3_launch_inst<true>(p, num_sms, st) : stem3_launch_inst<false>(p, num_sms, st);
   if (C == 32) return p.x_u8 ? stem2_launch_inst<32, true>(p, num_sms, st) : stem2_launch_inst<32, false>(p, num_sms, st);
   if (C == 64) return p.x_u8 ? stem2_launch_inst<64, true>(p, num_sms, st) : stem2_launch_inst<64, false>(p, num_sms, st);
   return cudaErrorInvalidValue;

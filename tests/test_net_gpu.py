@@ -169,7 +169,7 @@ def test_forward_u8_equals_forward_of_input_transform():
         assert np.array_equal(seg.cpu().numpy(), PO.argmax_labels(want.cpu().numpy(), H, W))
 
 
-@pytest.mark.parametrize('opts', [dict(use_pair=0), dict(use_pair=2), dict(ws_stages=2), dict(use_stem2=0),
+@pytest.mark.parametrize('opts', [dict(use_pair=0), dict(use_pair=2), dict(ws_stages=2), dict(use_stem2=0), dict(use_stem2=1),
                                   dict(use_ws=0), dict(use_pair=0, ws_stages=2, use_stem2=0)],
                          ids=lambda o: ','.join(f'{k}={v}' for k, v in o.items()))
 @pytest.mark.parametrize('name,shape', [('pidnet_s', (2, 3, 192, 320)), ('pidnet_m', (1, 3, 128, 192))])
