@@ -39,6 +39,7 @@
 // layers have K of only 64..512, so they are pure streaming and live or die by the per-tile overhead.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace pidnet {
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
     }
   };
 
+  if (threadIdx.x == 0) pdl_launch_dependents();
   if (threadIdx.x == 0) {
     mbar_init(w_full, PAIR ? 2 : 1);
     for (int s = 0; s < kMaxPatch; ++s) {
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
     if (PAIR) tmem_alloc_pair<4 * BN>(tmem_slot);
     else tmem_alloc<4 * BN>(tmem_slot);
   }
+  pdl_wait();   // everything above overlaps the previous kernel's tail; global memory is touched only from here on
   if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) bias_s[threadIdx.x - 64] = p.bias[c_out0 + threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
@@ -423,23 +426,40 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
   }
 }
 
+// All instances are launched with programmatic stream serialization (see ptx.cuh); PDL can be disabled with PIDNET_PDL=0.
+static bool pdl_enabled() {
+  static const bool on = [] { const char* v = std::getenv("PIDNET_PDL"); return !(v && v[0] == '0'); }();
+  return on;
+}
+template <class Kernel>
+cudaError_t ws_launch_ex(Kernel kernel, const Conv3Launch& L, int cluster, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = L.grid; cfg.blockDim = dim3(kWsThreads, 1, 1); cfg.dynamicSmemBytes = L.smem_bytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, L.p);
+}
 template <int BN, int CK>
 cudaError_t ws_launch_inst(const Conv3Launch& L, cudaStream_t stream) {
-  if (L.mode == 0) conv3_ws_kernel<BN, CK, 0, false><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
-  else conv3_ws_kernel<BN, CK, 1, false><<<L.grid, kWsThreads, L.smem_bytes, stream>>>(L.p);
-  return cudaGetLastError();
+  if (L.mode == 0) return ws_launch_ex(conv3_ws_kernel<BN, CK, 0, false>, L, 1, stream);
+  return ws_launch_ex(conv3_ws_kernel<BN, CK, 1, false>, L, 1, stream);
 }
 // CTA-pair instance: launched as 2-CTA clusters along x
 template <int BN, int CK>
 cudaError_t ws_launch_pair(const Conv3Launch& L, cudaStream_t stream) {
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = L.grid; cfg.blockDim = dim3(kWsThreads, 1, 1); cfg.dynamicSmemBytes = L.smem_bytes; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv3_ws_kernel<BN, CK, 0, true>, L.p);
+  return ws_launch_ex(conv3_ws_kernel<BN, CK, 0, true>, L, 2, stream);
 }
 template <int BN, int CK>
 cudaError_t ws_init_inst() {

@@ -157,6 +157,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (block scheduling, barrier / TMEM
+// setup) while its predecessor in the stream is still draining; it must execute pdl_wait() before it touches any global
+// memory (the wait returns when the predecessor grid has completed and its writes are visible).  A predecessor calls
+// pdl_launch_dependents() to say "from my side the next grid may be scheduled" (persistent kernels: at the start -- the
+// dependent's CTAs cannot become resident before ours exit anyway).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of a 2-CTA cluster (the two SMs of a TPC) execute ONE tcgen05.mma of M = 256: each CTA supplies its own
 // 128 rows of A and HALF of the N rows of B from the same smem offsets, and owns 128 lanes x N columns of the accumulator.
