@@ -1774,7 +1774,8 @@ int pidnet_train_profile(pidnet_trainer* h, void* stream, const float* x, const 
       out += line;
     }
     for (size_t i = 0; i < bw.size(); ++i) {
-      std::snprintf(line, sizeof(line), "B %.5f %s %s\n", bw[i], t.bops[i].kernel.empty() ? "-" : t.bops[i].kernel.c_str(), t.bops[i].name.c_str());
+      const Op& op = i < t.bops.size() ? t.bops[i] : t.post_ops[i - t.bops.size()];
+      std::snprintf(line, sizeof(line), "B %.5f %s %s\n", bw[i], op.kernel.empty() ? "-" : op.kernel.c_str(), op.name.c_str());
       out += line;
     }
     if (buf && cap) std::snprintf(buf, cap, "%s", out.c_str());
@@ -1830,7 +1831,7 @@ int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd) {
   return guard([&] {
     TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
     if (fwd) *fwd = static_cast<int>(t.b.ops.size() + 1);   // + the batched weight packing
-    if (bwd) *bwd = static_cast<int>(t.bops.size());
+    if (bwd) *bwd = static_cast<int>(t.bops.size() + t.post_ops.size());
   });
 }
 

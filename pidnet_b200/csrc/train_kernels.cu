@@ -1028,6 +1028,109 @@ cudaError_t pack_all_launch(const PackJob* dev_jobs, const unsigned* dev_block_s
   return cudaGetLastError();
 }
 
+// --------------------------------------------------------------------------- stem weight gradient (see train_kernels.cuh)
+namespace {
+constexpr int kSwWarps = 4;   // warps per block; each warp works on its own 32-pixel chunks
+__global__ void __launch_bounds__(kSwWarps * 32) stem_wgrad_kernel(const float* __restrict__ x, int N, int H, int W, View dy,
+                                                                  float* __restrict__ dW) {
+  __shared__ __align__(16) float xs[kSwWarps][32][32];          // im2col rows of the chunk (k = (ci*3+r)*3+s, 27..31 = 0)
+  __shared__ __align__(16) __nv_bfloat16 dys[kSwWarps][32][32];  // dY rows of the chunk (this block's 32-channel slice)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Ho = dy.H, Wo = dy.W;
+  const long P = static_cast<long>(N) * Ho * Wo;
+  const long chunks = (P + 31) / 32;
+  const int co0 = blockIdx.y * 32;
+  const int cg = lane & 7, kg = lane >> 3;   // thread tile: co 4cg..4cg+3  x  k 8kg..8kg+7
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const long plane = static_cast<long>(H) * W;
+  for (long c = static_cast<long>(blockIdx.x) * kSwWarps + warp; c < chunks; c += static_cast<long>(gridDim.x) * kSwWarps) {
+    // ---- stage: lane = pixel
+    const long pix = c * 32 + lane;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+    uint4 d4[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (pix < P) {
+      const int ow = static_cast<int>(pix % Wo);
+      const long t1 = pix / Wo;
+      const int oh = static_cast<int>(t1 % Ho);
+      const int n = static_cast<int>(t1 / Ho);
+      const float* xn = x + static_cast<long>(n) * 3 * plane;
+      const int ih0 = 2 * oh - 1, iw0 = 2 * ow - 1;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int ih = ih0 + r;
+          const bool rok = ih >= 0 && ih < H;
+          const float* rp = xn + ci * plane + static_cast<long>(rok ? ih : 0) * W;
+#pragma unroll
+          for (int s2 = 0; s2 < 3; ++s2) {
+            const int iw = iw0 + s2;
+            if (rok && iw >= 0 && iw < W) v[(ci * 3 + r) * 3 + s2] = __ldg(rp + iw);
+          }
+        }
+      const uint4* dp = reinterpret_cast<const uint4*>(dy.ptr + pix * dy.ps + co0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d4[q] = __ldg(dp + q);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(&xs[warp][lane][q * 4]) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(&dys[warp][lane][q * 8]) = d4[q];
+    __syncwarp();
+    // ---- 32 pixels x (4 co x 8 k) FMAs per thread
+#pragma unroll 4
+    for (int pz = 0; pz < 32; ++pz) {
+      const uint2 dq = *reinterpret_cast<const uint2*>(&dys[warp][pz][cg * 4]);
+      const float4 xa = *reinterpret_cast<const float4*>(&xs[warp][pz][kg * 8]);
+      const float4 xb = *reinterpret_cast<const float4*>(&xs[warp][pz][kg * 8 + 4]);
+      const float dv[4] = {__uint_as_float(dq.x << 16), __uint_as_float(dq.x & 0xFFFF0000u), __uint_as_float(dq.y << 16),
+                           __uint_as_float(dq.y & 0xFFFF0000u)};
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
+    }
+    __syncwarp();
+  }
+  // block reduction through smem (the staging buffers are free now), then ONE atomic per output and block
+  __syncthreads();
+  float* red = &xs[0][0][0];   // [kSwWarps][32 co][32 k] floats == sizeof(xs)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[(warp * 32 + cg * 4 + i) * 32 + kg * 8 + j] = acc[i][j];
+  __syncthreads();
+  for (int o = threadIdx.x; o < 32 * 32; o += kSwWarps * 32) {
+    const int co = o >> 5, k = o & 31;
+    if (k < 27) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSwWarps; ++w) sum += red[(w * 32 + co) * 32 + k];
+      atomicAdd(dW + static_cast<long>(co0 + co) * 27 + k, sum);
+    }
+  }
+}
+}  // namespace
+
+cudaError_t stem_wgrad_launch(const float* x, int N, int H, int W, View dy, float* dW, int num_sms, cudaStream_t st) {
+  if (dy.C % 32 != 0 || dy.ps % 8 != 0) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(dW, 0, static_cast<size_t>(dy.C) * 27 * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  const long chunks = (static_cast<long>(N) * dy.H * dy.W + 31) / 32;
+  long bx = static_cast<long>(num_sms) * 4;   // one resident wave (96 registers x 128 threads: 5 blocks per SM)
+  if (bx * kSwWarps > chunks) bx = (chunks + kSwWarps - 1) / kSwWarps;
+  stem_wgrad_kernel<<<dim3(static_cast<unsigned>(bx), dy.C / 32, 1), kSwWarps * 32, 0, st>>>(x, N, H, W, dy, dW);
+  return cudaGetLastError();
+}
+
 cudaError_t nchw_to_nhwc_launch(const float* x, int N, int C, int H, int W, View out, cudaStream_t st) {
   nchw_to_nhwc_kernel<<<blocks_for(static_cast<long>(N) * H * W, 256), 256, 0, st>>>(x, N, C, H, W, out);
   return cudaGetLastError();

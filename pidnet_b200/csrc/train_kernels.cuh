@@ -75,6 +75,13 @@ cudaError_t bag_train_bwd_launch(View p, View i_low, View d, View dout, View dp,
 // dst[c] += sums[c]  (bias gradients from a per-channel reduction)
 cudaError_t add_sums_launch(double* sums, float* dst, int C, int Cacc, cudaStream_t st);
 
+// ---- weight gradient of the 3-channel stem conv (conv1.0: 3x3, stride 2, pad 1) straight from the caller's fp32 NCHW image:
+//   dW[co][ci][r][s] = sum_{n,oh,ow} dY[n,oh,ow,co] * x[n,ci,2oh-1+r,2ow-1+s]      (overwrites dW: [Cout][3][3][3] fp32)
+// K = pixels is the whole problem (5.4 GFLOP at 12 x 1024^2): a register-tiled SIMT kernel (one warp owns the full 32 x 27
+// gradient of a 32-channel slice for its pixel chunks; 4 co x 8 k accumulators per thread) instead of the tcgen05 wgrad on
+// an 8-channel padded NHWC copy of the image (0.52 ms + 0.11 ms for the copy).
+cudaError_t stem_wgrad_launch(const float* x, int N, int H, int W, View dy, float* dW, int num_sms, cudaStream_t st);
+
 // ---- wgrad on tcgen05 with MN-major operands (wgrad_tc.cu):
 //   dW[co][ci_off+ci][r][s] += sum_pixels dY[p][co] * X[tap(p)][ci]       (fp32 atomics into the torch-layout gradient)
 struct WgradParams {
