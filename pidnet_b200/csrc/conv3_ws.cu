@@ -427,10 +427,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
 }
 
 // All instances are launched with programmatic stream serialization (see ptx.cuh); PDL can be disabled with PIDNET_PDL=0.
-static bool pdl_enabled() {
-  static const bool on = [] { const char* v = std::getenv("PIDNET_PDL"); return !(v && v[0] == '0'); }();
-  return on;
-}
 template <class Kernel>
 cudaError_t ws_launch_ex(Kernel kernel, const Conv3Launch& L, int cluster, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, BK>::kAliasOut ? 2 : 1) conv
   int num_k = 0;
   for (int s = 0; s < p.nsrc; ++s) num_k += p.src[s].ntaps * p.src[s].chunks;
 
-  // ---- one-time setup
+  // ---- one-time setup (overlaps the previous kernel's tail under programmatic dependent launch, see ptx.cuh)
+  if (threadIdx.x == 0) pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, BK>::kAliasOut ? 2 : 1) conv
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<BN>(tmem_slot);
+  pdl_wait();   // global memory is touched only from here on
   if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias[c_out0 + threadIdx.x];
   tc_fence_before();
   __syncthreads();
@@ -239,8 +241,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, BK>::kAliasOut ? 2 : 1) conv
 
 template <int BN, int BK>
 cudaError_t launch_inst(const ConvLaunch& L, cudaStream_t stream) {
-  conv_tc_kernel<BN, BK><<<L.grid, kThreads, Cfg<BN, BK>::kSmem, stream>>>(L.p);
-  return cudaGetLastError();
+  return launch_pdl(conv_tc_kernel<BN, BK>, L.grid, dim3(kThreads, 1, 1), Cfg<BN, BK>::kSmem, stream, L.p);
 }
 
 template <int BN, int BK>

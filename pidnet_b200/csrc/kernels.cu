@@ -1,5 +1,6 @@
 // HBM-bound fused kernels: 128-bit vectorised NHWC bf16 access, fp32 math.
 #include "kernels.cuh"
+#include "ptx.cuh"
 #include <cstdlib>
 
 namespace pidnet {
@@ -231,6 +232,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
 // --------------------------------------------------------------------------- PagFM fuse
 template <int LP>  // lanes per pixel = C/8
 __global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View out, int relu, Dec dec) {
+  pdl_wait();
+  pdl_launch_dependents();
   const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, dec, LP, x.W, x.H, x.N);
   const int C = x.C, cg = ix.cg;
   const Lerp lw = lerp_of(ix.w, low.W, dec.sw);
@@ -292,6 +295,8 @@ __global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View ou
 // --------------------------------------------------------------------------- upadd / affine
 __global__ void __launch_bounds__(256) upadd_kernel(View a, View b, View r, View out, const float* __restrict__ s,
                                                     const float* __restrict__ t, int relu, Dec dec) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int groups = out.C >> 3;
   const unsigned total = static_cast<unsigned>(out.N) * out.H * out.W * groups;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,6 +358,8 @@ struct RowPair {
 };
 __global__ void __launch_bounds__(256) upadd_strip_kernel(View a, View b, View r, View out, const float* __restrict__ s,
                                                           const float* __restrict__ t, int relu, Dec dec) {
+  pdl_wait();
+  pdl_launch_dependents();
   const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, dec, out.C >> 3, out.W, out.H, out.N);
   if (!ix.valid) return;
   const int cg = ix.cg;
@@ -411,6 +418,8 @@ __global__ void __launch_bounds__(256) upadd_strip_kernel(View a, View b, View r
 __global__ void __launch_bounds__(256) pool_affine_kernel(View x, View out, int k, int stride, int pad,
                                                           const float* __restrict__ s, const float* __restrict__ t,
                                                           int relu) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float red[];  // [splits][groups*8]
   const int groups = x.C >> 3;
   const int splits = blockDim.x / groups;
@@ -467,6 +476,8 @@ __global__ void __launch_bounds__(256) pool_affine_kernel(View x, View out, int 
 template <bool kBag>
 __global__ void __launch_bounds__(256) bag_strip_kernel(View p, View il, View d, View out, const float* __restrict__ s,
                                                         const float* __restrict__ t, Dec dec) {
+  pdl_wait();
+  pdl_launch_dependents();
   const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, dec, p.C >> 3, p.W, p.H, p.N);
   if (!ix.valid) return;
   const int cg = ix.cg;
@@ -526,6 +537,8 @@ __global__ void __launch_bounds__(256) bag_strip_kernel(View p, View il, View d,
 // ---- flat (one thread per pixel x 8 channels) forms, the default for PagFM / Light_Bag: measured faster than their strip forms, which need 152 registers (PIDNET_ELTWISE_STRIP=1 selects those)
 template <int LP>  // lanes per pixel = C/8
 __global__ void __launch_bounds__(256) pag_fuse_flat_kernel(View x, View low, View out, int relu, Dec dec) {
+  pdl_wait();
+  pdl_launch_dependents();
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned npix = static_cast<unsigned>(x.N) * x.H * x.W;
   const bool valid = gid / LP < npix;
@@ -561,6 +574,8 @@ __global__ void __launch_bounds__(256) pag_fuse_flat_kernel(View x, View low, Vi
 }
 
 __global__ void __launch_bounds__(256) lightbag_uv_flat_kernel(View p, View il, View d, View out, Dec dec) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int groups = p.C >> 3;
   const long total = static_cast<long>(p.N) * p.H * p.W * groups;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -587,6 +602,8 @@ __global__ void __launch_bounds__(256) lightbag_uv_flat_kernel(View p, View il, 
 
 __global__ void __launch_bounds__(256) bag_blend_flat_kernel(View p, View il, View d, View out, const float* __restrict__ s,
                                                              const float* __restrict__ t, Dec dec) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int groups = p.C >> 3;
   const long total = static_cast<long>(p.N) * p.H * p.W * groups;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -675,12 +692,12 @@ cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t s
   if (flat) {
     const unsigned nbf = blocks_for(static_cast<long>(x.N) * x.H * x.W * LP, 256);
     switch (LP) {
-      case 1: pag_fuse_flat_kernel<1><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
-      case 2: pag_fuse_flat_kernel<2><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
-      case 4: pag_fuse_flat_kernel<4><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
-      case 8: pag_fuse_flat_kernel<8><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
-      case 16: pag_fuse_flat_kernel<16><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
-      case 32: pag_fuse_flat_kernel<32><<<nbf, 256, 0, st>>>(x, low, out, relu, dflat); break;
+      case 1: launch_pdl(pag_fuse_flat_kernel<1>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
+      case 2: launch_pdl(pag_fuse_flat_kernel<2>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
+      case 4: launch_pdl(pag_fuse_flat_kernel<4>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
+      case 8: launch_pdl(pag_fuse_flat_kernel<8>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
+      case 16: launch_pdl(pag_fuse_flat_kernel<16>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
+      case 32: launch_pdl(pag_fuse_flat_kernel<32>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
       default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -688,12 +705,12 @@ cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t s
   const long total = static_cast<long>(x.N) * ((x.H + kStrip - 1) / kStrip) * x.W * LP;   // one thread per strip
   const unsigned nb = blocks_for(total, 256);
   switch (LP) {
-    case 1: pag_fuse_kernel<1><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
-    case 2: pag_fuse_kernel<2><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
-    case 4: pag_fuse_kernel<4><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
-    case 8: pag_fuse_kernel<8><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
-    case 16: pag_fuse_kernel<16><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
-    case 32: pag_fuse_kernel<32><<<nb, 256, 0, st>>>(x, low, out, relu, dstrip); break;
+    case 1: launch_pdl(pag_fuse_kernel<1>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
+    case 2: launch_pdl(pag_fuse_kernel<2>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
+    case 4: launch_pdl(pag_fuse_kernel<4>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
+    case 8: launch_pdl(pag_fuse_kernel<8>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
+    case 16: launch_pdl(pag_fuse_kernel<16>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
+    case 32: launch_pdl(pag_fuse_kernel<32>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -709,10 +726,9 @@ cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, c
   if (b.ptr) {
     const long strips = static_cast<long>(out.N) * ((out.H + kStrip - 1) / kStrip) * out.W * (out.C / 8);
     if (static_cast<long>(b.H) * b.W * b.ps >= (1L << 31)) return cudaErrorInvalidValue;   // 32-bit offsets inside an image
-    upadd_strip_kernel<<<blocks_for(strips, 256), 256, 0, st>>>(
-        a, b, r, out, s, t, relu, make_dec(out.C / 8, out.W, (out.H + kStrip - 1) / kStrip, b.H, out.H, b.W, out.W));
+    launch_pdl(upadd_strip_kernel, dim3(blocks_for(strips, 256), 1, 1), dim3(256, 1, 1), 0, st, a, b, r, out, s, t, relu, make_dec(out.C / 8, out.W, (out.H + kStrip - 1) / kStrip, b.H, out.H, b.W, out.W));
   } else {
-    upadd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a, b, r, out, s, t, relu,
+    launch_pdl(upadd_kernel, dim3(blocks_for(total, 256), 1, 1), dim3(256, 1, 1), 0, st, a, b, r, out, s, t, relu,
                                                           make_dec(out.C / 8, out.W, out.H, 0, 0, 0, 0));
   }
   return cudaGetLastError();
@@ -725,7 +741,7 @@ cudaError_t pool_affine_launch(View x, View out, int k, int stride, int pad, con
   const int splits = 256 / groups;
   const int threads = splits * groups;
   const size_t smem = static_cast<size_t>(threads) * 8 * sizeof(float);
-  pool_affine_kernel<<<out.N * out.H * out.W, threads, smem, st>>>(x, out, k, stride, pad, s, t, relu);
+  launch_pdl(pool_affine_kernel, dim3(out.N * out.H * out.W, 1, 1), dim3(threads, 1, 1), smem, st, x, out, k, stride, pad, s, t, relu);
   return cudaGetLastError();
 }
 
@@ -734,13 +750,12 @@ cudaError_t lightbag_uv_launch(View p, View i_low, View d, View out, cudaStream_
   if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
   static const bool flat = getenv("PIDNET_ELTWISE_STRIP") == nullptr;
   if (flat) {
-    lightbag_uv_flat_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out,
+    launch_pdl(lightbag_uv_flat_kernel, dim3(blocks_for(total, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out,
                                                                      make_dec(p.C / 8, p.W, p.H, i_low.H, p.H, i_low.W, p.W));
     return cudaGetLastError();
   }
   const long strips = static_cast<long>(p.N) * ((p.H + kStrip - 1) / kStrip) * p.W * (p.C / 8);
-  bag_strip_kernel<false><<<blocks_for(strips, 256), 256, 0, st>>>(
-      p, i_low, d, out, nullptr, nullptr, make_dec(p.C / 8, p.W, (p.H + kStrip - 1) / kStrip, i_low.H, p.H, i_low.W, p.W));
+  launch_pdl(bag_strip_kernel<false>, dim3(blocks_for(strips, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out, nullptr, nullptr, make_dec(p.C / 8, p.W, (p.H + kStrip - 1) / kStrip, i_low.H, p.H, i_low.W, p.W));
   return cudaGetLastError();
 }
 
@@ -750,12 +765,11 @@ cudaError_t bag_blend_launch(View p, View i_low, View d, View out, const float* 
   const long strips = static_cast<long>(p.N) * ((p.H + kStrip - 1) / kStrip) * p.W * (p.C / 8);
   static const bool flat = getenv("PIDNET_ELTWISE_STRIP") == nullptr;
   if (flat) {   // (measured on PIDNet-L: strip form 0.68 ms at 152 registers, flat form below)
-    bag_blend_flat_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p, i_low, d, out, s, t,
+    launch_pdl(bag_blend_flat_kernel, dim3(blocks_for(total, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out, s, t,
                                                                    make_dec(p.C / 8, p.W, p.H, i_low.H, p.H, i_low.W, p.W));
     return cudaGetLastError();
   }
-  bag_strip_kernel<true><<<blocks_for(strips, 256), 256, 0, st>>>(
-      p, i_low, d, out, s, t, make_dec(p.C / 8, p.W, (p.H + kStrip - 1) / kStrip, i_low.H, p.H, i_low.W, p.W));
+  launch_pdl(bag_strip_kernel<true>, dim3(blocks_for(strips, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out, s, t, make_dec(p.C / 8, p.W, (p.H + kStrip - 1) / kStrip, i_low.H, p.H, i_low.W, p.W));
   return cudaGetLastError();
 }
 

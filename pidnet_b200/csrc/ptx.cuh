@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -165,6 +166,23 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // dependent's CTAs cannot become resident before ours exit anyway).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// host side: launch `kernel` with the PDL attribute (PIDNET_PDL=0 turns the attribute off; the device-side instructions
+// are no-ops for a normally launched grid)
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* v = std::getenv("PIDNET_PDL"); return !(v && v[0] == '0'); }();
+  return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of a 2-CTA cluster (the two SMs of a TPC) execute ONE tcgen05.mma of M = 256: each CTA supplies its own

@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(kS2Threads, C == 32 ? 2 : 1) stem2_tc_kernel(c
   volatile uint32_t* slot_gen = reinterpret_cast<volatile uint32_t*>(gen + G::kOffMisc + 512 + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < G::kW2Bytes / 16; i += kS2Threads)
     reinterpret_cast<uint4*>(gen + G::kOffW2)[i] = reinterpret_cast<const uint4*>(p.w2_swz)[i];
   for (int i = threadIdx.x; i < G::kW1Bytes / 16; i += kS2Threads)
@@ -396,6 +398,8 @@ __global__ void __launch_bounds__(kS3Threads, 1) stem3_tc_kernel(const __grid_co
   volatile uint32_t* slot_gen = reinterpret_cast<volatile uint32_t*>(gen + kOffMisc + 512 + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < G::kW2Bytes / 16; i += kS3Threads)
     reinterpret_cast<uint4*>(gen + kOffW2)[i] = reinterpret_cast<const uint4*>(p.w2_swz)[i];
   for (int i = threadIdx.x; i < G::kW1Bytes / 16; i += kS3Threads)
@@ -695,8 +699,7 @@ cudaError_t stem3_launch_inst(const Stem2Params& p, int num_sms, cudaStream_t st
   }
   long blocks = static_cast<long>(p.N) * p.tiles_w * p.tiles_h;
   if (blocks > num_sms) blocks = num_sms;
-  stem3_tc_kernel<U8><<<static_cast<unsigned>(blocks), kS3Threads, kSmem, st>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(stem3_tc_kernel<U8>, dim3(static_cast<unsigned>(blocks), 1, 1), dim3(kS3Threads, 1, 1), kSmem, st, p);
 }
 
 template <int C, bool U8>
@@ -711,8 +714,7 @@ cudaError_t stem2_launch_inst(const Stem2Params& p, int num_sms, cudaStream_t st
   long blocks = static_cast<long>(p.N) * p.tiles_w * p.tiles_h;
   const long cap = static_cast<long>(num_sms) * (C == 32 ? 2 : 1);
   if (blocks > cap) blocks = cap;
-  stem2_tc_kernel<C, U8><<<static_cast<unsigned>(blocks), kS2Threads, G::kSmem, st>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(stem2_tc_kernel<C, U8>, dim3(static_cast<unsigned>(blocks), 1, 1), dim3(kS2Threads, 1, 1), G::kSmem, st, p);
 }
 
 }  // namespace
