@@ -974,12 +974,42 @@ struct Engine {
     // scale branches: BN -> ReLU (after the pool) then 1x1
     T a0 = affine_relu("spp.scale0.bnrelu", x, bn("spp.scale0.0"), nullptr);
     T s0 = conv_plain("spp.scale0.conv", a0, "spp.scale0.2", nullptr, 1, false, nullptr);
-    T sk[4];
+    T sk[4], ak[4];
+    static const bool use_pyramid = env_int("PIDNET_POOL_PYRAMID", 1) != 0;
+    if (use_pyramid && x.C % 32 == 0 && static_cast<size_t>(x.H + 1) * (x.W + 1) * 128 <= 200 * 1024) {
+      // all four pooled branches (+ their BN + ReLU) from one summed-area table per 32-channel slice: one launch
+      std::vector<float> sall, tall;
+      View ov[4];
+      for (int k = 0; k < 4; ++k) {
+        const int oh = k < 3 ? (x.H + 2 * pp[k] - pk[k]) / pstr[k] + 1 : 1, ow = k < 3 ? (x.W + 2 * pp[k] - pk[k]) / pstr[k] + 1 : 1;
+        if (oh < 1 || ow < 1) fail("spp: pooled map is empty");
+        ak[k] = b.new_tensor(x.N, oh, ow, x.C);
+        ov[k] = ak[k].view();
+        const Affine a = bn("spp.scale" + std::to_string(k + 1) + ".1");
+        sall.insert(sall.end(), a.s.begin(), a.s.end());
+        tall.insert(tall.end(), a.t.begin(), a.t.end());
+      }
+      const float* sd = b.upload_f32(sall);
+      const float* td = b.upload_f32(tall);
+      const View xv = x.view();
+      const View o0 = ov[0], o1 = ov[1], o2 = ov[2], o3 = ov[3];
+      const int op = b.add_op("spp.pools", {&x}, [xv, o0, o1, o2, o3, sd, td](cudaStream_t st, const RunArgs&) {
+        const View outs[4] = {o0, o1, o2, o3};
+        return pool_pyramid_launch(xv, outs, sd, td, st);
+      });
+      double ob = 0;
+      for (int k = 0; k < 4; ++k) { ak[k].prod = op; ob += Builder::tbytes(ak[k]); }
+      b.label(op, "pool_pyramid", Builder::tbytes(x) + ob);
+    } else {
+      for (int k = 0; k < 4; ++k) {
+        const std::string sp = "spp.scale" + std::to_string(k + 1);
+        ak[k] = k < 3 ? pool_affine(sp + ".pool", x, pk[k], pstr[k], pp[k], bn(sp + ".1"))
+                      : pool_affine(sp + ".pool", x, 0, 1, 0, bn(sp + ".1"));
+      }
+    }
     for (int k = 0; k < 4; ++k) {
       const std::string sp = "spp.scale" + std::to_string(k + 1);
-      T ak = k < 3 ? pool_affine(sp + ".pool", x, pk[k], pstr[k], pp[k], bn(sp + ".1"))
-                   : pool_affine(sp + ".pool", x, 0, 1, 0, bn(sp + ".1"));
-      sk[k] = conv_plain(sp + ".conv", ak, sp + ".3", nullptr, 1, false, nullptr);
+      sk[k] = conv_plain(sp + ".conv", ak[k], sp + ".3", nullptr, 1, false, nullptr);
     }
     const Affine acomp = bn("spp.compression.0");
     T comp_in = b.new_tensor(x.N, x.H, x.W, 5 * ppm);

@@ -471,6 +471,78 @@ __global__ void __launch_bounds__(256) pool_affine_kernel(View x, View out, int 
   }
 }
 
+// --------------------------------------------------------------------------- pooled pyramid (see kernels.cuh)
+struct PyramidParams {
+  View x;
+  View out[4];
+  const float* s;   // [4][C]
+  const float* t;
+};
+__global__ void __launch_bounds__(256) pool_pyramid_kernel(PyramidParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ float sat[];   // [(H+1)][(W+1)][32]: sat[h][w][c] = sum of x[<h][<w][c]
+  const int H = p.x.H, W = p.x.W, W1 = W + 1;
+  const int groups = p.x.C >> 5;              // 32-channel slices
+  const int n = blockIdx.x / groups, c0 = (blockIdx.x - n * groups) * 32;
+  const bf16* xin = p.x.ptr + static_cast<long>(n) * H * W * p.x.ps + c0;
+  // zero border, then the pixels (thread = pixel x 8-channel group)
+  for (int i = threadIdx.x; i < (H + 1 + W) * 32; i += 256) {
+    const int c = i & 31, j = i >> 5;          // j < W1: row 0; else column 0 of row j - W
+    if (j < W1) sat[j * 32 + c] = 0.f;
+    else sat[static_cast<long>(j - W) * W1 * 32 + c] = 0.f;
+  }
+  for (int i = threadIdx.x; i < H * W * 4; i += 256) {
+    const int g = i & 3, pix = i >> 2;
+    const int h = pix / W, w = pix - h * W;
+    const F8 v = ld8(xin + static_cast<long>(pix) * p.x.ps + g * 8);
+    float* d = sat + (static_cast<long>(h + 1) * W1 + w + 1) * 32 + g * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = v.v[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * 32; i += 256) {   // prefix along w
+    const int c = i & 31, h = i >> 5;
+    float* r = sat + static_cast<long>(h + 1) * W1 * 32 + c;
+    float a = 0.f;
+    for (int w = 1; w <= W; ++w) { a += r[w * 32]; r[w * 32] = a; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W * 32; i += 256) {   // prefix along h
+    const int c = i & 31, w = i >> 5;
+    float* r = sat + static_cast<long>(w + 1) * 32 + c;
+    float a = 0.f;
+    for (int h = 1; h <= H; ++h) { a += r[static_cast<long>(h) * W1 * 32]; r[static_cast<long>(h) * W1 * 32] = a; }
+  }
+  __syncthreads();
+  auto box = [&](int h0, int h1, int w0, int w1, int c) {
+    return sat[(static_cast<long>(h1) * W1 + w1) * 32 + c] - sat[(static_cast<long>(h0) * W1 + w1) * 32 + c] -
+           sat[(static_cast<long>(h1) * W1 + w0) * 32 + c] + sat[(static_cast<long>(h0) * W1 + w0) * 32 + c];
+  };
+#pragma unroll
+  for (int lv = 0; lv < 4; ++lv) {
+    const View& o = p.out[lv];
+    const int k = lv == 0 ? 5 : (lv == 1 ? 9 : 17), stride = lv == 0 ? 2 : (lv == 1 ? 4 : 8), pad = stride;
+    const float* sc = p.s + lv * p.x.C + c0;
+    const float* sh = p.t + lv * p.x.C + c0;
+    bf16* ob = o.ptr + static_cast<long>(n) * o.H * o.W * o.ps + c0;
+    for (int i = threadIdx.x; i < o.H * o.W * 32; i += 256) {
+      const int c = i & 31, op = i >> 5;
+      const int oh = op / o.W, ow = op - oh * o.W;
+      float v;
+      if (lv == 3) {
+        v = box(0, H, 0, W, c) / static_cast<float>(H * W);
+      } else {   // count_include_pad=True: the divisor is k*k, the sum runs over the in-image part of the window
+        const int h0 = max(oh * stride - pad, 0), w0 = max(ow * stride - pad, 0);
+        const int h1 = min(oh * stride - pad + k, H), w1 = min(ow * stride - pad + k, W);
+        v = box(h0, h1, w0, w1, c) / static_cast<float>(k * k);
+      }
+      v = fmaxf(v * __ldg(sc + c) + __ldg(sh + c), 0.f);
+      ob[static_cast<long>(op) * o.ps + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 // --------------------------------------------------------------------------- Light_Bag / Bag
 // (strip walk: the x8 upsample of the PPM output costs 4 row gathers per 8 pixels instead of 32 corner gathers)
 template <bool kBag>
@@ -731,6 +803,23 @@ cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, c
     launch_pdl(upadd_kernel, dim3(blocks_for(total, 256), 1, 1), dim3(256, 1, 1), 0, st, a, b, r, out, s, t, relu,
                                                           make_dec(out.C / 8, out.W, out.H, 0, 0, 0, 0));
   }
+  return cudaGetLastError();
+}
+
+cudaError_t pool_pyramid_launch(View x, const View out[4], const float* s, const float* t, cudaStream_t st) {
+  if (x.C % 32 != 0) return cudaErrorNotSupported;
+  const size_t smem = static_cast<size_t>(x.H + 1) * (x.W + 1) * 32 * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorNotSupported;
+  static size_t opted = 0;
+  if (smem > 48 * 1024 && smem > opted) {
+    cudaError_t e = cudaFuncSetAttribute(pool_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    opted = 200 * 1024;
+  }
+  PyramidParams p;
+  p.x = x; p.s = s; p.t = t;
+  for (int i = 0; i < 4; ++i) p.out[i] = out[i];
+  launch_pdl(pool_pyramid_kernel, dim3(x.N * (x.C / 32), 1, 1), dim3(256, 1, 1), smem, st, p);
   return cudaGetLastError();
 }
 
