@@ -1016,11 +1016,29 @@ struct Engine {
     if (!large) {
       const Affine asp = bn("spp.scale_process.0");
       T sp_in = b.new_tensor(x.N, x.H, x.W, 4 * ppm);
-      for (int k = 0; k < 4; ++k) {
-        T dst = Builder::slice(sp_in, k * ppm, ppm);
-        Affine a = slice(asp, k * ppm, ppm);
-        T w = upadd("spp.scale" + std::to_string(k + 1) + ".upadd", s0, sk[k], &a, true, &dst);
-        sp_in.prod = w.prod;  // all four writers are on this lane; the last one orders the consumer
+      {   // relu(bn_k(scale0 + U(scale_k))) for the four branches in ONE launch, each into its channel slice of sp_in
+        View av[4], bv[4], ovs[4];
+        const float* sd[4];
+        const float* td[4];
+        double bytes = 0;
+        for (int k = 0; k < 4; ++k) {
+          T dst = Builder::slice(sp_in, k * ppm, ppm);
+          Affine a = slice(asp, k * ppm, ppm);
+          av[k] = s0.view(); bv[k] = sk[k].view(); ovs[k] = dst.view();
+          sd[k] = b.upload_f32(a.s); td[k] = b.upload_f32(a.t);
+          bytes += Builder::tbytes(s0) + Builder::tbytes(sk[k]) + Builder::tbytes(dst);
+        }
+        const View a0 = av[0], a1 = av[1], a2 = av[2], a3 = av[3], b0 = bv[0], b1 = bv[1], b2 = bv[2], b3 = bv[3];
+        const View o0 = ovs[0], o1 = ovs[1], o2 = ovs[2], o3 = ovs[3];
+        const float *s0p = sd[0], *s1p = sd[1], *s2p = sd[2], *s3p = sd[3], *t0p = td[0], *t1p = td[1], *t2p = td[2], *t3p = td[3];
+        sp_in.prod = b.add_op("spp.scale1-4.upadd", {&s0, &sk[0], &sk[1], &sk[2], &sk[3]},
+                              [=](cudaStream_t st, const RunArgs&) {
+                                const View aa[4] = {a0, a1, a2, a3}, bb[4] = {b0, b1, b2, b3}, oo[4] = {o0, o1, o2, o3};
+                                const float* ss[4] = {s0p, s1p, s2p, s3p};
+                                const float* ts[4] = {t0p, t1p, t2p, t3p};
+                                return upadd_batch_launch(4, aa, bb, oo, ss, ts, 1, st);
+                              });
+        b.label(sp_in.prod, "upadd", bytes);
       }
       T c0 = Builder::slice(comp_in, 0, ppm);
       affine_relu("spp.x_.bnrelu", s0, slice(acomp, 0, ppm), &c0);

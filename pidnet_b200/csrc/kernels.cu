@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace pidnet {
 
@@ -356,10 +357,9 @@ struct RowPair {
     }
   }
 };
-__global__ void __launch_bounds__(256) upadd_strip_kernel(View a, View b, View r, View out, const float* __restrict__ s,
-                                                          const float* __restrict__ t, int relu, Dec dec) {
-  pdl_wait();
-  pdl_launch_dependents();
+__device__ __forceinline__ void upadd_strip_body(const View& a, const View& b, const View& r, const View& out,
+                                                 const float* __restrict__ s, const float* __restrict__ t, int relu,
+                                                 const Dec& dec) {
   const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, dec, out.C >> 3, out.W, out.H, out.N);
   if (!ix.valid) return;
   const int cg = ix.cg;
@@ -411,6 +411,26 @@ __global__ void __launch_bounds__(256) upadd_strip_kernel(View a, View b, View r
       st8(out.ptr + (pixn + static_cast<long>(h) * out.W) * out.ps + cg * 8, v);
     }
   }
+}
+__global__ void __launch_bounds__(256) upadd_strip_kernel(View a, View b, View r, View out, const float* __restrict__ s,
+                                                          const float* __restrict__ t, int relu, Dec dec) {
+  pdl_wait();
+  pdl_launch_dependents();
+  upadd_strip_body(a, b, r, out, s, t, relu, dec);
+}
+// up to four independent jobs with the same output geometry in one launch (blockIdx.y = job): the PAPPM branch adds
+struct UpaddBatch {
+  View a[4], b[4], out[4];
+  const float* s[4];
+  const float* t[4];
+  Dec dec[4];
+  int relu;
+};
+__global__ void __launch_bounds__(256) upadd_strip_batch_kernel(const __grid_constant__ UpaddBatch p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int j = blockIdx.y;
+  upadd_strip_body(p.a[j], p.b[j], View{nullptr, 0, 0, 0, 0, 0}, p.out[j], p.s[j], p.t[j], p.relu, p.dec[j]);
 }
 
 // --------------------------------------------------------------------------- avg pool + affine
@@ -803,6 +823,25 @@ cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, c
     launch_pdl(upadd_kernel, dim3(blocks_for(total, 256), 1, 1), dim3(256, 1, 1), 0, st, a, b, r, out, s, t, relu,
                                                           make_dec(out.C / 8, out.W, out.H, 0, 0, 0, 0));
   }
+  return cudaGetLastError();
+}
+
+cudaError_t upadd_batch_launch(int njobs, const View* a, const View* b, const View* out, const float* const* s,
+                               const float* const* t, int relu, cudaStream_t st) {
+  if (njobs < 1 || njobs > 4) return cudaErrorInvalidValue;
+  UpaddBatch p;
+  std::memset(&p, 0, sizeof(p));
+  p.relu = relu;
+  for (int j = 0; j < njobs; ++j) {
+    if (!b[j].ptr || out[j].N != out[0].N || out[j].H != out[0].H || out[j].W != out[0].W || out[j].C != out[0].C)
+      return cudaErrorInvalidValue;
+    if (static_cast<long>(b[j].H) * b[j].W * b[j].ps >= (1L << 31)) return cudaErrorInvalidValue;
+    p.a[j] = a[j]; p.b[j] = b[j]; p.out[j] = out[j]; p.s[j] = s[j]; p.t[j] = t[j];
+    p.dec[j] = make_dec(out[j].C / 8, out[j].W, (out[j].H + kStrip - 1) / kStrip, b[j].H, out[j].H, b[j].W, out[j].W);
+  }
+  const long strips = static_cast<long>(out[0].N) * ((out[0].H + kStrip - 1) / kStrip) * out[0].W * (out[0].C / 8);
+  if (strips * kStrip + 256 >= (1L << 32)) return cudaErrorInvalidValue;
+  launch_pdl(upadd_strip_batch_kernel, dim3(blocks_for(strips, 256), njobs, 1), dim3(256, 1, 1), 0, st, p);
   return cudaGetLastError();
 }
 

@@ -69,6 +69,10 @@ cudaError_t upadd_launch(View a, View b, View out, const float* s, const float* 
 cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, const float* t, int relu, cudaStream_t st);
 
 // ---- average pool (count_include_pad) + affine + ReLU; k == 0 means global average pool
+// up to four upsample-add jobs of identical output geometry in ONE launch (PAPPM: relu(bn_k(scale0 + U(scale_k))), k = 1..4)
+cudaError_t upadd_batch_launch(int njobs, const View* a, const View* b, const View* out, const float* const* s,
+                               const float* const* t, int relu, cudaStream_t st);
+
 // ---- the four pooled branches of PAPPM / DAPPM (AvgPool 5/2/2, 9/4/4, 17/8/8 and the global pool, each + BN + ReLU) from ONE
 // pass over x: a block builds the summed-area table of a 32-channel slice of one image in shared memory (fp32) and every
 // pooled output is four table look-ups.  out[0..2]: k = 5, 9, 17; out[3]: 1x1.  s / t: the four BN affines, [4][C].
