@@ -972,13 +972,20 @@ struct Engine {
     const int ppm = cfg.ppm_planes, outp = cfg.planes * 4;
     static const int pk[3] = {5, 9, 17}, pstr[3] = {2, 4, 8}, pp[3] = {2, 4, 8};
     // scale branches: BN -> ReLU (after the pool) then 1x1
-    T a0 = affine_relu("spp.scale0.bnrelu", x, bn("spp.scale0.0"), nullptr);
-    T s0 = conv_plain("spp.scale0.conv", a0, "spp.scale0.2", nullptr, 1, false, nullptr);
-    T sk[4], ak[4];
     static const bool use_pyramid = env_int("PIDNET_POOL_PYRAMID", 1) != 0;
-    if (use_pyramid && x.C % 32 == 0 && static_cast<size_t>(x.H + 1) * (x.W + 1) * 128 <= 200 * 1024) {
-      // all four pooled branches (+ their BN + ReLU) from one summed-area table per 32-channel slice: one launch
-      std::vector<float> sall, tall;
+    const bool pyramid = use_pyramid && x.C % 32 == 0 && static_cast<size_t>(x.H + 1) * (x.W + 1) * 128 <= 200 * 1024;
+    T a0, sc_in;   // relu(bn(x)) operands of scale0 and of the shortcut: by-products of the pyramid kernel when it is used
+    if (pyramid) {
+      a0 = b.new_tensor(x.N, x.H, x.W, x.C);
+      sc_in = b.new_tensor(x.N, x.H, x.W, x.C);
+    } else {
+      a0 = affine_relu("spp.scale0.bnrelu", x, bn("spp.scale0.0"), nullptr);
+    }
+    T ak[4];
+    if (pyramid) {
+      // all four pooled branches (+ their BN + ReLU) from one summed-area table per 32-channel slice, plus the two
+      // full-resolution relu(bn(x)) operands: ONE launch reads x once for six consumers
+      std::vector<float> sall, tall, se, te;
       View ov[4];
       for (int k = 0; k < 4; ++k) {
         const int oh = k < 3 ? (x.H + 2 * pp[k] - pk[k]) / pstr[k] + 1 : 1, ow = k < 3 ? (x.W + 2 * pp[k] - pk[k]) / pstr[k] + 1 : 1;
@@ -989,16 +996,25 @@ struct Engine {
         sall.insert(sall.end(), a.s.begin(), a.s.end());
         tall.insert(tall.end(), a.t.begin(), a.t.end());
       }
+      for (const char* key : {"spp.scale0.0", "spp.shortcut.0"}) {
+        const Affine a = bn(key);
+        se.insert(se.end(), a.s.begin(), a.s.end());
+        te.insert(te.end(), a.t.begin(), a.t.end());
+      }
       const float* sd = b.upload_f32(sall);
       const float* td = b.upload_f32(tall);
+      const float* sed = b.upload_f32(se);
+      const float* ted = b.upload_f32(te);
       const View xv = x.view();
-      const View o0 = ov[0], o1 = ov[1], o2 = ov[2], o3 = ov[3];
-      const int op = b.add_op("spp.pools", {&x}, [xv, o0, o1, o2, o3, sd, td](cudaStream_t st, const RunArgs&) {
+      const View o0 = ov[0], o1 = ov[1], o2 = ov[2], o3 = ov[3], e0 = a0.view(), e1 = sc_in.view();
+      const int op = b.add_op("spp.pools+bnrelu", {&x}, [xv, o0, o1, o2, o3, e0, e1, sd, td, sed, ted](cudaStream_t st, const RunArgs&) {
         const View outs[4] = {o0, o1, o2, o3};
-        return pool_pyramid_launch(xv, outs, sd, td, st);
+        const View ews[2] = {e0, e1};
+        return pool_pyramid_launch(xv, outs, sd, td, ews, sed, ted, st);
       });
-      double ob = 0;
+      double ob = Builder::tbytes(a0) + Builder::tbytes(sc_in);
       for (int k = 0; k < 4; ++k) { ak[k].prod = op; ob += Builder::tbytes(ak[k]); }
+      a0.prod = op; sc_in.prod = op;
       b.label(op, "pool_pyramid", Builder::tbytes(x) + ob);
     } else {
       for (int k = 0; k < 4; ++k) {
@@ -1007,6 +1023,9 @@ struct Engine {
                       : pool_affine(sp + ".pool", x, 0, 1, 0, bn(sp + ".1"));
       }
     }
+    T s0 = conv_plain("spp.scale0.conv", a0, "spp.scale0.2", nullptr, 1, false, nullptr);
+    T sk[4];
+
     for (int k = 0; k < 4; ++k) {
       const std::string sp = "spp.scale" + std::to_string(k + 1);
       sk[k] = conv_plain(sp + ".conv", ak[k], sp + ".3", nullptr, 1, false, nullptr);
@@ -1075,7 +1094,7 @@ struct Engine {
         comp_in.prod = w.prod;
       }
     }
-    T sc_in = affine_relu("spp.shortcut.bnrelu", x, bn("spp.shortcut.0"), nullptr);
+    if (!pyramid) sc_in = affine_relu("spp.shortcut.bnrelu", x, bn("spp.shortcut.0"), nullptr);
     std::vector<float> bias;
     std::vector<ConvSrcSpec> srcs;
     srcs.push_back(src_of(comp_in, "spp.compression.2", nullptr, 1, 1, &bias));

@@ -497,6 +497,9 @@ struct PyramidParams {
   View out[4];
   const float* s;   // [4][C]
   const float* t;
+  View ew[2];       // optional full-resolution by-products relu(se[j] * x + te[j]) (PAPPM scale0 / shortcut operands)
+  const float* se;  // [2][C]
+  const float* te;
 };
 __global__ void __launch_bounds__(256) pool_pyramid_kernel(PyramidParams p) {
   pdl_wait();
@@ -519,6 +522,16 @@ __global__ void __launch_bounds__(256) pool_pyramid_kernel(PyramidParams p) {
     float* d = sat + (static_cast<long>(h + 1) * W1 + w + 1) * 32 + g * 8;
 #pragma unroll
     for (int e = 0; e < 8; ++e) d[e] = v.v[e];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (p.ew[j].ptr) {
+        const float* sc = p.se + j * p.x.C + c0 + g * 8;
+        const float* sh = p.te + j * p.x.C + c0 + g * 8;
+        F8 o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = fmaxf(v.v[e] * __ldg(sc + e) + __ldg(sh + e), 0.f);
+        st8(p.ew[j].ptr + (static_cast<long>(n) * H * W + pix) * p.ew[j].ps + c0 + g * 8, o);
+      }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < H * 32; i += 256) {   // prefix along w
@@ -845,7 +858,8 @@ cudaError_t upadd_batch_launch(int njobs, const View* a, const View* b, const Vi
   return cudaGetLastError();
 }
 
-cudaError_t pool_pyramid_launch(View x, const View out[4], const float* s, const float* t, cudaStream_t st) {
+cudaError_t pool_pyramid_launch(View x, const View out[4], const float* s, const float* t, const View ew[2], const float* se,
+                                const float* te, cudaStream_t st) {
   if (x.C % 32 != 0) return cudaErrorNotSupported;
   const size_t smem = static_cast<size_t>(x.H + 1) * (x.W + 1) * 32 * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorNotSupported;
@@ -856,8 +870,9 @@ cudaError_t pool_pyramid_launch(View x, const View out[4], const float* s, const
     opted = 200 * 1024;
   }
   PyramidParams p;
-  p.x = x; p.s = s; p.t = t;
+  p.x = x; p.s = s; p.t = t; p.se = se; p.te = te;
   for (int i = 0; i < 4; ++i) p.out[i] = out[i];
+  for (int i = 0; i < 2; ++i) p.ew[i] = ew ? ew[i] : View{nullptr, 0, 0, 0, 0, 0};
   launch_pdl(pool_pyramid_kernel, dim3(x.N * (x.C / 32), 1, 1), dim3(256, 1, 1), smem, st, p);
   return cudaGetLastError();
 }

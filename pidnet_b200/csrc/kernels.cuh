@@ -77,7 +77,10 @@ cudaError_t upadd_batch_launch(int njobs, const View* a, const View* b, const Vi
 // pass over x: a block builds the summed-area table of a 32-channel slice of one image in shared memory (fp32) and every
 // pooled output is four table look-ups.  out[0..2]: k = 5, 9, 17; out[3]: 1x1.  s / t: the four BN affines, [4][C].
 // Returns cudaErrorNotSupported when the table does not fit in shared memory (caller falls back to pool_affine_launch).
-cudaError_t pool_pyramid_launch(View x, const View out[4], const float* s, const float* t, cudaStream_t st);
+// ew / se / te (optional): two full-resolution by-products relu(se[j] * x + te[j]) written in the same pass (PAPPM's
+// scale0 and shortcut operands), so x is read once for all six consumers.
+cudaError_t pool_pyramid_launch(View x, const View out[4], const float* s, const float* t, const View ew[2], const float* se,
+                                const float* te, cudaStream_t st);
 cudaError_t pool_affine_launch(View x, View out, int k, int stride, int pad, const float* s, const float* t, int relu,
                                cudaStream_t st);
 
