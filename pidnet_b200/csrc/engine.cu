@@ -1035,10 +1035,10 @@ struct Engine {
     if (!large) {
       const Affine asp = bn("spp.scale_process.0");
       T sp_in = b.new_tensor(x.N, x.H, x.W, 4 * ppm);
-      {   // relu(bn_k(scale0 + U(scale_k))) for the four branches in ONE launch, each into its channel slice of sp_in
-        View av[4], bv[4], ovs[4];
-        const float* sd[4];
-        const float* td[4];
+      {   // relu(bn_k(scale0 + U(scale_k))) for the four branches and relu(bn_0(scale0)) (the first slice of the compression
+          // input) in ONE launch; job 4 is "null + U(scale0)" at scale 1, an exact identity interpolation
+        std::vector<View> av(5), bv(5), ovs(5);
+        std::vector<const float*> sd(5), td(5);
         double bytes = 0;
         for (int k = 0; k < 4; ++k) {
           T dst = Builder::slice(sp_in, k * ppm, ppm);
@@ -1047,20 +1047,20 @@ struct Engine {
           sd[k] = b.upload_f32(a.s); td[k] = b.upload_f32(a.t);
           bytes += Builder::tbytes(s0) + Builder::tbytes(sk[k]) + Builder::tbytes(dst);
         }
-        const View a0 = av[0], a1 = av[1], a2 = av[2], a3 = av[3], b0 = bv[0], b1 = bv[1], b2 = bv[2], b3 = bv[3];
-        const View o0 = ovs[0], o1 = ovs[1], o2 = ovs[2], o3 = ovs[3];
-        const float *s0p = sd[0], *s1p = sd[1], *s2p = sd[2], *s3p = sd[3], *t0p = td[0], *t1p = td[1], *t2p = td[2], *t3p = td[3];
-        sp_in.prod = b.add_op("spp.scale1-4.upadd", {&s0, &sk[0], &sk[1], &sk[2], &sk[3]},
-                              [=](cudaStream_t st, const RunArgs&) {
-                                const View aa[4] = {a0, a1, a2, a3}, bb[4] = {b0, b1, b2, b3}, oo[4] = {o0, o1, o2, o3};
-                                const float* ss[4] = {s0p, s1p, s2p, s3p};
-                                const float* ts[4] = {t0p, t1p, t2p, t3p};
-                                return upadd_batch_launch(4, aa, bb, oo, ss, ts, 1, st);
+        T c0 = Builder::slice(comp_in, 0, ppm);
+        {
+          Affine a = slice(acomp, 0, ppm);
+          av[4] = View{nullptr, 0, 0, 0, 0, 0}; bv[4] = s0.view(); ovs[4] = c0.view();
+          sd[4] = b.upload_f32(a.s); td[4] = b.upload_f32(a.t);
+          bytes += Builder::tbytes(s0) + Builder::tbytes(c0);
+        }
+        sp_in.prod = b.add_op("spp.scale1-4.upadd+x_.bnrelu", {&s0, &sk[0], &sk[1], &sk[2], &sk[3]},
+                              [av, bv, ovs, sd, td](cudaStream_t st, const RunArgs&) {
+                                return upadd_batch_launch(5, av.data(), bv.data(), ovs.data(), sd.data(), td.data(), 1, st);
                               });
+        comp_in.prod = sp_in.prod;
         b.label(sp_in.prod, "upadd", bytes);
       }
-      T c0 = Builder::slice(comp_in, 0, ppm);
-      affine_relu("spp.x_.bnrelu", s0, slice(acomp, 0, ppm), &c0);
       // grouped 3x3 (groups=4, model_utils.py:230) as four convs on channel slices; epilogue applies the
       // compression BN slice + ReLU
       const HostParam& gw = P("spp.scale_process.2.weight");  // [4*ppm][ppm][3][3]

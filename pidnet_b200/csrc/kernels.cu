@@ -418,12 +418,14 @@ __global__ void __launch_bounds__(256) upadd_strip_kernel(View a, View b, View r
   pdl_launch_dependents();
   upadd_strip_body(a, b, r, out, s, t, relu, dec);
 }
-// up to four independent jobs with the same output geometry in one launch (blockIdx.y = job): the PAPPM branch adds
+// up to kUpaddJobs independent jobs with the same output geometry in one launch (blockIdx.y = job): the PAPPM branch adds
+// (a job whose `b` has the output's own size is a plain affine + ReLU: identity interpolation is exact)
+constexpr int kUpaddJobs = 5;
 struct UpaddBatch {
-  View a[4], b[4], out[4];
-  const float* s[4];
-  const float* t[4];
-  Dec dec[4];
+  View a[kUpaddJobs], b[kUpaddJobs], out[kUpaddJobs];
+  const float* s[kUpaddJobs];
+  const float* t[kUpaddJobs];
+  Dec dec[kUpaddJobs];
   int relu;
 };
 __global__ void __launch_bounds__(256) upadd_strip_batch_kernel(const __grid_constant__ UpaddBatch p) {
@@ -841,7 +843,7 @@ cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, c
 
 cudaError_t upadd_batch_launch(int njobs, const View* a, const View* b, const View* out, const float* const* s,
                                const float* const* t, int relu, cudaStream_t st) {
-  if (njobs < 1 || njobs > 4) return cudaErrorInvalidValue;
+  if (njobs < 1 || njobs > kUpaddJobs) return cudaErrorInvalidValue;
   UpaddBatch p;
   std::memset(&p, 0, sizeof(p));
   p.relu = relu;
