@@ -98,7 +98,8 @@ int pidnet_op_info(pidnet_engine* h, int i, char* name, int name_cap, char* kern
  * tcgen05 cta_group::2 for 3x3 layers with Cin >= 128) | 0 | 2 (wherever the pair instance exists);
  * "ws_stages" = 3 (default) | 2 staging buffers of the weight-stationary kernels; "use_stem2" = 2
  * (default: conv1.0 -> conv1.3 fused in one kernel, warp-specialised pipeline for 32-channel stems) | 1 (lock-step
- * fused kernel) | 0 (two kernels).  The same switches can be set for a whole
+ * fused kernel) | 0 (two kernels); "use_pyramid" = 1 (default: the pooled PAPPM / DAPPM branches from one summed-area-table
+ * kernel) | 0 (one pooling kernel per branch).  The same switches can be set for a whole
  * process with PIDNET_WS_PAIR / PIDNET_WS_STAGES / PIDNET_STEM2 (A/B measurements). */
 int pidnet_set_option(pidnet_engine* h, const char* name, int value);
 

@@ -193,6 +193,7 @@ struct Builder {
   int conv_impl = 0;
   int use_ws = 1;   // weight-stationary halo-patch kernel for 3x3 stride-1 convs
   int use_stem2 = env_int("PIDNET_STEM2", 2);       // fused conv1.0 -> conv1.3 kernel (stem2_tc.cu): 1 lock-step, 2 pipelined (C = 32)
+  int use_pyramid = env_int("PIDNET_POOL_PYRAMID", 1);   // PAPPM / DAPPM pooled branches from one summed-area-table kernel
   int use_pair = env_int("PIDNET_WS_PAIR", 1);      // CTA pairs (tcgen05 cta_group::2) where conv3_ws has the instance
   int ws_stages = env_int("PIDNET_WS_STAGES", 3);   // rotating staging buffers of the weight-stationary kernels (2 or 3)
   int num_sms = 148;
@@ -683,7 +684,7 @@ struct Engine {
   int lanes = 3;
   int conv_impl = 0;
   int use_ws = 1;
-  int use_pair = -1, ws_stages = -1, use_stem2 = -1;   // -1: builder default (environment / built-in)
+  int use_pair = -1, ws_stages = -1, use_stem2 = -1, use_pyramid = -1;   // -1: builder default (environment / built-in)
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;  // capture origin (the caller's stream may be the legacy default stream)
   // uint8 input path: per-channel table of the reference's input_transform (datasets/base_dataset.py:36-44), evaluated
@@ -972,8 +973,7 @@ struct Engine {
     const int ppm = cfg.ppm_planes, outp = cfg.planes * 4;
     static const int pk[3] = {5, 9, 17}, pstr[3] = {2, 4, 8}, pp[3] = {2, 4, 8};
     // scale branches: BN -> ReLU (after the pool) then 1x1
-    static const bool use_pyramid = env_int("PIDNET_POOL_PYRAMID", 1) != 0;
-    const bool pyramid = use_pyramid && x.C % 32 == 0 && static_cast<size_t>(x.H + 1) * (x.W + 1) * 128 <= 200 * 1024;
+    const bool pyramid = b.use_pyramid && x.C % 32 == 0 && static_cast<size_t>(x.H + 1) * (x.W + 1) * 128 <= 200 * 1024;
     T a0, sc_in;   // relu(bn(x)) operands of scale0 and of the shortcut: by-products of the pyramid kernel when it is used
     if (pyramid) {
       a0 = b.new_tensor(x.N, x.H, x.W, x.C);
@@ -1365,6 +1365,7 @@ struct Engine {
     if (use_pair >= 0) b.use_pair = use_pair;
     if (ws_stages >= 0) b.ws_stages = ws_stages;
     if (use_stem2 >= 0) b.use_stem2 = use_stem2;
+    if (use_pyramid >= 0) b.use_pyramid = use_pyramid;
     b.reset(true);
     build();  // dry pass: sizes only
     const size_t act_bytes = b.act_cur, wt_bytes = b.wt_cur;
@@ -1547,6 +1548,7 @@ int pidnet_set_option(pidnet_engine* h, const char* name, int value) {
     else if (k == "use_ws") h->e.use_ws = value ? 1 : 0;
     else if (k == "use_pair") h->e.use_pair = value ? 1 : 0;
     else if (k == "use_stem2") h->e.use_stem2 = value < 0 ? 0 : (value > 2 ? 2 : value);
+    else if (k == "use_pyramid") h->e.use_pyramid = value ? 1 : 0;
     else if (k == "ws_stages") h->e.ws_stages = value == 2 ? 2 : 3;
     else fail("unknown option '" + k + "'");
     h->e.planned = false;

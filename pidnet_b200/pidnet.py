@@ -171,7 +171,8 @@ class PIDNet(nn.Module):
         """Engine switches, applied at the next plan (include/pidnet_b200.h, pidnet_set_option):
         'conv_impl': 0 tcgen05 (default) | 1 SIMT cross-check;  'lanes': 3 (default) | 1;  'use_ws': 1 | 0;
         'use_pair': 1 (CTA-pair conv kernel for Cin >= 128, default) | 0 | 2;  'ws_stages': 3 (default) | 2;
-        'use_stem2': 2 (fused conv1.0 -> conv1.3 kernel, pipelined form for 32-channel stems; default) | 1 (lock-step) | 0."""
+        'use_stem2': 2 (fused conv1.0 -> conv1.3 kernel, pipelined form for 32-channel stems; default) | 1 (lock-step) | 0;
+        'use_pyramid': 1 (single-launch pooling pyramid, default) | 0."""
         self._options[name] = int(value)
         self._planned = None
 

@@ -68,6 +68,7 @@ CASES = [
     ('tiny_l', 5, True, 2, 128, 128),
     ('s', 19, False, 1, 256, 512),
     ('s', 19, True, 2, 128, 256),
+    ('s', 19, False, 1, 200, 328),    # ragged everywhere: 50x82 stem tiles, 25x41 / 13x21 maps, 4x6 pooling pyramid input
     ('m', 11, True, 1, 360, 480),     # CamVid geometry at half size: 45x60 -> 23x30 -> 12x15 -> 6x8 (odd sizes)
     ('l', 19, True, 1, 128, 256),
 ]
@@ -169,7 +170,7 @@ def test_forward_u8_equals_forward_of_input_transform():
         assert np.array_equal(seg.cpu().numpy(), PO.argmax_labels(want.cpu().numpy(), H, W))
 
 
-@pytest.mark.parametrize('opts', [dict(use_pair=0), dict(use_pair=2), dict(ws_stages=2), dict(use_stem2=0), dict(use_stem2=1),
+@pytest.mark.parametrize('opts', [dict(use_pair=0), dict(use_pair=2), dict(ws_stages=2), dict(use_stem2=0), dict(use_stem2=1), dict(use_pyramid=0),
                                   dict(use_ws=0), dict(use_pair=0, ws_stages=2, use_stem2=0)],
                          ids=lambda o: ','.join(f'{k}={v}' for k, v in o.items()))
 @pytest.mark.parametrize('name,shape', [('pidnet_s', (2, 3, 192, 320)), ('pidnet_m', (1, 3, 128, 192))])
