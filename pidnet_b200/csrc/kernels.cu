@@ -230,69 +230,6 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
   }
 }
 
-// --------------------------------------------------------------------------- PagFM fuse
-template <int LP>  // lanes per pixel = C/8
-__global__ void __launch_bounds__(256) pag_fuse_kernel(View x, View low, View out, int relu, Dec dec) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, dec, LP, x.W, x.H, x.N);
-  const int C = x.C, cg = ix.cg;
-  const Lerp lw = lerp_of(ix.w, low.W, dec.sw);
-  const bf16* limg = low.ptr + static_cast<long>(ix.n) * low.H * low.W * low.ps;
-  const long o0 = static_cast<long>(lw.i0) * low.ps, o1 = static_cast<long>(lw.i1) * low.ps;
-  // one low-res row, horizontally interpolated: y (channels cg*8..), z (C + cg*8..) and the scalar t (channel 2C)
-  auto hrow = [&](int row, F8& y, F8& z, float& t) {
-    y = hsample8(limg, row, low.W, low.ps, o0 + cg * 8, o1 + cg * 8, lw.l);
-    z = hsample8(limg, row, low.W, low.ps, o0 + C + cg * 8, o1 + C + cg * 8, lw.l);
-    const bf16* r = limg + static_cast<long>(row) * low.W * low.ps + 2 * C;
-    t = (1.f - lw.l) * __bfloat162float(r[o0]) + lw.l * __bfloat162float(r[o1]);
-  };
-  // rows past the image bottom (partial last strip) are clamped, computed redundantly and not stored: every lane runs
-  // all kStrip iterations, so the full-mask shuffles below are always convergent
-  const long pixn = static_cast<long>(ix.n) * x.H * x.W + ix.w;
-  uint4 xr[kStrip];
-#pragma unroll
-  for (int r = 0; r < kStrip; ++r)
-    xr[r] = __ldg(reinterpret_cast<const uint4*>(x.ptr + (pixn + static_cast<long>(min(ix.h0 + r, x.H - 1)) * x.W) * x.ps + cg * 8));
-  F8 y0, z0, y1, z1;
-  float t0 = 0.f, t1 = 0.f;
-  int r0 = -1, r1 = -1;
-#pragma unroll
-  for (int r = 0; r < kStrip; ++r) {
-    const int h = min(ix.h0 + r, x.H - 1);
-    const Lerp lh = lerp_of(h, low.H, dec.sh);
-    if (lh.i0 != r0) {
-      if (lh.i0 == r1) { y0 = y1; z0 = z1; t0 = t1; }
-      else hrow(lh.i0, y0, z0, t0);
-      r0 = lh.i0;
-    }
-    if (lh.i1 != r1) {
-      if (lh.i1 == r0) { y1 = y0; z1 = z0; t1 = t0; }
-      else hrow(lh.i1, y1, z1, t1);
-      r1 = lh.i1;
-    }
-    F8 xv;
-    xv.v[0] = __uint_as_float(xr[r].x << 16); xv.v[1] = __uint_as_float(xr[r].x & 0xFFFF0000u);
-    xv.v[2] = __uint_as_float(xr[r].y << 16); xv.v[3] = __uint_as_float(xr[r].y & 0xFFFF0000u);
-    xv.v[4] = __uint_as_float(xr[r].z << 16); xv.v[5] = __uint_as_float(xr[r].z & 0xFFFF0000u);
-    xv.v[6] = __uint_as_float(xr[r].w << 16); xv.v[7] = __uint_as_float(xr[r].w & 0xFFFF0000u);
-    const F8 yv = vlerp8(y0, y1, lh.l), zv = vlerp8(z0, z1, lh.l);
-    float dot = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dot += xv.v[e] * zv.v[e];
-#pragma unroll
-    for (int o = LP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    const float g = sigmoidf_(dot + (1.f - lh.l) * t0 + lh.l * t1);
-    F8 o;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float v = (1.f - g) * xv.v[e] + g * yv.v[e];
-      o.v[e] = relu ? fmaxf(v, 0.f) : v;
-    }
-    if (ix.valid && ix.h0 + r < x.H) st8(out.ptr + (pixn + static_cast<long>(h) * x.W) * out.ps + cg * 8, o);
-  }
-}
-
 // --------------------------------------------------------------------------- upadd / affine
 __global__ void __launch_bounds__(256) upadd_kernel(View a, View b, View r, View out, const float* __restrict__ s,
                                                     const float* __restrict__ t, int relu, Dec dec) {
@@ -578,70 +515,10 @@ __global__ void __launch_bounds__(256) pool_pyramid_kernel(PyramidParams p) {
   }
 }
 
-// --------------------------------------------------------------------------- Light_Bag / Bag
-// (strip walk: the x8 upsample of the PPM output costs 4 row gathers per 8 pixels instead of 32 corner gathers)
-template <bool kBag>
-__global__ void __launch_bounds__(256) bag_strip_kernel(View p, View il, View d, View out, const float* __restrict__ s,
-                                                        const float* __restrict__ t, Dec dec) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const StripIdx ix = strip_decode(blockIdx.x * blockDim.x + threadIdx.x, dec, p.C >> 3, p.W, p.H, p.N);
-  if (!ix.valid) return;
-  const int cg = ix.cg;
-  const Lerp lw = lerp_of(ix.w, il.W, dec.sw);
-  const bf16* limg = il.ptr + static_cast<long>(ix.n) * il.H * il.W * il.ps;
-  const long o0 = static_cast<long>(lw.i0) * il.ps + cg * 8, o1 = static_cast<long>(lw.i1) * il.ps + cg * 8;
-  const long pixn = static_cast<long>(ix.n) * p.H * p.W + ix.w;
-  const int rows = min(kStrip, p.H - ix.h0);
-  uint4 pr[kStrip], dr[kStrip];
-#pragma unroll
-  for (int k = 0; k < kStrip; ++k) {
-    if (k < rows) {
-      const long pix = pixn + static_cast<long>(ix.h0 + k) * p.W;
-      pr[k] = __ldg(reinterpret_cast<const uint4*>(p.ptr + pix * p.ps + cg * 8));
-      dr[k] = __ldg(reinterpret_cast<const uint4*>(d.ptr + pix * d.ps + cg * 8));
-    }
-  }
-  F8 sc, sh;
-  if (kBag) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { sc.v[e] = __ldg(s + cg * 8 + e); sh.v[e] = __ldg(t + cg * 8 + e); }
-  }
-  RowPair rp;
-#pragma unroll
-  for (int k = 0; k < kStrip; ++k) {
-    if (k < rows) {
-      const int h = ix.h0 + k;
-      const Lerp lh = lerp_of(h, il.H, dec.sh);
-      rp.advance(lh, [&](int row) { return hsample8(limg, row, il.W, il.ps, o0, o1, lw.l); });
-      const F8 iv = vlerp8(rp.a, rp.b, lh.l);
-      const F8 pv = cvt8(pr[k]), dv = cvt8(dr[k]);
-      bf16* op = out.ptr + (pixn + static_cast<long>(h) * p.W) * out.ps + cg * 8;
-      if (kBag) {
-        F8 o;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float g = sigmoidf_(dv.v[e]);
-          const float a = g * pv.v[e] + (1.f - g) * iv.v[e];
-          o.v[e] = fmaxf(a * sc.v[e] + sh.v[e], 0.f);
-        }
-        st8(op, o);
-      } else {
-        F8 u, v;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float g = sigmoidf_(dv.v[e]);
-          u.v[e] = (1.f - g) * iv.v[e] + pv.v[e];
-          v.v[e] = iv.v[e] + g * pv.v[e];
-        }
-        st8(op, u);
-        st8(op + p.C, v);
-      }
-    }
-  }
-}
-
-// ---- flat (one thread per pixel x 8 channels) forms, the default for PagFM / Light_Bag: measured faster than their strip forms, which need 152 registers (PIDNET_ELTWISE_STRIP=1 selects those)
+// --------------------------------------------------------------------------- PagFM fuse, Light_Bag / Bag
+// One thread per pixel x 8 channels.  (Strip-walk forms of these three kernels -- as upadd_strip_kernel above -- were
+// measured and dropped: fewer instructions, but 152 registers left 12 % occupancy: PagFM 0.20 vs 0.15 ms, Light_Bag 0.31
+// vs 0.25 ms, Bag 0.68 ms on PIDNet-L.)
 template <int LP>  // lanes per pixel = C/8
 __global__ void __launch_bounds__(256) pag_fuse_flat_kernel(View x, View low, View out, int relu, Dec dec) {
   pdl_wait();
@@ -792,32 +669,16 @@ cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, cons
 cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t st) {
   const int LP = x.C / 8;
   if (static_cast<long>(x.N) * x.H * x.W * LP + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic
-  static const bool flat = getenv("PIDNET_ELTWISE_STRIP") == nullptr;
   if (static_cast<long>(low.H) * low.W * low.ps >= (1L << 31)) return cudaErrorInvalidValue;   // 32-bit offsets inside an image
-  const Dec dflat = make_dec(LP, x.W, x.H, low.H, x.H, low.W, x.W);
-  const Dec dstrip = make_dec(LP, x.W, (x.H + kStrip - 1) / kStrip, low.H, x.H, low.W, x.W);
-  if (flat) {
-    const unsigned nbf = blocks_for(static_cast<long>(x.N) * x.H * x.W * LP, 256);
-    switch (LP) {
-      case 1: launch_pdl(pag_fuse_flat_kernel<1>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
-      case 2: launch_pdl(pag_fuse_flat_kernel<2>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
-      case 4: launch_pdl(pag_fuse_flat_kernel<4>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
-      case 8: launch_pdl(pag_fuse_flat_kernel<8>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
-      case 16: launch_pdl(pag_fuse_flat_kernel<16>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
-      case 32: launch_pdl(pag_fuse_flat_kernel<32>, dim3(nbf, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dflat); break;
-      default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
-  }
-  const long total = static_cast<long>(x.N) * ((x.H + kStrip - 1) / kStrip) * x.W * LP;   // one thread per strip
-  const unsigned nb = blocks_for(total, 256);
+  const Dec dec = make_dec(LP, x.W, x.H, low.H, x.H, low.W, x.W);
+  const dim3 grid(blocks_for(static_cast<long>(x.N) * x.H * x.W * LP, 256), 1, 1), block(256, 1, 1);
   switch (LP) {
-    case 1: launch_pdl(pag_fuse_kernel<1>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
-    case 2: launch_pdl(pag_fuse_kernel<2>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
-    case 4: launch_pdl(pag_fuse_kernel<4>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
-    case 8: launch_pdl(pag_fuse_kernel<8>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
-    case 16: launch_pdl(pag_fuse_kernel<16>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
-    case 32: launch_pdl(pag_fuse_kernel<32>, dim3(nb, 1, 1), dim3(256, 1, 1), 0, st, x, low, out, relu, dstrip); break;
+    case 1: launch_pdl(pag_fuse_flat_kernel<1>, grid, block, 0, st, x, low, out, relu, dec); break;
+    case 2: launch_pdl(pag_fuse_flat_kernel<2>, grid, block, 0, st, x, low, out, relu, dec); break;
+    case 4: launch_pdl(pag_fuse_flat_kernel<4>, grid, block, 0, st, x, low, out, relu, dec); break;
+    case 8: launch_pdl(pag_fuse_flat_kernel<8>, grid, block, 0, st, x, low, out, relu, dec); break;
+    case 16: launch_pdl(pag_fuse_flat_kernel<16>, grid, block, 0, st, x, low, out, relu, dec); break;
+    case 32: launch_pdl(pag_fuse_flat_kernel<32>, grid, block, 0, st, x, low, out, relu, dec); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -893,28 +754,16 @@ cudaError_t pool_affine_launch(View x, View out, int k, int stride, int pad, con
 cudaError_t lightbag_uv_launch(View p, View i_low, View d, View out, cudaStream_t st) {
   const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
   if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
-  static const bool flat = getenv("PIDNET_ELTWISE_STRIP") == nullptr;
-  if (flat) {
-    launch_pdl(lightbag_uv_flat_kernel, dim3(blocks_for(total, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out,
-                                                                     make_dec(p.C / 8, p.W, p.H, i_low.H, p.H, i_low.W, p.W));
-    return cudaGetLastError();
-  }
-  const long strips = static_cast<long>(p.N) * ((p.H + kStrip - 1) / kStrip) * p.W * (p.C / 8);
-  launch_pdl(bag_strip_kernel<false>, dim3(blocks_for(strips, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out, nullptr, nullptr, make_dec(p.C / 8, p.W, (p.H + kStrip - 1) / kStrip, i_low.H, p.H, i_low.W, p.W));
+  launch_pdl(lightbag_uv_flat_kernel, dim3(blocks_for(total, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out,
+             make_dec(p.C / 8, p.W, p.H, i_low.H, p.H, i_low.W, p.W));
   return cudaGetLastError();
 }
 
 cudaError_t bag_blend_launch(View p, View i_low, View d, View out, const float* s, const float* t, cudaStream_t st) {
   const long total = static_cast<long>(p.N) * p.H * p.W * (p.C / 8);
   if (total + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic in the kernel
-  const long strips = static_cast<long>(p.N) * ((p.H + kStrip - 1) / kStrip) * p.W * (p.C / 8);
-  static const bool flat = getenv("PIDNET_ELTWISE_STRIP") == nullptr;
-  if (flat) {   // (measured on PIDNet-L: strip form 0.68 ms at 152 registers, flat form below)
-    launch_pdl(bag_blend_flat_kernel, dim3(blocks_for(total, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out, s, t,
-                                                                   make_dec(p.C / 8, p.W, p.H, i_low.H, p.H, i_low.W, p.W));
-    return cudaGetLastError();
-  }
-  launch_pdl(bag_strip_kernel<true>, dim3(blocks_for(strips, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out, s, t, make_dec(p.C / 8, p.W, (p.H + kStrip - 1) / kStrip, i_low.H, p.H, i_low.W, p.W));
+  launch_pdl(bag_blend_flat_kernel, dim3(blocks_for(total, 256), 1, 1), dim3(256, 1, 1), 0, st, p, i_low, d, out, s, t,
+             make_dec(p.C / 8, p.W, p.H, i_low.H, p.H, i_low.W, p.W));
   return cudaGetLastError();
 }
 
