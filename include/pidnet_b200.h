@@ -41,6 +41,9 @@ typedef struct pidnet_cfg {
 const char* pidnet_last_error(void);
 /* ABI version of this header (bumped on any signature change). */
 int pidnet_abi_version(void);
+/* Test hook (host only): n / d computed with the launch-time magic-number division the elementwise kernels use to decode
+ * their thread index; must equal n / d for every 32-bit n and every d >= 1 (tests/test_host.py). */
+unsigned pidnet_debug_fastdiv(unsigned n, unsigned d);
 
 /* replaces PIDNet.__init__ (models/pidnet.py:19-100): creates an engine for one model topology. */
 int pidnet_create(const pidnet_cfg* cfg, pidnet_engine** out);

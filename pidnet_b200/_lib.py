@@ -28,6 +28,7 @@ _vp, _fp, _i, _i64p = C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_i
 SIGNATURES = {
     'pidnet_last_error': (C.c_char_p, []),
     'pidnet_abi_version': (_i, []),
+    'pidnet_debug_fastdiv': (C.c_uint, [C.c_uint, C.c_uint]),
     'pidnet_create': (_i, [C.POINTER(Cfg), C.POINTER(_vp)]),
     'pidnet_destroy': (_i, [_vp]),
     'pidnet_set_param': (_i, [_vp, C.c_char_p, _vp, _i64p, _i]),

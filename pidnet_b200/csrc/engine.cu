@@ -1507,6 +1507,7 @@ extern "C" {
 
 const char* pidnet_last_error(void) { return g_err.c_str(); }
 int pidnet_abi_version(void) { return 1; }
+unsigned pidnet_debug_fastdiv(unsigned n, unsigned d) { return d ? fastdiv_debug(n, d) : 0u; }
 
 int pidnet_create(const pidnet_cfg* cfg, pidnet_engine** out) {
   return guard([&] {

@@ -50,6 +50,13 @@ inline FastDiv make_fastdiv(uint32_t d) {
   }
   return f;
 }
+// host restatement of fdiv() for the CPU test suite (pidnet_debug_fastdiv): exactness of the magic numbers is what every
+// elementwise kernel's index decode rests on
+uint32_t fastdiv_host(uint32_t n, uint32_t d) {
+  const FastDiv f = make_fastdiv(d);
+  const uint32_t t = static_cast<uint32_t>((static_cast<uint64_t>(f.mul) * n) >> 32);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
   const uint32_t t = __umulhi(f.mul, n);
   return (t + ((n - t) >> f.sh1)) >> f.sh2;
@@ -651,6 +658,8 @@ __global__ void __launch_bounds__(128) conv_ref_kernel(const ConvRefParams p) {
 inline unsigned blocks_for(long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
 }  // namespace
+
+uint32_t fastdiv_debug(uint32_t n, uint32_t d) { return fastdiv_host(n, d); }
 
 cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, const float* w, const float* bias,
                              cudaStream_t st) {

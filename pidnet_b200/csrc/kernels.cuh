@@ -69,6 +69,9 @@ cudaError_t upadd_launch(View a, View b, View out, const float* s, const float* 
 cudaError_t upadd_res_launch(View a, View b, View r, View out, const float* s, const float* t, int relu, cudaStream_t st);
 
 // ---- average pool (count_include_pad) + affine + ReLU; k == 0 means global average pool
+// n / d through the launch-time magic-number division the elementwise kernels decode their thread index with (host copy)
+uint32_t fastdiv_debug(uint32_t n, uint32_t d);
+
 // up to five upsample-add jobs of identical output geometry in ONE launch (PAPPM: relu(bn_k(scale0 + U(scale_k))), k = 1..4,
 // and relu(bn_0(scale0)) as the job "null + U(scale0)" whose interpolation is the identity)
 cudaError_t upadd_batch_launch(int njobs, const View* a, const View* b, const View* out, const float* const* s,

@@ -137,3 +137,20 @@ def test_shard_ranges_partition_the_batch():
             assert b == c and a <= b and c <= d
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_fastdiv_is_exact():
+    """The elementwise kernels decode (channel group, w, h, n) from the thread index with a launch-time magic-number division
+    (Granlund-Montgomery round-up, kernels.cu); a wrong quotient would silently permute pixels.  Exhaustive over small n for
+    every divisor the engine can meet (channel groups, widths, heights up to 4096) plus edge and random 32-bit dividends."""
+    import random
+    lib = _lib.load()
+    rng = random.Random(0)
+    edge = [0, 1, 2, 2 ** 16 - 1, 2 ** 16, 2 ** 31 - 1, 2 ** 31, 2 ** 32 - 2, 2 ** 32 - 1]
+    for d in list(range(1, 4097)) + [2 ** 20 + 7, 2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1]:
+        ns = edge + [d - 1, d, d + 1, 2 * d - 1, 2 * d, 3 * d + 1] + [rng.randrange(2 ** 32) for _ in range(24)]
+        if d <= 64:
+            ns += list(range(0, 1024))
+        for n in ns:
+            n &= 0xFFFFFFFF
+            assert lib.pidnet_debug_fastdiv(n, d) == n // d, (n, d)
