@@ -146,8 +146,12 @@ int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d,
  * MODEL.ALIGN_CORNERS=True, TRAIN.IGNORE_LABEL) are passed explicitly.
  *   x_p, x_m, x_d : device fp32 NCHW low-res logits [N,C,h,w], [N,C,h,w], [N,1,h,w] (the three PIDNet outputs)
  *   labels        : device int64 [N,H,W];  bd_gt: device fp32 [N,H,W] (0/1)
- *   out12 (device fp32[12]): loss (== losses.mean()), loss_s (== loss_list[0].mean()), loss_b, pixel acc,
- *                   ohem(x_,labels), ohem(x_,bd_label), the two OHEM thresholds, the two valid counts, |K1|, |K2|
+ *   out16 (device fp32[16]): loss (== losses.mean()), loss_s (== loss_list[0].mean()), loss_b, pixel acc (over label >= 0
+ *                   pixels, utils/utils.py:29-35), ohem(x_,labels), ohem(x_,bd_label), the two OHEM thresholds, the two valid
+ *                   counts, |K1|, |K2|, [12] = number of labels that are neither ignore_label nor in [0, C) (the reference's
+ *                   gather faults on them: such pixels are dropped, never used as an index, and the loss is NaN),
+ *                   [13] = number of labels >= 0, [14..15] reserved.  An empty OHEM set (the reference raises IndexError,
+ *                   utils/criterion.py:73) gives a NaN loss and contributes no gradient.
  *   grad_*        : optional device fp32 buffers shaped like the logits; receive d(loss.mean())/d(logits)
  * No host synchronisation; `workspace` needs pidnet_criterion_workspace_bytes(N,H,W) device bytes. */
 typedef struct pidnet_criterion_cfg {
@@ -163,7 +167,7 @@ typedef struct pidnet_criterion_cfg {
 size_t pidnet_criterion_workspace_bytes(int N, int H, int W);
 int pidnet_criterion(void* stream, const float* x_p, const float* x_m, const float* x_d, int N, int C, int h, int w,
                      const int64_t* labels, const float* bd_gt, int H, int W, const float* class_weights,
-                     const pidnet_criterion_cfg* cfg, void* workspace, size_t workspace_bytes, float* out12,
+                     const pidnet_criterion_cfg* cfg, void* workspace, size_t workspace_bytes, float* out16,
                      float* grad_p, float* grad_m, float* grad_d);
 /* F.interpolate(x, size=(H,W), mode='bilinear', align_corners=True) on fp32 NCHW (utils/utils.py:44-46) */
 int pidnet_upsample_align_corners(void* stream, const float* x, int NC, int h, int w, float* out, int H, int W);
@@ -175,16 +179,34 @@ int pidnet_upsample_align_corners(void* stream, const float* x, int NC, int h, i
  * caller's fp32 gradient buffers.  Parameters are BOUND, not copied: `dev_param` / `dev_grad` point at the storage of
  * the torch parameters (and of the running_mean / running_var buffers, dev_grad = NULL), keys are the reference
  * state_dict keys.  Gradients of different ranks are summed by the caller (NCCL all-reduce of the flat buffer).
- * S/M topologies (m == 2), augment = 1. */
+ * S, M and L topologies, augment = 1. */
 typedef struct pidnet_trainer pidnet_trainer;
 int pidnet_train_create(const pidnet_cfg* cfg, pidnet_trainer** out);
 int pidnet_train_destroy(pidnet_trainer* h);
 int pidnet_train_bind(pidnet_trainer* h, const char* key, float* dev_param, float* dev_grad, const int64_t* shape, int ndim);
 int pidnet_train_plan(pidnet_trainer* h, int N, int H, int W, size_t* arena_bytes);
-/* out12: device fp32[12] as in pidnet_criterion; out_main/out_p/out_d: optional device copies of the low-res logits */
+/* out16: device fp32[16] as in pidnet_criterion; out_main/out_p/out_d: optional device copies of the low-res logits.
+ * backward: 1 = forward + criterion + backward of everything in this call; 0 = forward + criterion values only;
+ *           2 = forward + criterion values AND logit gradients, the network backward is left to pidnet_train_backward
+ *               (this is how `loss.backward()` of the reference loop, utils/function.py:47, triggers it). */
 int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x_nchw, const int64_t* labels, const float* bd_gt,
-                      const float* class_weights, const pidnet_criterion_cfg* cfg, int backward, float* out12,
+                      const float* class_weights, const pidnet_criterion_cfg* cfg, int backward, float* out16,
                       float* out_main, float* out_p, float* out_d);
+/* Backward of the last train-mode forward of this handle (pidnet_train_forward, or pidnet_train_step with backward 0 / 2):
+ * what autograd runs for `outputs = self.model(inputs)` (utils/utils.py:39) when a loss built on the three outputs calls
+ * .backward().  g_main / g_p / g_d: device fp32 gradients w.r.t. x_ / x_extra_p / x_extra_d shaped like the logits, or all
+ * NULL to use the gradients the engine's own criterion left behind (backward = 2).  x_nchw: the image of that forward (the
+ * stem's weight gradient reads it).  segment: -1 = the whole backward; k in [0, pidnet_train_num_segments) = the k-th of
+ * the consecutive op ranges the backward is split into -- call them in order; after range k the flat-gradient ranges
+ * reported by pidnet_train_segment_ranges(k) are final, so the caller can overlap their all-reduce with range k+1
+ * (SURVEY 8e "bucketed in reverse layer order"; replaces DataParallel's reduce, tools/train.py:136). */
+int pidnet_train_backward(pidnet_trainer* h, void* stream, const float* x_nchw, const float* g_main, const float* g_p,
+                          const float* g_d, int segment);
+int pidnet_train_num_segments(pidnet_trainer* h);
+/* begin_end: int64 pairs [begin, end) in floats relative to grad_base (the start of the caller's flat gradient buffer);
+ * begin_end may be NULL to query n_pairs only. */
+int pidnet_train_segment_ranges(pidnet_trainer* h, int segment, const float* grad_base, int64_t* begin_end, int cap_pairs,
+                                int* n_pairs);
 /* PIDNet.forward in train mode (models/pidnet.py:136-182 with nn.BatchNorm2d in training mode): batch statistics, running
  * statistics updated, the three low-res outputs copied to the optional device buffers; no criterion, no backward */
 int pidnet_train_forward(pidnet_trainer* h, void* stream, const float* x_nchw, float* out_main, float* out_p, float* out_d);
@@ -192,7 +214,8 @@ int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd);
 /* options: "use_graph" 1 (default: the step replays two CUDA graphs after one eager step) | 0 (eager launches);
  *          "overlap_wgrad" 1 (default: weight-gradient GEMMs run on a side stream next to the dgrad chain) | 0;
  *          "fused_bn" 1 (default: single-launch BatchNorm kernels with a grid barrier) | 0 (3-kernel form; re-plan);
- *          "wgrad_halo" 1 (default: halo-patch weight-gradient kernel for 3x3 stride-1 convs) | 0 (tap-by-tap; re-plan) */
+ *          "wgrad_halo" 1 (default: halo-patch weight-gradient kernel for 3x3 stride-1 convs) | 0 (tap-by-tap; re-plan);
+ *          "bwd_segments" 4 (default) .. 16: number of ranges pidnet_train_backward splits the backward into */
 int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value);
 int pidnet_train_profile(pidnet_trainer* h, void* stream, const float* x_nchw, const int64_t* labels, const float* bd_gt,
                          const float* class_weights, const pidnet_criterion_cfg* cfg, char* buf, size_t cap, float* crit_ms);
@@ -218,17 +241,6 @@ int pidnet_postprocess(void* stream, const float* logits, int N, int C, int h, i
  * The poly learning-rate schedule of utils/utils.py:154-160 is host arithmetic (pidnet_b200/optim.py:adjust_learning_rate). */
 int pidnet_sgd_step(void* stream, float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                     float dampening, float weight_decay, int nesterov, int first_step, float grad_scale);
-
-/* Hardware probe used by tools/probe_halo.py (documents how tcgen05 reads shifted windows of a
- * TMA-written halo patch; not on the product path). */
-int pidnet_probe_halo(void* stream, const void* x_18x10x64_bf16, const void* w_64x64_bf16, int r, int s, int mode,
-                      float* out_128x64);
-
-int pidnet_probe_mn(void* stream, const void* a_64x128_bf16, const void* b_64x64_bf16, int lbo, int sbo, float* out_128x64);
-int pidnet_probe_mma_rate(void* stream, int N, int iters, int distinct, int blocks, long long* out_cycles_dev);
-/* CTA-pair (tcgen05 cta_group::2, M = 256) probes: operand-split convention and MMA rate (tools/probe_pair.py). */
-int pidnet_probe_pair(void* stream, const void* a_256x64_bf16, const void* b_64x64_bf16, int swap_b, float* out_256x64);
-int pidnet_probe_mma_rate_pair(void* stream, int N, int iters, int distinct, int pairs, long long* out_cycles_dev);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,9 @@ SIGNATURES = {
     'pidnet_train_bind': (_i, [_vp, C.c_char_p, _vp, _vp, _i64p, _i]),
     'pidnet_train_plan': (_i, [_vp, _i, _i, _i, C.POINTER(C.c_size_t)]),
     'pidnet_train_step': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(CriterionCfg), _i, _vp, _vp, _vp, _vp]),
+    'pidnet_train_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    'pidnet_train_num_segments': (_i, [_vp]),
+    'pidnet_train_segment_ranges': (_i, [_vp, _i, _vp, _i64p, _i, C.POINTER(_i)]),
     'pidnet_train_profile': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(CriterionCfg), C.c_char_p, C.c_size_t, C.POINTER(C.c_float)]),
     'pidnet_train_debug_tensor': (_i, [_vp, C.c_char_p, _i, _vp, _i64p]),
     'pidnet_train_num_launches': (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
@@ -64,15 +67,36 @@ SIGNATURES = {
     'pidnet_train_set_option': (_i, [_vp, C.c_char_p, _i]),
     'pidnet_postprocess': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_int64, _vp, _vp]),
     'pidnet_sgd_step': (_i, [_vp, _vp, _vp, _vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, _i, _i, C.c_float]),
+    'pidnet_op_bag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+}
+
+# hardware probes (include/pidnet_b200_probe.h): only in libpidnet_b200_probe.so, built on demand for tools/probe_*.py
+PROBE_SIGNATURES = {
     'pidnet_probe_mn': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     'pidnet_probe_mma_rate': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'pidnet_probe_pair': (_i, [_vp, _vp, _vp, _i, _vp]),
     'pidnet_probe_mma_rate_pair': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'pidnet_probe_halo': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
-    'pidnet_op_bag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
+PROBE_LIB_PATH = os.path.join(_HERE, 'lib', 'libpidnet_b200_probe.so')
 
 _lib = None
+_probe_lib = None
+
+
+def load_probe():
+    """The probe build (product sources + csrc/probe.cu with -DPIDNET_PROBES); `python -m pidnet_b200.build --probes`."""
+    global _probe_lib
+    if _probe_lib is None:
+        if not os.path.exists(PROBE_LIB_PATH):
+            raise RuntimeError(f'pidnet_b200: {PROBE_LIB_PATH} is missing -- build it with `python -m pidnet_b200.build --probes`')
+        lib = C.CDLL(PROBE_LIB_PATH)
+        for name, (res, args) in {**SIGNATURES, **PROBE_SIGNATURES}.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _probe_lib = lib
+    return _probe_lib
 
 
 def load():

@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libpidnet_b200.so')
-SOURCES = ['conv_tc.cu', 'conv3_ws.cu', 'stem_tc.cu', 'stem2_tc.cu', 'criterion.cu', 'train_kernels.cu', 'wgrad_tc.cu', 'kernels.cu', 'engine.cu', 'probe.cu']
+PROBE_LIB = os.path.join(HERE, 'lib', 'libpidnet_b200_probe.so')
+SOURCES = ['conv_tc.cu', 'conv3_ws.cu', 'stem_tc.cu', 'stem2_tc.cu', 'criterion.cu', 'train_kernels.cu', 'wgrad_tc.cu', 'kernels.cu', 'engine.cu']
 HEADERS = ['conv_tc.cuh', 'kernels.cuh', 'ptx.cuh', 'criterion.cuh', 'train_kernels.cuh', 'train.inc', os.path.join('..', '..', 'include', 'pidnet_b200.h')]
 
 
@@ -31,18 +32,23 @@ def needs_build():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, probes=False):
+    """probes=True builds libpidnet_b200_probe.so instead: the same sources + csrc/probe.cu with -DPIDNET_PROBES (hardware
+    probes for tools/probe_*.py; the product library never contains them)."""
+    lib = PROBE_LIB if probes else LIB
+    if not force and not probes and not needs_build():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     objs = []
     common = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
+    if probes:
+        common += ['-DPIDNET_PROBES']
     if verbose:
         common += ['-Xptxas', '-v']
     procs = []
-    for s in SOURCES:
-        o = os.path.join(HERE, 'lib', s.replace('.cu', '.o'))
+    for s in SOURCES + (['probe.cu'] if probes else []):
+        o = os.path.join(HERE, 'lib', s.replace('.cu', '.probe.o' if probes else '.o'))
         objs.append(o)
         cmd = [_nvcc()] + common + ['-c', os.path.join(CSRC, s), '-o', o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -52,13 +58,13 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-cudart', 'static', '-Xcompiler', '-fPIC']
+    cmd = [_nvcc(), '-shared', '-o', lib] + objs + ['-cudart', 'static', '-Xcompiler', '-fPIC']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError('link failed: ' + ' '.join(cmd))
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, probes='--probes' in sys.argv))

@@ -73,7 +73,7 @@ class FusedCriterion:
             self._ws = torch.empty(need, dtype=torch.uint8, device=x_m.device)
         wt = self.sem_loss.criterion.weight
         wt = wt.to(x_m.device, torch.float32).contiguous() if wt is not None else None
-        out = torch.empty(12, dtype=torch.float32, device=x_m.device)
+        out = torch.empty(16, dtype=torch.float32, device=x_m.device)
         grads = [torch.empty_like(t) for t in (x_p, x_m, x_d)] if need_grads else [None, None, None]
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         stream = torch.cuda.current_stream(x_m.device).cuda_stream
@@ -123,15 +123,14 @@ class FullModel(nn.Module):
     def _train_forward(self, inputs, labels, bd_gt):
         """Train mode: one engine call does forward (BN batch statistics), criterion and backward; the returned
         loss is attached to autograd so `loss.mean().backward()` delivers the parameter gradients."""
-        from .train import EngineTrainer, _TrainStepFn
+        from .train import _TrainStepFn
         from .pidnet import PIDNet
         if not isinstance(self.model, PIDNet):
             raise TypeError('pidnet_b200.FullModel trains pidnet_b200.PIDNet models only (call .eval() for loss evaluation)')
         trainer = self.model.engine_trainer()
-        names = [k for k, _ in self.model.named_parameters()]
         params = [p for _, p in self.model.named_parameters()]
         wt = self.sem_loss.criterion.weight
-        res = _TrainStepFn.apply(trainer, inputs, labels, bd_gt, wt, self._crit.cfg, names, *params)
+        res = _TrainStepFn.apply(trainer, inputs, labels, bd_gt, wt, self._crit.cfg, *params)
         loss, out12, x_p, x_m, x_d = res
         h, w = labels.size(1), labels.size(2)
         ups = [upsample_align_corners(o, (h, w)) for o in (x_p, x_m)] if self.return_outputs else []
@@ -142,7 +141,16 @@ class FullModel(nn.Module):
         """The `EngineTrainer` behind the train-mode forward (created on first use)."""
         return self.model.engine_trainer()
 
-    def check_valid(self, out):
-        """The reference raises IndexError when an OHEM set has no valid pixel (criterion.py:73)."""
-        if float(out[8]) == 0 or float(out[9]) == 0:
+    def check_valid(self, out=None):
+        """The reference raises IndexError when an OHEM set has no valid pixel (utils/criterion.py:73) and faults on labels
+        outside [0, C).  The fused criterion reports both without a host sync: the loss turns NaN, an empty selection
+        contributes no gradient, and the trainer raises at its next step; call this to raise NOW (synchronises)."""
+        if out is None:
+            if getattr(self.model, '_engine_trainer', None) is not None:
+                self.model._engine_trainer.poll_errors(wait=True)
+            return
+        o = out.detach().cpu()
+        if o.numel() > 12 and float(o[12]) > 0:
+            raise RuntimeError(f'pidnet_b200: {int(o[12])} label(s) are neither ignore_label nor in [0, num_classes)')
+        if float(o[8]) == 0 or float(o[9]) == 0:
             raise IndexError('index -1 is out of bounds for dimension 0 with size 0')

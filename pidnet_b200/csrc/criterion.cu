@@ -21,8 +21,10 @@ namespace {
 constexpr int kMaxC = 32;
 
 // accumulator slots (double)
-enum { A_CE_P = 0, A_ACC, A_BCE_POS, A_BCE_NEG, A_NPOS, A_NNEG, A_NV1, A_NV2, A_NLT1, A_NLT2, A_S1, A_S2, A_K1, A_K2,
-       A_COUNT };
+// [0, A_PIXEND) are filled by the per-pixel pass: A_NGE0 counts labels >= 0 (the denominator of pixel_acc, utils/utils.py:31-34),
+// A_NBAD labels that are neither ignore_label nor a class index (the reference's gather would fault on them)
+enum { A_CE_P = 0, A_ACC, A_BCE_POS, A_BCE_NEG, A_NPOS, A_NNEG, A_NV1, A_NV2, A_NLT1, A_NLT2, A_NGE0, A_NBAD, A_PIXEND,
+       A_S1 = A_PIXEND, A_S2, A_K1, A_K2, A_COUNT };
 // select state (per OHEM set s): u32 [need, prefix, rank, thr_bits]
 struct SelState {
   unsigned need[2], prefix[2], rank[2];
@@ -86,18 +88,22 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // CMAX: compile-time bound of the class loop (logits stay in registers; no dynamically indexed arrays)
 template <int CMAX>
 __global__ void __launch_bounds__(256) crit_pixel_kernel(CritParams p) {
-  __shared__ double red[A_NLT2 + 1][8];
+  __shared__ double red[A_PIXEND][8];
   const long npix = static_cast<long>(p.N) * p.H * p.W;
   const long pix = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   // every slot receives at most one value per thread: the warp reduction runs in fp32 (exact for the
   // counters, one rounding for the losses), the cross-warp / cross-block accumulation in fp64
-  float acc[A_NLT2 + 1];
+  float acc[A_PIXEND];
 #pragma unroll
-  for (int i = 0; i <= A_NLT2; ++i) acc[i] = 0.f;
+  for (int i = 0; i < A_PIXEND; ++i) acc[i] = 0.f;
   if (pix < npix) {
     const PixelCtx c = make_ctx(pix, p.H, p.W, p.h, p.w);
     const long t64 = p.labels[pix];
-    const bool valid1 = t64 != p.ignore_label;
+    // a label that is neither ignore_label nor a class index is never used as an index: the pixel is dropped and counted
+    const bool inrange = t64 >= 0 && t64 < p.C;
+    const bool valid1 = t64 != p.ignore_label && inrange;
+    if (t64 != p.ignore_label && !inrange) acc[A_NBAD] = 1.f;
+    if (t64 >= 0) acc[A_NGE0] = 1.f;
     const int t = valid1 ? static_cast<int>(t64) : 0;
     const size_t plane = static_cast<size_t>(p.h) * p.w;
     const float* xm = p.x_m + static_cast<size_t>(c.n) * p.C * plane;
@@ -153,12 +159,12 @@ __global__ void __launch_bounds__(256) crit_pixel_kernel(CritParams p) {
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int i = 0; i <= A_NLT2; ++i) {
+  for (int i = 0; i < A_PIXEND; ++i) {
     const float v = warp_sum_f(acc[i]);
     if (lane == 0) red[i][warp] = static_cast<double>(v);
   }
   __syncthreads();
-  if (threadIdx.x <= A_NLT2) {
+  if (threadIdx.x < A_PIXEND) {
     double v = 0.0;
     for (int q = 0; q < 8; ++q) v += red[threadIdx.x][q];
     if (v != 0.0) atomicAdd(p.accum + threadIdx.x, v);
@@ -264,10 +270,16 @@ __global__ void crit_final_kernel(CritParams p, const SelState* st) {
   const double loss_b = p.coeff_bce * bce;
   const double loss_s = aux + p.bw1 * ohem1;
   float* o = p.out;
-  o[0] = static_cast<float>(loss_s + loss_b + p.sb * ohem2);   // == losses.mean() of the reference
-  o[1] = static_cast<float>(loss_s);                           // == loss_list[0].mean()
+  // out-of-range labels: the reference's gather faults (device assert); here the loss is poisoned and o[12] reports the count
+  const double poison = a[A_NBAD] > 0 ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+  o[0] = static_cast<float>(loss_s + loss_b + p.sb * ohem2 + poison);   // == losses.mean() of the reference
+  o[1] = static_cast<float>(loss_s + poison);                           // == loss_list[0].mean()
   o[2] = static_cast<float>(loss_b);
-  o[3] = static_cast<float>(a[A_ACC] / (nhw + 1e-10));
+  o[3] = static_cast<float>(a[A_ACC] / (a[A_NGE0] + 1e-10));            // pixel_acc: label >= 0 pixels, utils/utils.py:29-35
+  o[12] = static_cast<float>(a[A_NBAD]);
+  o[13] = static_cast<float>(a[A_NGE0]);
+  o[14] = 0.f;
+  o[15] = 0.f;
   o[4] = static_cast<float>(ohem1);
   o[5] = static_cast<float>(ohem2);
   o[6] = st->thr[0];
@@ -327,8 +339,8 @@ __global__ void __launch_bounds__(256) crit_backward_kernel(CritParams p, const 
       // main head: coefficient from both OHEM selections
       const float pm = p.ws_p[pix];
       float coef = 0.f;
-      if (pm < st->thr[0]) coef += static_cast<float>(p.bw1 / p.accum[A_K1]);
-      if ((f & 2) && pm < st->thr[1]) coef += static_cast<float>(p.sb / p.accum[A_K2]);
+      if (pm < st->thr[0] && p.accum[A_K1] > 0) coef += static_cast<float>(p.bw1 / p.accum[A_K1]);
+      if ((f & 2) && pm < st->thr[1] && p.accum[A_K2] > 0) coef += static_cast<float>(p.sb / p.accum[A_K2]);
       if (coef != 0.f) {
         const float* xm = p.x_m + static_cast<size_t>(n) * p.C * plane;
         float vm[kMaxC], mx = -FLT_MAX, se = 0.f;
@@ -447,8 +459,8 @@ __global__ void __launch_bounds__(256) crit_backward_tiled_kernel(CritParams p, 
   float coef = 0.f;
   if (f & 1) {
     const float pm = p.ws_p[pix];
-    if (pm < st->thr[0]) coef += static_cast<float>(p.bw1 / p.accum[A_K1]);
-    if ((f & 2) && pm < st->thr[1]) coef += static_cast<float>(p.sb / p.accum[A_K2]);
+    if (pm < st->thr[0] && p.accum[A_K1] > 0) coef += static_cast<float>(p.bw1 / p.accum[A_K1]);
+    if ((f & 2) && pm < st->thr[1] && p.accum[A_K2] > 0) coef += static_cast<float>(p.sb / p.accum[A_K2]);
   }
   if (__any_sync(0xffffffffu, coef != 0.f)) {
     float mx = -FLT_MAX, se = 0.f;
@@ -549,15 +561,15 @@ __device__ __forceinline__ void stage_lowres(const CritParams& p, const RunTile&
 template <int CMAX>
 __global__ void __launch_bounds__(256) crit_pixel_run_kernel(CritParams p) {
   extern __shared__ float lo[];
-  __shared__ double red[A_NLT2 + 1][8];
+  __shared__ double red[A_PIXEND][8];
   const RunTile t = run_tile(p);
   stage_lowres(p, t, lo, nullptr);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int y = t.ty * kRH + warp;
-  float acc[A_NLT2 + 1];
+  float acc[A_PIXEND];
 #pragma unroll
-  for (int i = 0; i <= A_NLT2; ++i) acc[i] = 0.f;
+  for (int i = 0; i < A_PIXEND; ++i) acc[i] = 0.f;
   if (y < p.H) {
     const Lerp ly = lerp_ac(y, p.h, p.H);
     const int r0 = (ly.i0 - t.ly0) * kRLW - t.lx0, r1 = (ly.i1 - t.ly0) * kRLW - t.lx0;
@@ -576,7 +588,10 @@ __global__ void __launch_bounds__(256) crit_pixel_run_kernel(CritParams p) {
         return fmaf(w00, q[a00], fmaf(w01, q[a01], fmaf(w10, q[a10], w11 * q[a11])));
       };
       const long t64 = p.labels[pix];
-      const bool valid1 = t64 != p.ignore_label;
+      const bool inrange = t64 >= 0 && t64 < p.C;
+      const bool valid1 = t64 != p.ignore_label && inrange;
+      if (t64 != p.ignore_label && !inrange) acc[A_NBAD] += 1.f;
+      if (t64 >= 0) acc[A_NGE0] += 1.f;
       const int tg = valid1 ? static_cast<int>(t64) : 0;
       float v[CMAX];
       float mx = -FLT_MAX, vt = 0.f;
@@ -627,12 +642,12 @@ __global__ void __launch_bounds__(256) crit_pixel_run_kernel(CritParams p) {
     }
   }
 #pragma unroll
-  for (int i = 0; i <= A_NLT2; ++i) {
+  for (int i = 0; i < A_PIXEND; ++i) {
     const float v = warp_sum_f(acc[i]);
     if (lane == 0) red[i][warp] = static_cast<double>(v);
   }
   __syncthreads();
-  if (threadIdx.x <= A_NLT2) {
+  if (threadIdx.x < A_PIXEND) {
     double v = 0.0;
     for (int q = 0; q < 8; ++q) v += red[threadIdx.x][q];
     if (v != 0.0) atomicAdd(p.accum + threadIdx.x, v);
@@ -685,7 +700,9 @@ __global__ void __launch_bounds__(256, CMAX <= 20 ? 2 : 1) crit_backward_run_ker
     const int r0 = (ly.i0 - t.ly0) * kRLW - t.lx0, r1 = (ly.i1 - t.ly0) * kRLW - t.lx0;
     const float wy0 = 1.f - ly.l, wy1 = ly.l;
     const double nhw = static_cast<double>(p.N) * p.H * p.W;
-    const float c_k1 = static_cast<float>(p.bw1 / p.accum[A_K1]), c_k2 = static_cast<float>(p.sb / p.accum[A_K2]);
+    // an empty OHEM selection (the reference raises IndexError, criterion.py:73) contributes no gradient; the loss is NaN
+    const float c_k1 = p.accum[A_K1] > 0 ? static_cast<float>(p.bw1 / p.accum[A_K1]) : 0.f;
+    const float c_k2 = p.accum[A_K2] > 0 ? static_cast<float>(p.sb / p.accum[A_K2]) : 0.f;
     const float c_aux = static_cast<float>(p.bw0 / nhw);
     const int* my_code = s_code + warp * kRS + lane * (kPX + 1);
     const float* my_z = s_z + warp * kRS + lane * (kPX + 1);

@@ -23,6 +23,7 @@
 #include "criterion.cuh"
 #include "train_kernels.cuh"
 
+#ifdef PIDNET_PROBES   // hardware probes (probe.cu): only in the tools' libpidnet_b200_probe.so, never in the product library
 namespace pidnet {
 struct ProbeParams {
   CUtensorMap tmA, tmB;
@@ -45,6 +46,7 @@ struct PairProbeParams {
 cudaError_t pair_probe_launch(const PairProbeParams& p, cudaStream_t st);
 cudaError_t mma_rate_pair_launch(int N, int iters, int distinct, int pairs, long long* out, cudaStream_t st);
 }  // namespace pidnet
+#endif
 
 namespace pidnet {
 
@@ -162,6 +164,7 @@ struct Op {
   double bytes = 0;     // algorithmic bytes: every distinct input and the output once
   int lane = 0;
   std::vector<int> deps;  // producer ops on other lanes
+  std::vector<float*> gwrites;   // training backward: parameter-gradient pointers this op finalises (bucketed all-reduce)
   bool record = false;
   std::function<cudaError_t(cudaStream_t, const RunArgs&)> fn;
 };
@@ -1506,7 +1509,7 @@ struct pidnet_engine {
 extern "C" {
 
 const char* pidnet_last_error(void) { return g_err.c_str(); }
-int pidnet_abi_version(void) { return 1; }
+int pidnet_abi_version(void) { return 2; }
 unsigned pidnet_debug_fastdiv(unsigned n, unsigned d) { return d ? fastdiv_debug(n, d) : 0u; }
 
 int pidnet_create(const pidnet_cfg* cfg, pidnet_engine** out) {
@@ -1805,9 +1808,10 @@ int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x, const int
     if (!h || !x || !labels || !bd_gt || !cfg) fail("null argument");
     TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    t.step(st, x, labels, bd_gt, class_weights, *cfg, backward != 0);
+    if (backward < 0 || backward > 2) fail("pidnet_train_step: backward must be 0, 1 or 2");
+    t.step(st, x, labels, bd_gt, class_weights, *cfg, backward);
     const size_t lp = static_cast<size_t>(t.N) * t.h8 * t.w8;
-    if (out12) CK(cudaMemcpyAsync(out12, t.out12, 12 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out12) CK(cudaMemcpyAsync(out12, t.out12, 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (out_main) CK(cudaMemcpyAsync(out_main, t.logits[0], lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
     if (out_p) CK(cudaMemcpyAsync(out_p, t.logits[1], lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
     if (out_d) CK(cudaMemcpyAsync(out_d, t.logits[2], lp * 4, cudaMemcpyDeviceToDevice, st));
@@ -1820,11 +1824,50 @@ int pidnet_train_forward(pidnet_trainer* h, void* stream, const float* x, float*
     TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     pidnet_criterion_cfg none{};
-    t.step(st, x, nullptr, nullptr, nullptr, none, false);
+    t.step(st, x, nullptr, nullptr, nullptr, none, 0);
     const size_t lp = static_cast<size_t>(t.N) * t.h8 * t.w8;
     if (out_main) CK(cudaMemcpyAsync(out_main, t.logits[0], lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
     if (out_p) CK(cudaMemcpyAsync(out_p, t.logits[1], lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
     if (out_d) CK(cudaMemcpyAsync(out_d, t.logits[2], lp * 4, cudaMemcpyDeviceToDevice, st));
+  });
+}
+/* network backward of the last train-mode forward (pidnet_train_forward, or pidnet_train_step with backward = 0 / 2) */
+int pidnet_train_backward(pidnet_trainer* h, void* stream, const float* x, const float* g_main, const float* g_p, const float* g_d,
+                          int segment) {
+  return guard([&] {
+    if (!h) fail("null handle");
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool any = g_main || g_p || g_d;
+    if (any && !(g_main && g_p && g_d)) fail("pidnet_train_backward: pass all three logit gradients or none");
+    if (any && segment <= 0) {
+      if (!t.planned) fail("pidnet_train_backward called before pidnet_train_plan");
+      const size_t lp = static_cast<size_t>(t.N) * t.h8 * t.w8;
+      CK(cudaMemcpyAsync(t.dlogits[0], g_main, lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(t.dlogits[1], g_p, lp * t.cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(t.dlogits[2], g_d, lp * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    t.backward_from_logits(st, x, segment);
+  });
+}
+int pidnet_train_num_segments(pidnet_trainer* h) {
+  return h ? reinterpret_cast<pidnet_trainer_*>(h)->t.nseg : -1;
+}
+int pidnet_train_segment_ranges(pidnet_trainer* h, int segment, const float* grad_base, int64_t* begin_end, int cap_pairs,
+                                int* n_pairs) {
+  return guard([&] {
+    if (!h || !grad_base || !n_pairs) fail("null argument");
+    TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
+    if (!t.planned) fail("pidnet_train_segment_ranges called before pidnet_train_plan");
+    if (segment < 0 || segment >= t.nseg) fail("segment index out of range");
+    const auto rs = t.segment_ranges(segment);
+    *n_pairs = static_cast<int>(rs.size());
+    if (!begin_end) return;
+    if (static_cast<int>(rs.size()) > cap_pairs) fail("pidnet_train_segment_ranges: buffer too small");
+    for (size_t i = 0; i < rs.size(); ++i) {
+      begin_end[2 * i] = static_cast<int64_t>(rs[i].first - grad_base);
+      begin_end[2 * i + 1] = begin_end[2 * i] + static_cast<int64_t>(rs[i].second);
+    }
   });
 }
 /* measurement: per-launch device times of one training step.  Writes a text table (one line per launch:
@@ -1891,6 +1934,10 @@ int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value) {
       t.drop_graphs();
     } else if (std::string(name) == "overlap_wgrad") {
       t.overlap_wgrad = value != 0;
+      t.drop_graphs();
+    } else if (std::string(name) == "bwd_segments") {
+      if (value < 1 || value > 16) fail("bwd_segments must be in 1..16");
+      t.nseg = value;
       t.drop_graphs();
     } else {
       fail(std::string("unknown training option '") + name + "'");
@@ -1963,6 +2010,7 @@ int pidnet_upsample_align_corners(void* stream, const float* x, int NC, int h, i
   return guard([&] { CK(upsample_ac_launch(x, NC, h, w, out, H, W, reinterpret_cast<cudaStream_t>(stream))); });
 }
 
+#ifdef PIDNET_PROBES
 // hardware probe: MN-major operands. a: [64][128] bf16, b: [64][64] bf16 (device), out [128][64] fp32
 int pidnet_probe_mn(void* stream, const void* a, const void* b, int lbo, int sbo, float* out) {
   return guard([&] {
@@ -2025,6 +2073,8 @@ int pidnet_probe_halo(void* stream, const void* x, const void* w, int r, int s, 
     CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
   });
 }
+
+#endif   // PIDNET_PROBES
 
 }  // extern "C"
 #pragma GCC visibility pop

@@ -44,6 +44,9 @@ class FusedSGD:
         self.steps = 0
 
     def zero_grad(self, set_to_none=True):
+        if not set_to_none:
+            self.trainer.flat_grad.zero_()
+            return
         for p in self.param_groups[0]['params']:
             p.grad = None
 
@@ -60,6 +63,7 @@ class FusedSGD:
                                                 float(g['weight_decay']), int(bool(g['nesterov'])), int(self.steps == 0),
                                                 float(grad_scale)))
         self.steps += 1
+        tr.model._generation += 1       # the kernel rewrote the parameters in place: eval plans must re-read them
 
     def state_dict(self):
         return dict(momentum_buffer=self.momentum_buffer.clone(), steps=self.steps,

@@ -165,6 +165,10 @@ class PIDNet(nn.Module):
         self._fingerprint = None
         self._options = {}
         self.use_graph = False
+        # bumped by everything that rewrites parameters / buffers behind torch's back (the training engine and FusedSGD write
+        # the flat buffers from CUDA kernels, which changes neither data_ptr nor tensor._version): part of the fingerprint
+        # below, so an eval forward after a training epoch re-reads the weights (reference loop: train, validate, repeat)
+        self._generation = 0
 
     # ----------------------------------------------------------------------- engine plumbing
     def set_engine_option(self, name, value):
@@ -180,7 +184,7 @@ class PIDNet(nn.Module):
         return [(k, v) for k, v in self.state_dict(keep_vars=True).items() if v.dtype.is_floating_point]
 
     def _weights_fingerprint(self):
-        return tuple((v.data_ptr(), v._version) for _, v in self._tensors())
+        return (self._generation,) + tuple((v.data_ptr(), v._version) for _, v in self._tensors())
 
     def _ensure_engine(self):
         lib = _lib.load()
@@ -225,17 +229,21 @@ class PIDNet(nn.Module):
     # ----------------------------------------------------------------------- forward
     def forward(self, x):
         if self.training:
-            # train-mode forward (batch statistics + running-stat update).  Gradients only exist through
-            # pidnet_b200.FullModel, which runs forward + loss + backward as ONE engine step.
-            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-                raise NotImplementedError('pidnet_b200: a differentiable train-mode forward runs through pidnet_b200.FullModel '
-                                          '(forward + loss + backward in one engine call); wrap the call in torch.no_grad() for a '
-                                          'statistics-only forward, or call .eval() for inference')
+            # train-mode forward (batch statistics + running-stat update), models/pidnet.py:136-182 under nn.Module.train().
+            # Under autograd the three outputs carry a graph node whose backward is the engine's backward pass, so the
+            # reference's own FullModel (utils/utils.py:39) or any custom loss can wrap this model.
             if not self.augment:
                 raise NotImplementedError('pidnet_b200: the train-mode engine needs augment=True (three outputs)')
             if not x.is_cuda:
                 raise RuntimeError('pidnet_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback')
-            return self.engine_trainer().forward_train(x)
+            if x.dim() != 4 or x.shape[1] != 3:
+                raise ValueError(f'expected input [N,3,H,W], got {tuple(x.shape)}')
+            trainer = self.engine_trainer()
+            params = [p for p in self.parameters()]
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                from .train import _TrainForwardFn
+                return list(_TrainForwardFn.apply(trainer, x, *params))
+            return trainer.forward_train(x)
         if not x.is_cuda:
             raise RuntimeError('pidnet_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback')
         if x.dim() != 4 or x.shape[1] != 3:

@@ -92,7 +92,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.pidnet_abi_version() == 1
+    assert lib.pidnet_abi_version() == 2
 
 
 def test_abi_error_paths_without_gpu():

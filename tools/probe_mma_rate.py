@@ -3,7 +3,7 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pidnet_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_probe()
 dev = torch.device('cuda:0')
 for blocks in (1, 148):
     for N in (32, 64, 128, 256):

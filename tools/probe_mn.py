@@ -3,7 +3,7 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pidnet_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_probe()
 dev = torch.device('cuda:0')
 g = torch.Generator().manual_seed(0)
 a = torch.randn(64, 128, generator=g).to(torch.bfloat16).to(dev)
