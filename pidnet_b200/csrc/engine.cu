@@ -724,7 +724,7 @@ struct Engine {
     cudaGraphExec_t exec;
   };
   std::vector<GraphEntry> graphs;
-  static constexpr size_t kMaxGraphs = 4;
+  static constexpr size_t kMaxGraphs = 8;   // (input, output) pointer sets of double-buffered callers whose outputs come from a caching allocator
 
   ~Engine() { release(); }
   void release() {

@@ -47,6 +47,32 @@ def allreduce_flat_gradient(flat, numel=None, average=True):
     return flat
 
 
+class BucketedAllReduce:
+    """Gradient exchange overlapped with the backward pass ("bucketed in reverse layer order"): the
+    backward runs in consecutive ranges; after range k the caller passes the [begin, end) float ranges of the flat gradient
+    that range finalised and `launch` starts one ASYNC all-reduce per range, which proceeds on the communication stream while
+    range k + 1 computes.  `finish` makes the caller's stream wait for all of them (the 1/world averaging is folded into
+    the caller's final scaling kernel).  Backend-agnostic: NCCL on GPUs, gloo in the CPU tests."""
+
+    def __init__(self, flat):
+        self.flat = flat
+        self.works = []
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def launch(self, ranges):
+        if self.world == 1:
+            return
+        for b, e in ranges:
+            if e > b:
+                self.works.append(dist.all_reduce(self.flat[b:e], op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        return self.world
+
+
 class ShardedInference:
     """Runs `model` on this rank's slice of a global batch.  `gather=True` (tests / small batches only)
     all-gathers the logits so every rank sees the full result in the original order."""

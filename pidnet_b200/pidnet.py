@@ -308,13 +308,14 @@ class PIDNet(nn.Module):
                 int(self.use_graph if use_graph is None else use_graph)))
         return [out_p, out, out_d] if self.augment else out
 
-    def segment(self, frames, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    def segment(self, frames, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None, logits=None):
         """tools/custom.py:86-92 on the device: uint8 BGR frames -> uint8 label maps [N,H,W] (fused input transform,
-        network, x8 align_corners upsample and argmax; only 3 B/pixel go up and 1 B/pixel comes back)."""
+        network, x8 align_corners upsample and argmax; only 3 B/pixel go up and 1 B/pixel comes back).  `out` / `logits`:
+        optional preallocated label-map / logits tensors (pointer-stable calls replay the CUDA graph when use_graph is set)."""
         from .postprocess import upsample_argmax
-        outs = self.forward_u8(frames, mean, std)
-        logits = outs[1] if self.augment else outs
-        return upsample_argmax(logits, frames.shape[1:3])
+        outs = self.forward_u8(frames, mean, std, out=logits)
+        lg = outs[1] if self.augment else outs
+        return upsample_argmax(lg, frames.shape[1:3], out=out)
 
     # ----------------------------------------------------------------------- introspection for tests / bench
     def forward_into(self, x, out, out_p=None, out_d=None, use_graph=True):

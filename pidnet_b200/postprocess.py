@@ -35,10 +35,14 @@ def _call(logits, size, pred, labels, ignore, conf, prune=True):
                                           p(conf), p(ws)))
 
 
-def upsample_argmax(logits, size, prune=True):
+def upsample_argmax(logits, size, prune=True, out=None):
     """uint8 [N,H,W] == torch.argmax(F.interpolate(logits, size, mode='bilinear', align_corners=True), dim=1).
-    prune=False forces the exhaustive per-pixel class loop (same result; used by the parity tests)."""
-    pred = torch.empty(logits.shape[0], int(size[0]), int(size[1]), dtype=torch.uint8, device=logits.device)
+    prune=False forces the exhaustive per-pixel class loop (same result; used by the parity tests); `out` (optional) is a
+    preallocated uint8 [N,H,W] device tensor to write into."""
+    pred = out if out is not None else torch.empty(logits.shape[0], int(size[0]), int(size[1]), dtype=torch.uint8,
+                                                   device=logits.device)
+    if pred.dtype != torch.uint8 or tuple(pred.shape) != (logits.shape[0], int(size[0]), int(size[1])) or not pred.is_contiguous():
+        raise ValueError('out must be a contiguous uint8 [N,H,W] tensor')
     _call(logits, size, pred, None, -1, None, prune)
     return pred
 

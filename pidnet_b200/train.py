@@ -231,13 +231,12 @@ class EngineTrainer:
                 if world > 1:
                     dist.all_reduce(self.flat_grad[:self.n_param], op=dist.ReduceOp.SUM)
             else:
-                works = []
+                from .parallel import BucketedAllReduce
+                exchange = BucketedAllReduce(self.flat_grad)
                 for seg, ranges in enumerate(self.segment_ranges()):
                     _lib.check(self.lib.pidnet_train_backward(self.h, C.c_void_p(stream), p(x), p(gm), p(gp), p(gd), seg))
-                    for b, e in ranges:
-                        works.append(dist.all_reduce(self.flat_grad[b:e], op=dist.ReduceOp.SUM, async_op=True))
-                for w in works:
-                    w.wait()
+                    exchange.launch(ranges)
+                exchange.finish()
         return world
 
     def allreduce_gradients(self, average=True):

@@ -1,0 +1,136 @@
+"""Worker of tests/test_train_api_gpu.py::test_two_rank_nccl_gradient_is_the_mean_of_the_shard_gradients
+(launched with torchrun, 2 ranks, NCCL).  Each rank trains on its own batch shard, exactly like one nn.DataParallel replica
+(tools/train.py:136): local OHEM / BCE normalisation, local BatchNorm statistics, then the gradient exchange.
+
+Checks, on every rank:
+  1. bucketed + overlapped all-reduce (backward in ranges, one async NCCL all-reduce per finalised range) == the mean of the
+     two ranks' LOCAL engine gradients (computed first without any exchange and all-gathered) up to the engine's run-to-run noise;
+  2. the single whole-buffer all-reduce gives the same;
+  3. the averaged engine gradient agrees with the mean of the two fp32-ORACLE shard gradients (torch autograd through the
+     reference restatement, each shard with its own loss normalisation) within the bf16 training tolerance;
+  4. parameters and BatchNorm buffers were broadcast from rank 0 when the trainer was created."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+
+import torch
+import torch.distributed as dist
+
+from oracle import criterion_oracle as CO
+from oracle import pidnet_oracle as O
+from pidnet_b200 import BondaryLoss, FullModel, OhemCrossEntropy, PIDNet
+
+
+def rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ncls, N, H, W, keep = 19, 4, 128, 256, 3000
+    cfg = O.config_for('pidnet_s', ncls, True)
+    # different initial weights per rank on purpose: the trainer must broadcast rank 0's
+    sd_rank = O.make_state_dict(cfg, 100 + rank, randomize_bn=False)
+    sd0 = O.make_state_dict(cfg, 100, randomize_bn=False)
+    model = PIDNet(m=cfg['m'], n=cfg['n'], num_classes=ncls, planes=cfg['planes'], ppm_planes=cfg['ppm_planes'],
+                   head_planes=cfg['head_planes'], augment=True)
+    model.load_state_dict(sd_rank)
+    weight = torch.tensor(CO.CITYSCAPES_CLASS_WEIGHTS)
+    full = FullModel(model.to(dev), OhemCrossEntropy(255, 0.9, keep, weight), BondaryLoss(), return_outputs=False).to(dev).train()
+    tr = full.trainer
+    for k, v in model.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert torch.equal(v.cpu(), sd0[k]), f'rank {rank}: {k} was not broadcast from rank 0'
+    # per-rank shard
+    shards = []
+    for r in range(world):
+        x = torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(1000 + r))
+        _, labels, bd = CO.synthetic_batch(N, ncls, H, W, 2000 + r)
+        shards.append((x, labels, bd))
+    x, labels, bd = [t.to(dev) for t in shards[rank]]
+
+    def local_grad():
+        tr.step(x, labels, bd, weight, full._crit.cfg, backward=2, want_logits=False)
+        tr.backward(x, allreduce=False)
+        return tr.flat_grad[:tr.n_param].clone()
+
+    g_local = local_grad()
+    g_local2 = local_grad()
+    noise = rel(g_local2, g_local)
+    gathered = [torch.empty_like(g_local) for _ in range(world)]
+    dist.all_gather(gathered, g_local)
+    g_mean = sum(gathered) / world
+
+    # (1) the reference loop: forward, zero_grad, loss.backward() -> bucketed all-reduce inside backward
+    tr.overlap_allreduce = True
+    for it in range(3):     # the last iterations replay the per-range CUDA graphs
+        loss = full(x, labels, bd)[0].mean()
+        full.zero_grad()
+        loss.backward()
+    g_bucket = torch.cat([p.grad.flatten() for p in model.parameters()])
+    flat_bucket = tr.flat_grad[:tr.n_param].clone()
+    nranges = sum(len(s) for s in tr.segment_ranges())
+    # (2) single all-reduce
+    tr.overlap_allreduce = False
+    loss = full(x, labels, bd)[0].mean()
+    full.zero_grad()
+    loss.backward()
+    flat_single = tr.flat_grad[:tr.n_param].clone()
+    torch.cuda.synchronize()
+    e1, e2 = rel(flat_bucket, g_mean), rel(flat_single, g_mean)
+    # every rank must hold the same averaged gradient bit for bit
+    other = [torch.empty_like(flat_bucket) for _ in range(world)]
+    dist.all_gather(other, flat_bucket)
+    assert all(torch.equal(o, other[0]) for o in other), 'ranks disagree on the averaged gradient'
+    tol = max(3 * noise, 1e-5)
+    print(f'rank {rank}: bucketed ({nranges} ranges) vs mean of local gradients {e1:.3e}, single all-reduce {e2:.3e}, '
+          f'run-to-run noise {noise:.3e}', flush=True)
+    assert e1 <= tol and e2 <= tol, (e1, e2, noise)
+    assert g_bucket.numel() == sum(p.numel() for p in model.parameters())
+
+    # (3) fp32 oracle: mean over shards of each shard's own gradient
+    ref, ref_own = None, None
+    for r in range(world):
+        sd = {k: v.clone().to(dev) for k, v in sd0.items()}
+        params = [(k, v) for k, v in sd.items() if v.dtype.is_floating_point and 'running_' not in k]
+        for _, v in params:
+            v.requires_grad_(True)
+        xr, lr_, br = [t.to(dev) for t in shards[r]]
+        outs = O.pidnet_forward(sd, xr, training=True)
+        losses, _, _, _ = CO.full_model_forward(list(outs), lr_, br, weight.to(dev), dict(ohem_keep=keep))
+        losses.mean().backward()
+        gsd = {k: v.grad for k, v in params}
+        flat = torch.cat([(gsd[k] if gsd[k] is not None else torch.zeros_like(sd[k])).flatten() for k, _ in model.named_parameters()])
+        ref = flat if ref is None else ref + flat
+        if r == rank:
+            ref_own = flat
+    ref = ref / world
+    got = torch.cat([tr.grad_views[k].flatten() for k, _ in model.named_parameters()])
+    cosine = lambda a, b: float(a.double() @ b.double() / (a.double().norm() * b.double().norm()))
+    cos = cosine(got, ref)
+    # yardstick: this rank's LOCAL engine gradient against its own oracle shard gradient (end to end on random-init weights the
+    # bf16 train-mode network is noisy; averaging over ranks must not make the agreement worse)
+    off, parts = 0, []
+    for p in model.parameters():
+        parts.append(g_local[off:off + p.numel()])
+        off += (p.numel() + 3) // 4 * 4
+    cos_local = cosine(torch.cat(parts), ref_own)
+    print(f'rank {rank}: averaged engine gradient vs mean of fp32-oracle shard gradients: cosine {cos:.4f}, rel-L2 {rel(got, ref):.3f} '
+          f'(local shard vs its oracle gradient: cosine {cos_local:.4f})', flush=True)
+    assert cos > 0.8 and cos >= cos_local - 0.03, (cos, cos_local)
+    dist.barrier()
+    if rank == 0:
+        print('NCCL_GRAD_OK', flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

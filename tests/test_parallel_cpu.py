@@ -45,6 +45,17 @@ def _worker(rank, world, port, ret):
         ok = ok and torch.equal(flat, want)
         summed = PAR.allreduce_flat_gradient(torch.ones(4) * (rank + 1), average=False)
         ok = ok and torch.equal(summed, torch.full((4,), 3.0))
+        # bucketed exchange: ranges finalised by successive backward segments are reduced asynchronously, out of order w.r.t.
+        # the buffer layout; untouched gaps (other segments' ranges, alignment padding) stay local until their turn
+        flat = torch.arange(32, dtype=torch.float32) * (rank + 1)
+        ex = PAR.BucketedAllReduce(flat)
+        ex.launch([(20, 28), (4, 8)])
+        ex.launch([(0, 4), (8, 20)])
+        assert ex.finish() == world
+        flat[:28] /= world
+        want = torch.arange(32, dtype=torch.float32) * 1.5
+        want[28:] = torch.arange(28, 32, dtype=torch.float32) * (rank + 1)
+        ok = ok and torch.equal(flat, want) and not ex.works
         ret[rank] = (ok, mx)
     finally:
         dist.destroy_process_group()

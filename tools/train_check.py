@@ -30,7 +30,9 @@ def emulate_bf16_storage():
     oc, ob = O._conv, O._bn
 
     def conv_e(c, x, name, stride=1, padding=0, groups=1):
-        return _ste(F.conv2d(x, _ste(c.sd[name + '.weight']), c.sd.get(name + '.bias'), stride, padding, 1, groups))
+        w = c.sd[name + '.weight']
+        w = w + (_bf(w) - w).detach()      # bf16 operand copy of the fp32 master weight; its gradient stays fp32 (engine: wgrad)
+        return _ste(F.conv2d(x, w, c.sd.get(name + '.bias'), stride, padding, 1, groups))
 
     def bn_e(c, x, name):
         return _ste(ob(c, x, name))
@@ -38,7 +40,10 @@ def emulate_bf16_storage():
     return oc, ob
 
 
-def run(name='pidnet_s', ncls=19, N=4, H=256, W=256, keep=4000, seed=5, verbose=True, emulate=False):
+def run(name='pidnet_s', ncls=19, N=4, H=256, W=256, keep=4000, seed=5, verbose=True, emulate=False, also_emulated=False):
+    """also_emulated: additionally run the stage-local oracle with bf16 STORAGE emulation (every conv / BN output and its gradient
+    rounded to bf16, bf16 weight operands -- what any bf16 implementation of the reference does) and append, per parameter,
+    the emulated oracle's own distance from the fp32 oracle: the yardstick the engine's distance is asserted against."""
     dev = torch.device('cuda:0')
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -64,7 +69,6 @@ def run(name='pidnet_s', ncls=19, N=4, H=256, W=256, keep=4000, seed=5, verbose=
     up = {'out_p': lg[0].grad, 'out': lg[1].grad, 'out_d': lg[2].grad}
     eng_out = {'out_p': eouts[0], 'out': eouts[1], 'out_d': eouts[2]}
     # ---- stage-local autograd
-    saved = emulate_bf16_storage() if emulate else None
     stages = O._stages(sd)
     names = [s[0] for s in stages]
     ev = {'x': x}
@@ -75,6 +79,8 @@ def run(name='pidnet_s', ncls=19, N=4, H=256, W=256, keep=4000, seed=5, verbose=
         else:
             ev[nm] = tr.debug_tensor(nm).to(dev)
             eg[nm] = tr.debug_tensor(nm, grad=True).to(dev)
+    emu_pg = _stage_param_grads(sd, ev, eg, up, H, W, dev) if also_emulated else None
+    saved = emulate_bf16_storage() if emulate else None
     ref_g = {nm: torch.zeros_like(ev[nm]) for nm in names}
     ref_pg = {}
     ref_run = {}
@@ -114,6 +120,9 @@ def run(name='pidnet_s', ncls=19, N=4, H=256, W=256, keep=4000, seed=5, verbose=
     for k, gr in ref_pg.items():
         a, b = tr.grad_views[k].double().flatten(), gr.double().flatten()
         rows_p.append((k, float((a - b).norm() / (b.norm() + 1e-30)), float(a @ b / (a.norm() * b.norm() + 1e-30)), float(b.norm())))
+    if emu_pg is not None:
+        rows_p = [r + (float((emu_pg[r[0]].double().flatten() - ref_pg[r[0]].double().flatten()).norm() / (r[3] + 1e-30))
+                       if r[0] in emu_pg else float('nan'),) for r in rows_p]
     if verbose:
         print('loss engine/ref', res['loss'], 'acc', res['acc'])
         print('stage-local forward rel-L2 :', ' '.join('%s=%.3g' % kv for kv in fwd_err.items()))
@@ -121,11 +130,34 @@ def run(name='pidnet_s', ncls=19, N=4, H=256, W=256, keep=4000, seed=5, verbose=
         rows_p.sort(key=lambda r: -r[1])
         print('parameter gradients, worst 30 of %d (rel-L2, cos, |ref|):' % len(rows_p))
         for r in rows_p[:30]:
-            print('   %-40s %.4g  %.5f  %.3g' % r)
+            print('   %-40s %.4g  %.5f  %.3g' % r[:4])
         import statistics
         print('median param-grad rel-L2 %.4g' % statistics.median([r[1] for r in rows_p]))
         print('running stats updated: %d, max rel err %.3g' % (len(run_err), max(run_err.values())))
     return res, fwd_err, rows_t, rows_p, run_err
+
+
+def _stage_param_grads(sd, ev, eg, up, H, W, dev):
+    """Stage-local parameter gradients of the bf16-storage-emulated oracle (same engine stage inputs / upstream gradients)."""
+    saved = emulate_bf16_storage()
+    try:
+        pg = {}
+        for nm, ins, fn in O._stages(sd):
+            psd = {k: v.detach().clone().to(dev) for k, v in sd.items()}
+            for k, v in psd.items():
+                if v.dtype.is_floating_point and 'running_' not in k:
+                    v.requires_grad_(True)
+            c = O._Ctx(psd, True)
+            c.size8 = (H // 8, W // 8)
+            inputs = [ev[i].detach().clone().requires_grad_(i != 'x') for i in ins]
+            out = fn(c, *inputs)
+            out.backward(up[nm] if nm in up else eg[nm])
+            for k, v in psd.items():
+                if v.requires_grad and v.grad is not None and float(v.grad.abs().sum()) > 0:
+                    pg[k] = pg.get(k, 0) + v.grad
+    finally:
+        O._conv, O._bn = saved
+    return pg
 
 
 if __name__ == '__main__':
