@@ -217,11 +217,39 @@ def test_training_step_parity_at_config5_geometry():
     assert len(run_err) > 100 and max(run_err.values()) < 2e-2, max(run_err.values())
 
 
+def _oracle_curve(sd0, batches, dev, weight, keep, perturb=0.0):
+    sd = {k: v.clone().to(dev) for k, v in sd0.items()}
+    if perturb:
+        g = torch.Generator(device='cpu').manual_seed(1)
+        for k, v in sd.items():
+            if v.dtype.is_floating_point and 'running_' not in k:
+                v.mul_(1 + perturb * torch.randn(v.shape, generator=g).to(dev))
+    params = [v for k, v in sd.items() if v.dtype.is_floating_point and 'running_' not in k]
+    for p in params:
+        p.requires_grad_(True)
+    ropt = torch.optim.SGD(params, lr=0.01, momentum=0.9, weight_decay=5e-4)
+    wd = weight.to(dev)
+    ref = []
+    for x, y, bd in batches:
+        outs = O.pidnet_forward(sd, x.to(dev), training=True)
+        losses, _, _, _ = CO.full_model_forward(list(outs), y.to(dev), bd.to(dev), wd, dict(ohem_keep=keep))
+        loss = losses.mean()
+        ropt.zero_grad(set_to_none=True)
+        loss.backward()
+        ropt.step()
+        ref.append(float(loss.detach()))
+    return ref
+
+
 def test_fifty_step_loss_curve_tracks_the_fp32_reference():
     """Engine (bf16 tensor cores, fused criterion, FusedSGD) and the fp32 oracle (torch autograd + torch.optim.SGD) train from the
-    same initial weights on the same 50 batches; the losses of the last 10 steps must agree within 5 %."""
+    same initial weights on the same 50 batches.  First losses must agree to 2 %.  After 50 steps the mean loss of the last 10
+    steps must agree within max(10 %, 1.5 x the reference's OWN reproducibility): train-mode BatchNorm + OHEM selection make
+    the trajectory chaotic -- the fp32 reference restarted from weights perturbed by half a bf16 ulp (2^-9 relative), or simply
+    re-run (cuDNN's non-deterministic reductions), lands 8-10 % away from itself (profiles/r02/loss_curve_study.txt, produced by
+    tools/loss_curve_study.py), so a tighter bound would test the random seed, not the engine."""
     dev = _dev()
-    N, H, W, steps = 4, 256, 512, 50
+    N, H, W, steps, keep = 4, 256, 512, 50, 20000
     cfg = O.config_for('pidnet_s', NCLS, True)
     sd0 = O.make_state_dict(cfg, 21, randomize_bn=False)
     weight = torch.tensor(CO.CITYSCAPES_CLASS_WEIGHTS)
@@ -232,7 +260,7 @@ def test_fifty_step_loss_curve_tracks_the_fp32_reference():
     model = PIDNet(m=cfg['m'], n=cfg['n'], num_classes=NCLS, planes=cfg['planes'], ppm_planes=cfg['ppm_planes'],
                    head_planes=cfg['head_planes'], augment=True)
     model.load_state_dict(sd0)
-    full = FullModel(model, OhemCrossEntropy(255, 0.9, 20000, weight), BondaryLoss(), return_outputs=False).to(dev).train()
+    full = FullModel(model, OhemCrossEntropy(255, 0.9, keep, weight), BondaryLoss(), return_outputs=False).to(dev).train()
     opt = FusedSGD(full, lr=0.01, momentum=0.9, weight_decay=5e-4)
     eng = []
     for x, y, bd in batches:
@@ -241,26 +269,17 @@ def test_fifty_step_loss_curve_tracks_the_fp32_reference():
         opt.zero_grad()
         loss.backward()
         opt.step()
-        eng.append(float(loss))
-    # fp32 oracle
-    sd = {k: v.clone().to(dev) for k, v in sd0.items()}
-    params = [v for k, v in sd.items() if v.dtype.is_floating_point and 'running_' not in k]
-    for p in params:
-        p.requires_grad_(True)
-    ropt = torch.optim.SGD(params, lr=0.01, momentum=0.9, weight_decay=5e-4)
-    wd = weight.to(dev)
-    ref = []
-    for x, y, bd in batches:
-        outs = O.pidnet_forward(sd, x.to(dev), training=True)
-        losses, _, _, _ = CO.full_model_forward(list(outs), y.to(dev), bd.to(dev), wd, dict(ohem_keep=20000))
-        loss = losses.mean()
-        ropt.zero_grad(set_to_none=True)
-        loss.backward()
-        ropt.step()
-        ref.append(float(loss))
+        eng.append(float(loss.detach()))
+    ref = _oracle_curve(sd0, batches, dev, weight, keep)
+    again = [_oracle_curve(sd0, batches, dev, weight, keep), _oracle_curve(sd0, batches, dev, weight, keep, perturb=2.0 ** -9)]
+    tail = lambda v: sum(v[-10:]) / 10
+    tail_e, tail_r = tail(eng), tail(ref)
+    spread = max(abs(tail(v) - tail_r) for v in again) / tail_r
     print('\n[loss curve] engine', [round(v, 3) for v in eng[::7]], '\n[loss curve] fp32  ', [round(v, 3) for v in ref[::7]])
+    print(f'[loss curve] last-10 mean: engine {tail_e:.4f}, fp32 {tail_r:.4f} ({100 * (tail_e / tail_r - 1):+.1f} %); the fp32 reference against '
+          f'itself (re-run / weights perturbed by 2^-9): {100 * spread:.1f} %')
     assert all(v == v for v in eng)
     assert abs(eng[0] - ref[0]) < 2e-2 * ref[0], (eng[0], ref[0])          # same weights, same batch: first losses agree
-    tail_e, tail_r = sum(eng[-10:]) / 10, sum(ref[-10:]) / 10
     assert tail_r < 0.7 * ref[0], 'the reference run itself did not learn'
-    assert abs(tail_e - tail_r) < 0.05 * tail_r, (tail_e, tail_r)
+    assert tail_e < 0.7 * eng[0], 'the engine run did not learn'
+    assert abs(tail_e - tail_r) < max(0.10, 1.5 * spread) * tail_r, (tail_e, tail_r, spread)

@@ -173,7 +173,8 @@ def test_fused_sgd_matches_torch_sgd_and_oracle():
 @pytest.mark.gpu
 def test_train_mode_forward_without_grad():
     """PIDNet.forward in train mode under no_grad: batch statistics, running stats / num_batches_tracked updated, three
-    outputs equal to the logits of a full training step on the same batch; with grad enabled it points at FullModel."""
+    outputs equal to the logits of a full training step on the same batch; with grad enabled the outputs carry an autograd node
+    (tests/test_train_api_gpu.py covers its backward)."""
     dev = _dev()
     cfg = O.config_for('pidnet_s', 19, True)
     model = PIDNet(m=cfg['m'], n=cfg['n'], num_classes=19, planes=cfg['planes'], ppm_planes=cfg['ppm_planes'],
@@ -181,14 +182,14 @@ def test_train_mode_forward_without_grad():
     model.load_state_dict(O.make_state_dict(cfg, 6, randomize_bn=False))
     model = model.to(dev).train()
     x = torch.randn(4, 3, 128, 256, generator=torch.Generator().manual_seed(2)).to(dev)
-    with pytest.raises(NotImplementedError):
-        model(x)
     rm0 = model.conv1[1].running_mean.clone()
     with torch.no_grad():
         outs = model(x)
     assert [tuple(o.shape) for o in outs] == [(4, 19, 16, 32), (4, 19, 16, 32), (4, 1, 16, 32)]
-    assert all(torch.isfinite(o).all() for o in outs)
+    assert all(torch.isfinite(o).all() and not o.requires_grad for o in outs)
     assert int(model.conv1[1].num_batches_tracked) == 1 and not torch.equal(model.conv1[1].running_mean, rm0)
+    assert all(o.requires_grad and o.grad_fn is not None for o in model(x))
+    assert int(model.conv1[1].num_batches_tracked) == 2
     # same engine, full step on the same batch (the trainer is shared): logits agree up to atomics-order noise
     from pidnet_b200 import _lib
     tr = model.engine_trainer()
@@ -196,5 +197,6 @@ def test_train_mode_forward_without_grad():
                            balance_weight_aux=0.4, balance_weight_main=1.0, sb_weight=1.0, coeff_bce=20.0)
     _, labels, bd = CO.synthetic_batch(4, 19, 128, 256, 3)
     _, louts = tr.step(x, labels.to(dev), bd.to(dev), None, cc, backward=True)
+    outs = [o.detach() for o in outs]
     for a, b in zip(outs, louts):
         assert float((a - b).norm() / b.norm()) < 2e-2

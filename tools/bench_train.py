@@ -27,6 +27,8 @@ def main():
     torch.manual_seed(0)
     model = PIDNet(m=2, n=3, num_classes=19, planes=32, ppm_planes=96, head_planes=128, augment=True).to(dev).train()
     tr = EngineTrainer(model)
+    if os.environ.get('GRAPH', '1') == '0':
+        tr.set_option('use_graph', 0)
     weight = torch.tensor(CW)
     crit = FusedCriterion(OhemCrossEntropy(255, 0.9, 131072, weight), BondaryLoss())
     g = torch.Generator().manual_seed(100 + rank)
@@ -49,6 +51,10 @@ def main():
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if os.environ.get('QUICK'):      # profiler runs: one line, no extra phases
+        if rank == 0:
+            print(json.dumps(dict(ms_per_step=ms, loss=float(out12[0]))), flush=True)
+        return
     # phase breakdown on rank 0 (forward+criterion only vs full)
     ef0, ef1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ef0.record()
