@@ -528,117 +528,254 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-struct RunTile {
-  int n, ty, tx, ly0, lx0;
+// ---- run kernels, column-owned form.  ncu on the first form (12 x 1024 x 1024, C = 19): 1106 / 2213 warp instructions per
+// label pixel (forward / backward), 66 % / 45 % issue-active, i.e. INSTRUCTION bound: four shared loads + four multiply-adds
+// per class and pixel for the interpolation, one runtime `k < C` test per class in every loop, and (backward) a gradient
+// flush that diverges inside the warp.  Here
+//  * the class count is a template constant for the dataset values (C = 19 Cityscapes, 11 CamVid): no per-class predicates;
+//  * a thread owns ONE LOW-RES COLUMN INTERVAL of one label row: all label pixels x with floor(x * (w-1)/(W-1)) == c (8 or 9
+//    consecutive pixels for the x8 heads).  They share their two low-res columns, so the vertically interpolated logits
+//    c0[k] = lerp_y(col c), d[k] = lerp_y(col c+1) - c0[k] are loaded ONCE per thread and a pixel costs one fma per class;
+//    in the backward pass the transposed interpolation accumulates in registers for the whole run and is flushed once --
+//    no reload / flush inside the pixel loop, hence no divergence (a first run-of-8-pixels form reloaded on a column change,
+//    which happens at a different pixel in every lane: the warp executed the reload block at almost every pixel);
+//  * the target logit is re-interpolated on its own (7 instructions) instead of a select per class; ex2 / lg2 everywhere;
+//  * labels / boundary targets come in and p / CE / flags go out through shared memory, so global IO stays coalesced.
+constexpr int kCT = 32;              // low-res columns per tile (one per lane)
+constexpr int kMaxRun = 10;          // label pixels per low-res column: <= ceil((W-1)/(w-1)) + 1
+constexpr int kCS = kCT * (kMaxRun + 1);   // padded smem row: pixel j of column lane c at c * 11 + j (odd stride: conflict-free)
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// per-pixel code byte: bits 0-4 class, 5 valid (label is a class index and not ignore_label), 6 label out of range, 7 label >= 0
+__device__ __forceinline__ unsigned label_code(long t64, long ignore, int C) {
+  const bool inrange = t64 >= 0 && t64 < C;
+  const bool valid = t64 != ignore && inrange;
+  return (valid ? (static_cast<unsigned>(t64) | 0x20u) : 0u) | ((t64 != ignore && !inrange) ? 0x40u : 0u) | (t64 >= 0 ? 0x80u : 0u);
+}
+// the low-res column lerp_ac assigns to label pixel x (its i0), and the first label pixel of column c (W for c >= w) --
+// both with lerp_ac's own float arithmetic, so that "the pixels of column c" is exactly {x : lerp_ac(x).i0 == c}
+__device__ __forceinline__ int col_of(int x, float scale, int w) { return min(static_cast<int>(scale * static_cast<float>(x)), w - 1); }
+__device__ __forceinline__ int first_x_of_col(int c, float scale, int w, int W) {
+  if (c <= 0) return 0;
+  if (c >= w) return W;
+  int x = scale > 0.f ? static_cast<int>(static_cast<float>(c) / scale) : W;
+  x = max(0, min(x, W));
+  while (x > 0 && col_of(x - 1, scale, w) >= c) --x;
+  while (x < W && col_of(x, scale, w) < c) ++x;
+  return x;
+}
+struct ColTile {
+  int n, ty, tx, ly0, lx0, xb, xe;
+  float scale;
 };
-__device__ __forceinline__ RunTile run_tile(const CritParams& p) {
-  RunTile t;
-  const int tiles_x = (p.W + kRW - 1) / kRW, tiles_y = (p.H + kRH - 1) / kRH;
+__device__ __forceinline__ ColTile col_tile(const CritParams& p) {
+  ColTile t;
+  const int tiles_x = (p.w + kCT - 1) / kCT, tiles_y = (p.H + kRH - 1) / kRH;
   t.n = blockIdx.x / (tiles_x * tiles_y);
   const int rem = blockIdx.x - t.n * tiles_x * tiles_y;
   t.ty = rem / tiles_x;
   t.tx = rem - t.ty * tiles_x;
+  t.scale = p.W > 1 ? static_cast<float>(p.w - 1) / static_cast<float>(p.W - 1) : 0.f;
   t.ly0 = lerp_ac(t.ty * kRH, p.h, p.H).i0;
-  t.lx0 = lerp_ac(t.tx * kRW, p.w, p.W).i0;
+  t.lx0 = t.tx * kCT;
+  t.xb = first_x_of_col(t.lx0, t.scale, p.w, p.W);
+  t.xe = first_x_of_col(t.lx0 + kCT, t.scale, p.w, p.W);
   return t;
 }
-// lo[ch][kRLH][kRLW]: [0,C) aux head, [C,2C) main head, 2C boundary
-__device__ __forceinline__ void stage_lowres(const CritParams& p, const RunTile& t, float* lo, float* zero) {
-  const int CH = 2 * p.C + 1;
-  const size_t plane = static_cast<size_t>(p.h) * p.w;
-  for (int i = threadIdx.x; i < CH * kRLP; i += blockDim.x) {
-    const int ch = i / kRLP, r = i - ch * kRLP;
+// lo[ch][kRLH][kRLW]: [0,C) aux head, [C,2C) main head, 2C boundary.  The per-element index arithmetic (two divisions, clamps,
+// a three-way pointer select) cost 122 instructions per staged value in the first version -- 335 per label pixel, more than
+// the softmax: the clamped source offsets are tabulated once per block, the heads are separate loops.
+__device__ __forceinline__ void stage_lowres_col(const CritParams& p, const ColTile& t, int C, float* lo, float* zero) {
+  __shared__ int s_off[kRLP];
+  for (int r = threadIdx.x; r < kRLP; r += blockDim.x) {
     const int ly = min(t.ly0 + r / kRLW, p.h - 1), lx = min(t.lx0 + r % kRLW, p.w - 1);
-    const float* src = ch < p.C ? p.x_p + (static_cast<size_t>(t.n) * p.C + ch) * plane
-                                : (ch < 2 * p.C ? p.x_m + (static_cast<size_t>(t.n) * p.C + (ch - p.C)) * plane
-                                                : p.x_d + static_cast<size_t>(t.n) * plane);
-    lo[i] = __ldg(src + static_cast<size_t>(ly) * p.w + lx);
-    if (zero) zero[i] = 0.f;
+    s_off[r] = ly * p.w + lx;
   }
+  __syncthreads();
+  const size_t plane = static_cast<size_t>(p.h) * p.w;
+  const float* base[3] = {p.x_p + static_cast<size_t>(t.n) * C * plane, p.x_m + static_cast<size_t>(t.n) * C * plane,
+                          p.x_d + static_cast<size_t>(t.n) * plane};
+#pragma unroll
+  for (int hd = 0; hd < 3; ++hd) {
+    const int nval = (hd == 2 ? 1 : C) * kRLP;
+    float* dst = lo + hd * C * kRLP;
+    float* zdst = zero ? zero + hd * C * kRLP : nullptr;
+    const float* src = base[hd];
+    for (int i = threadIdx.x; i < nval; i += blockDim.x) {
+      const int ch = i / kRLP, r = i - ch * kRLP;
+      // asynchronous 4-byte copies: all of a thread's ~22 loads are in flight at once (with plain loads the loop waited for
+      // each value before storing it -- ncu: a quarter of the kernel's samples sat on that store)
+      const unsigned sdst = static_cast<unsigned>(__cvta_generic_to_shared(dst + i));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(src + static_cast<size_t>(ch) * plane + s_off[r]) : "memory");
+      if (zdst) zdst[i] = 0.f;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_lowres_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// smem slot (within a row) of label pixel x of this tile
+__device__ __forceinline__ int col_slot(int x, const ColTile& t, int w, int W) {
+  const int c = col_of(x, t.scale, w);
+  return (c - t.lx0) * (kMaxRun + 1) + (x - first_x_of_col(c, t.scale, w, W));
 }
 
-// forward: lane l of warp w handles pixels x = tile_x0 + l + 32 j (j = 0..7) of row w -- coalesced IO, rolled loop
-template <int CMAX>
-__global__ void __launch_bounds__(256) crit_pixel_run_kernel(CritParams p) {
-  extern __shared__ float lo[];
+template <int CMAX, bool EXACT>
+__global__ void __launch_bounds__(256, 3) crit_pixel_run_kernel(CritParams p) {
+  extern __shared__ float lo[];                       // [CH][kRLH][kRLW]
   __shared__ double red[A_PIXEND][8];
-  const RunTile t = run_tile(p);
-  stage_lowres(p, t, lo, nullptr);
-  __syncthreads();
+  __shared__ unsigned char s_lab[kRH * kCS], s_zc[kRH * kCS], s_fl[kRH * kCS];   // staged label / boundary-target codes, flags
+  __shared__ float s_pm[kRH * kCS], s_ce[kRH * kCS];
+  const int C = EXACT ? CMAX : p.C;
+  const ColTile t = col_tile(p);
+  stage_lowres_col(p, t, C, lo, nullptr);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // coalesced staging of the tile's labels and boundary targets: a thread takes the same pixel column(s) of all 8 rows
+  for (int x = t.xb + static_cast<int>(threadIdx.x); x < t.xe; x += 256) {
+    const int slot = col_slot(x, t, p.w, p.W);
+    const int nrow = min(kRH, p.H - t.ty * kRH);
+    const long pix0 = (static_cast<long>(t.n) * p.H + t.ty * kRH) * p.W + x;
+    long lab[kRH];
+    float zz[kRH];
+#pragma unroll
+    for (int i = 0; i < kRH; ++i) {      // all 16 loads of the column in flight before the first use
+      const long pix = pix0 + static_cast<long>(i < nrow ? i : 0) * p.W;
+      lab[i] = __ldg(p.labels + pix);
+      zz[i] = __ldg(p.bd_gt + pix);
+    }
+#pragma unroll
+    for (int i = 0; i < kRH; ++i) {
+      if (i < nrow) {
+        s_lab[i * kCS + slot] = static_cast<unsigned char>(label_code(lab[i], p.ignore_label, C));
+        s_zc[i * kCS + slot] = static_cast<unsigned char>(zz[i] == 1.f ? 1u : (zz[i] == 0.f ? 0u : 2u));
+      }
+    }
+  }
+  stage_lowres_wait();
+  __syncthreads();
   const int y = t.ty * kRH + warp;
+  const int c = t.lx0 + lane;
   float acc[A_PIXEND];
 #pragma unroll
   for (int i = 0; i < A_PIXEND; ++i) acc[i] = 0.f;
-  if (y < p.H) {
+  const int my = warp * kCS + lane * (kMaxRun + 1);
+  if (y < p.H && c < p.w) {
+    const int xs = first_x_of_col(c, t.scale, p.w, p.W);
+    const int npx = first_x_of_col(c + 1, t.scale, p.w, p.W) - xs;
     const Lerp ly = lerp_ac(y, p.h, p.H);
-    const int r0 = (ly.i0 - t.ly0) * kRLW - t.lx0, r1 = (ly.i1 - t.ly0) * kRLW - t.lx0;
+    const int i1 = lane + (c < p.w - 1 ? 1 : 0);                 // staged column of lerp_ac(x).i1
+    const int r0 = (ly.i0 - t.ly0) * kRLW, r1 = (ly.i1 - t.ly0) * kRLW;
     const float wy0 = 1.f - ly.l, wy1 = ly.l;
-    const long row = (static_cast<long>(t.n) * p.H + y) * p.W;
+    const float logit_thr = __logf(p.bd_threshold / (1.f - p.bd_threshold));   // sigmoid(x) > thr  <=>  x > logit(thr)
+    const float fc = static_cast<float>(c);
+    float c0[CMAX], d[CMAX];
+    // ---------------- main head: p(target), weighted CE, argmax hit; OHEM counters
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) {
+      if (EXACT || k < C) {
+        const float* q = lo + (C + k) * kRLP;
+        const float a = fmaf(wy1, q[r1 + lane], wy0 * q[r0 + lane]), b = fmaf(wy1, q[r1 + i1], wy0 * q[r0 + i1]);
+        c0[k] = a; d[k] = b - a;
+      }
+    }
 #pragma unroll 1
-    for (int j = 0; j < kPX; ++j) {
-      const int x = t.tx * kRW + j * 32 + lane;
-      if (x >= p.W) break;
-      const long pix = row + x;
-      const Lerp lx = lerp_ac(x, p.w, p.W);
-      const float w00 = wy0 * (1.f - lx.l), w01 = wy0 * lx.l, w10 = wy1 * (1.f - lx.l), w11 = wy1 * lx.l;
-      const int a00 = r0 + lx.i0, a01 = r0 + lx.i1, a10 = r1 + lx.i0, a11 = r1 + lx.i1;
-      auto value = [&](int ch) {
-        const float* q = lo + ch * kRLP;
-        return fmaf(w00, q[a00], fmaf(w01, q[a01], fmaf(w10, q[a10], w11 * q[a11])));
-      };
-      const long t64 = p.labels[pix];
-      const bool inrange = t64 >= 0 && t64 < p.C;
-      const bool valid1 = t64 != p.ignore_label && inrange;
-      if (t64 != p.ignore_label && !inrange) acc[A_NBAD] += 1.f;
-      if (t64 >= 0) acc[A_NGE0] += 1.f;
-      const int tg = valid1 ? static_cast<int>(t64) : 0;
-      float v[CMAX];
-      float mx = -FLT_MAX, vt = 0.f;
+    for (int j = 0; j < npx; ++j) {
+      const float l = t.scale * static_cast<float>(xs + j) - fc;   // == lerp_ac(x).l (same product, i0 == c)
+      const unsigned code = s_lab[my + j];
+      const bool valid1 = (code & 0x20u) != 0;
+      const int tg = code & 0x1Fu;
+      float mx = -FLT_MAX;
       int amax = 0;
 #pragma unroll
       for (int k = 0; k < CMAX; ++k) {
-        if (k < p.C) {
-          v[k] = value(p.C + k);
-          if (v[k] > mx) { mx = v[k]; amax = k; }
-          if (k == tg) vt = v[k];
+        if (EXACT || k < C) {
+          const float v = fmaf(l, d[k], c0[k]);
+          if (v > mx) { mx = v; amax = k; }
         }
       }
       float se = 0.f;
       const float mxs = -mx * kLog2e;
 #pragma unroll
-      for (int k = 0; k < CMAX; ++k) if (k < p.C) se += ex2f(fmaf(v[k], kLog2e, mxs));
+      for (int k = 0; k < CMAX; ++k) if (EXACT || k < C) se += ex2f(fmaf(fmaf(l, d[k], c0[k]), kLog2e, mxs));
+      // the target's logit, interpolated on its own with the same operations as c0 / d above (bit-identical to v[tg])
+      const float* qt = lo + (C + tg) * kRLP;
+      const float ta = fmaf(wy1, qt[r1 + lane], wy0 * qt[r0 + lane]), tb = fmaf(wy1, qt[r1 + i1], wy0 * qt[r0 + i1]);
+      const float vt = fmaf(l, tb - ta, ta);
+      // (full-precision log / exp here: p feeds the OHEM order statistic, where a pixel within rounding of the threshold flips
+      //  in or out of the selection)
       const float lse = mx + logf(se);
-      const float wt = (valid1 && p.class_w) ? __ldg(p.class_w + tg) : 1.f;
       const float pm = expf(vt - lse);
-      if (static_cast<long>(amax) == t64) acc[A_ACC] += 1.f;   // pixel_acc counts every pixel (label >= 0), utils.py:31
-      if (valid1) {
-        float mp = -FLT_MAX, vtp = 0.f, sp = 0.f;
-#pragma unroll
-        for (int k = 0; k < CMAX; ++k) {
-          if (k < p.C) {
-            v[k] = value(k);
-            mp = fmaxf(mp, v[k]);
-            if (k == tg) vtp = v[k];
-          }
-        }
-        const float mps = -mp * kLog2e;
-#pragma unroll
-        for (int k = 0; k < CMAX; ++k) if (k < p.C) sp += ex2f(fmaf(v[k], kLog2e, mps));
-        acc[A_CE_P] += wt * (mp + logf(sp) - vtp);
-      }
-      const float xd = value(2 * p.C);
-      const float z = p.bd_gt[pix];
-      const float bce = fmaxf(xd, 0.f) - xd * z + log1pf(expf(-fabsf(xd)));
-      if (z == 1.f) { acc[A_BCE_POS] += bce; acc[A_NPOS] += 1.f; }
-      else if (z == 0.f) { acc[A_BCE_NEG] += bce; acc[A_NNEG] += 1.f; }
-      const float sg = 1.f / (1.f + expf(-xd));
-      const bool valid2 = valid1 && sg > p.bd_threshold;
+      const float wt = (valid1 && p.class_w) ? __ldg(p.class_w + tg) : 1.f;
+      if (valid1 && amax == tg) acc[A_ACC] += 1.f;             // pixel_acc numerator: prediction == label (label >= 0), utils.py:31-33
+      if (code & 0x80u) acc[A_NGE0] += 1.f;
+      if (code & 0x40u) acc[A_NBAD] += 1.f;
+      s_pm[my + j] = pm;
+      s_ce[my + j] = wt * (lse - vt);
       if (valid1) { acc[A_NV1] += 1.f; if (pm < p.ohem_thres) acc[A_NLT1] += 1.f; }
-      if (valid2) { acc[A_NV2] += 1.f; if (pm < p.ohem_thres) acc[A_NLT2] += 1.f; }
-      p.ws_p[pix] = pm;
-      p.ws_ce[pix] = wt * (lse - vt);
-      p.ws_flags[pix] = static_cast<unsigned char>((valid1 ? 1 : 0) | (valid2 ? 2 : 0));
+    }
+    // ---------------- boundary head: weighted BCE sums, bd_label validity
+    {
+      const float* q = lo + 2 * C * kRLP;
+      const float b0 = fmaf(wy1, q[r1 + lane], wy0 * q[r0 + lane]);
+      const float bd = fmaf(wy1, q[r1 + i1], wy0 * q[r0 + i1]) - b0;
+#pragma unroll 1
+      for (int j = 0; j < npx; ++j) {
+        const float l = t.scale * static_cast<float>(xs + j) - fc;
+        const float xd = fmaf(l, bd, b0);
+        const unsigned zc = s_zc[my + j];
+        // BCE with logits: max(x, 0) - x z + log(1 + exp(-|x|))
+        const float sp = __logf(1.f + __expf(-fabsf(xd)));
+        if (zc == 1u) { acc[A_BCE_POS] += fmaxf(xd, 0.f) - xd + sp; acc[A_NPOS] += 1.f; }
+        else if (zc == 0u) { acc[A_BCE_NEG] += fmaxf(xd, 0.f) + sp; acc[A_NNEG] += 1.f; }
+        const bool valid1 = (s_lab[my + j] & 0x20u) != 0;
+        const bool valid2 = valid1 && xd > logit_thr;
+        if (valid2) { acc[A_NV2] += 1.f; if (s_pm[my + j] < p.ohem_thres) acc[A_NLT2] += 1.f; }
+        s_fl[my + j] = static_cast<unsigned char>((valid1 ? 1 : 0) | (valid2 ? 2 : 0));
+      }
+    }
+    // ---------------- aux head: plain weighted CE over valid pixels (reduction none; ignored pixels contribute 0)
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) {
+      if (EXACT || k < C) {
+        const float* q = lo + k * kRLP;
+        const float a = fmaf(wy1, q[r1 + lane], wy0 * q[r0 + lane]), b = fmaf(wy1, q[r1 + i1], wy0 * q[r0 + i1]);
+        c0[k] = a; d[k] = b - a;
+      }
+    }
+#pragma unroll 1
+    for (int j = 0; j < npx; ++j) {
+      const unsigned code = s_lab[my + j];
+      if (!(code & 0x20u)) continue;
+      const int tg = code & 0x1Fu;
+      const float l = t.scale * static_cast<float>(xs + j) - fc;
+      float mp = -FLT_MAX;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) if (EXACT || k < C) mp = fmaxf(mp, fmaf(l, d[k], c0[k]));
+      float sp = 0.f;
+      const float mps = -mp * kLog2e;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) if (EXACT || k < C) sp += ex2f(fmaf(fmaf(l, d[k], c0[k]), kLog2e, mps));
+      const float* qt = lo + tg * kRLP;
+      const float ta = fmaf(wy1, qt[r1 + lane], wy0 * qt[r0 + lane]), tb = fmaf(wy1, qt[r1 + i1], wy0 * qt[r0 + i1]);
+      const float vtp = fmaf(l, tb - ta, ta);
+      const float wt = p.class_w ? __ldg(p.class_w + tg) : 1.f;
+      acc[A_CE_P] += wt * (fmaf(mp, kLog2e, lg2f(sp)) * kLn2 - vtp);
+    }
+  }
+  __syncthreads();
+  // coalesced write-out of p / CE / flags
+  for (int x = t.xb + static_cast<int>(threadIdx.x); x < t.xe; x += 256) {
+    const int slot = col_slot(x, t, p.w, p.W);
+#pragma unroll
+    for (int i = 0; i < kRH; ++i) {
+      const int yy = t.ty * kRH + i;
+      if (yy >= p.H) break;
+      const long pix = (static_cast<long>(t.n) * p.H + yy) * p.W + x;
+      p.ws_p[pix] = s_pm[i * kCS + slot];
+      p.ws_ce[pix] = s_ce[i * kCS + slot];
+      p.ws_flags[pix] = s_fl[i * kCS + slot];
     }
   }
 #pragma unroll
@@ -655,77 +792,85 @@ __global__ void __launch_bounds__(256) crit_pixel_run_kernel(CritParams p) {
 }
 
 // backward.  Phase 1 (coalesced): per pixel a code word {target | kept-by-OHEM-1 | kept-by-OHEM-2 | valid} and the
-// boundary target go to smem (row stride 32*9 so the run phase reads conflict-free).  Phase 2: every thread owns the
-// run x = tile_x0 + 8 lane + j; loops over heads and pixels are rolled (the unrolled form thrashed the I-cache).
-constexpr int kRS = 32 * (kPX + 1);   // padded smem row: pixel (lane, j) at lane * 9 + j
-template <int CMAX>
-__global__ void __launch_bounds__(256, CMAX <= 20 ? 2 : 1) crit_backward_run_kernel(CritParams p, const SelState* st) {
+// boundary target go to smem.  Phase 2: thread = (label row, low-res column); the transposed interpolation of its run
+// accumulates in registers (a0: column c, a1: column c + 1), the a1 of the left neighbour lane is folded in with one shuffle
+// and every lane adds its column to the two low-res rows of the shared gradient tile; one global atomic per tile element.
+template <int CMAX, bool EXACT>
+__global__ void __launch_bounds__(256, 2) crit_backward_run_kernel(CritParams p, const SelState* st) {
   extern __shared__ float sm[];
-  const int CH = 2 * p.C + 1;
+  const int C = EXACT ? CMAX : p.C;
+  const int CH = 2 * C + 1;
   float* lo = sm;
   float* tile = sm + CH * kRLP;
-  int* s_code = reinterpret_cast<int*>(tile + CH * kRLP);   // [kRH][kRS]
-  float* s_z = reinterpret_cast<float*>(s_code + kRH * kRS);
-  const RunTile t = run_tile(p);
-  stage_lowres(p, t, lo, tile);
+  int* s_code = reinterpret_cast<int*>(tile + CH * kRLP);   // [kRH][kCS]
+  float* s_z = reinterpret_cast<float*>(s_code + kRH * kCS);
+  const ColTile t = col_tile(p);
+  stage_lowres_col(p, t, C, lo, tile);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int y = t.ty * kRH + warp;
   const float thr0 = st->thr[0], thr1 = st->thr[1];
-  if (y < p.H) {
-    const long row = (static_cast<long>(t.n) * p.H + y) * p.W;
+  for (int x = t.xb + static_cast<int>(threadIdx.x); x < t.xe; x += 256) {
+    const int slot = col_slot(x, t, p.w, p.W);
+    const int nrow = min(kRH, p.H - t.ty * kRH);
+    const long pix0 = (static_cast<long>(t.n) * p.H + t.ty * kRH) * p.W + x;
+    unsigned fl[kRH];
+    float pmv[kRH], zz[kRH];
+    int lab[kRH];
 #pragma unroll
-    for (int i = 0; i < kPX; ++i) {
-      const int xl = i * 32 + lane, x = t.tx * kRW + xl;   // pixel xl of the tile row = (lane' = xl / 8, j = xl % 8)
-      int code = 0;
-      float z = -1.f;
-      if (x < p.W) {
-        const unsigned f = p.ws_flags[row + x];
-        z = p.bd_gt[row + x];
-        if (f & 1) {
-          const float pm = p.ws_p[row + x];
-          code = (static_cast<int>(p.labels[row + x]) & 0xFF) | 0x400;
-          if (pm < thr0) code |= 0x100;
-          if ((f & 2) && pm < thr1) code |= 0x200;
+    for (int i = 0; i < kRH; ++i) {      // all loads of the column in flight before the first use
+      const long pix = pix0 + static_cast<long>(i < nrow ? i : 0) * p.W;
+      fl[i] = p.ws_flags[pix];
+      pmv[i] = p.ws_p[pix];
+      lab[i] = static_cast<int>(__ldg(p.labels + pix));
+      zz[i] = __ldg(p.bd_gt + pix);
+    }
+#pragma unroll
+    for (int i = 0; i < kRH; ++i) {
+      if (i < nrow) {
+        int code = 0;
+        if (fl[i] & 1) {
+          code = (lab[i] & 0xFF) | 0x400;
+          if (pmv[i] < thr0) code |= 0x100;
+          if ((fl[i] & 2) && pmv[i] < thr1) code |= 0x200;
         }
+        s_code[i * kCS + slot] = code;
+        s_z[i * kCS + slot] = zz[i];
       }
-      const int slot = warp * kRS + (xl >> 3) * (kPX + 1) + (xl & 7);
-      s_code[slot] = code;
-      s_z[slot] = z;
     }
   }
+  stage_lowres_wait();
   __syncthreads();
-  const int x0 = t.tx * kRW + lane * kPX;
-  if (y < p.H && x0 < p.W) {
+  const int y = t.ty * kRH + warp;
+  const int c = t.lx0 + lane;
+  if (y < p.H) {                                               // (whole warps: the shuffles below stay convergent)
+    const bool live = c < p.w;
+    const int xs = live ? first_x_of_col(c, t.scale, p.w, p.W) : 0;
+    const int npx = live ? first_x_of_col(c + 1, t.scale, p.w, p.W) - xs : 0;
     const Lerp ly = lerp_ac(y, p.h, p.H);
-    const int r0 = (ly.i0 - t.ly0) * kRLW - t.lx0, r1 = (ly.i1 - t.ly0) * kRLW - t.lx0;
+    const int i1 = lane + (c < p.w - 1 ? 1 : 0);
+    const int r0 = (ly.i0 - t.ly0) * kRLW, r1 = (ly.i1 - t.ly0) * kRLW;
     const float wy0 = 1.f - ly.l, wy1 = ly.l;
     const double nhw = static_cast<double>(p.N) * p.H * p.W;
     // an empty OHEM selection (the reference raises IndexError, criterion.py:73) contributes no gradient; the loss is NaN
     const float c_k1 = p.accum[A_K1] > 0 ? static_cast<float>(p.bw1 / p.accum[A_K1]) : 0.f;
     const float c_k2 = p.accum[A_K2] > 0 ? static_cast<float>(p.sb / p.accum[A_K2]) : 0.f;
     const float c_aux = static_cast<float>(p.bw0 / nhw);
-    const int* my_code = s_code + warp * kRS + lane * (kPX + 1);
-    const float* my_z = s_z + warp * kRS + lane * (kPX + 1);
-    const int npx = min(kPX, p.W - x0);
-    float a0[CMAX], a1[CMAX];
+    const int* my_code = s_code + warp * kCS + lane * (kMaxRun + 1);
+    const float* my_z = s_z + warp * kCS + lane * (kMaxRun + 1);
+    const float fc = static_cast<float>(c);
+    // column of the tile that receives a1 of lane 31 (or of the image's last column, where i1 == i0)
+    float a0[CMAX], a1[CMAX], c0[CMAX], d[CMAX];
 #pragma unroll 1
     for (int hd = 0; hd < 2; ++hd) {   // 0: main head (OHEM coefficients), 1: aux head
-      const int ch0 = hd == 0 ? p.C : 0;
+      const int ch0 = hd == 0 ? C : 0;
 #pragma unroll
-      for (int k = 0; k < CMAX; ++k) a0[k] = a1[k] = 0.f;
-      int cur = -1;
-      auto flush = [&](int col) {
-        const int c1 = min(col + 1, p.w - 1);
-#pragma unroll
-        for (int k = 0; k < CMAX; ++k) {
-          if (k < p.C) {
-            float* tb = tile + (ch0 + k) * kRLP;
-            if (a0[k] != 0.f) { atomicAdd(tb + r0 + col, a0[k] * wy0); atomicAdd(tb + r1 + col, a0[k] * wy1); }
-            if (a1[k] != 0.f) { atomicAdd(tb + r0 + c1, a1[k] * wy0); atomicAdd(tb + r1 + c1, a1[k] * wy1); }
-            a0[k] = a1[k] = 0.f;
-          }
+      for (int k = 0; k < CMAX; ++k) {
+        if (EXACT || k < C) {
+          const float* q = lo + (ch0 + k) * kRLP;
+          const float a = fmaf(wy1, q[r1 + lane], wy0 * q[r0 + lane]), b = fmaf(wy1, q[r1 + i1], wy0 * q[r0 + i1]);
+          c0[k] = a; d[k] = b - a;
+          a0[k] = 0.f; a1[k] = 0.f;
         }
-      };
+      }
 #pragma unroll 1
       for (int j = 0; j < npx; ++j) {
         const int code = my_code[j];
@@ -734,37 +879,38 @@ __global__ void __launch_bounds__(256, CMAX <= 20 ? 2 : 1) crit_backward_run_ker
         const float wt = p.class_w ? __ldg(p.class_w + tg) : 1.f;
         const float cf = wt * (hd == 0 ? ((code & 0x100) ? c_k1 : 0.f) + ((code & 0x200) ? c_k2 : 0.f) : c_aux);
         if (cf == 0.f) continue;
-        const Lerp lx = lerp_ac(x0 + j, p.w, p.W);
-        if (lx.i0 != cur) {
-          if (cur >= 0) flush(cur);
-          cur = lx.i0;
-        }
-        const float w00 = wy0 * (1.f - lx.l), w01 = wy0 * lx.l, w10 = wy1 * (1.f - lx.l), w11 = wy1 * lx.l;
-        const int a00 = r0 + lx.i0, a01 = r0 + lx.i1, a10 = r1 + lx.i0, a11 = r1 + lx.i1;
+        const float l = t.scale * static_cast<float>(xs + j) - fc;
         float v[CMAX];
         float mx = -FLT_MAX, se = 0.f;
 #pragma unroll
-        for (int k = 0; k < CMAX; ++k) {
-          if (k < p.C) {
-            const float* q = lo + (ch0 + k) * kRLP;
-            v[k] = fmaf(w00, q[a00], fmaf(w01, q[a01], fmaf(w10, q[a10], w11 * q[a11])));
-            mx = fmaxf(mx, v[k]);
-          }
-        }
+        for (int k = 0; k < CMAX; ++k) if (EXACT || k < C) { v[k] = fmaf(l, d[k], c0[k]); mx = fmaxf(mx, v[k]); }
         const float mxs = -mx * kLog2e;
 #pragma unroll
-        for (int k = 0; k < CMAX; ++k) if (k < p.C) { v[k] = ex2f(fmaf(v[k], kLog2e, mxs)); se += v[k]; }
-        const float sc = cf / se, g0 = 1.f - lx.l, g1 = lx.l;
+        for (int k = 0; k < CMAX; ++k) if (EXACT || k < C) { v[k] = ex2f(fmaf(v[k], kLog2e, mxs)); se += v[k]; }
+        const float sc = __fdividef(cf, se), g0 = 1.f - l, g1 = l;
 #pragma unroll
         for (int k = 0; k < CMAX; ++k) {
-          if (k < p.C) {
+          if (EXACT || k < C) {
             const float g = fmaf(v[k], sc, k == tg ? -cf : 0.f);
             a0[k] = fmaf(g, g0, a0[k]);
             a1[k] = fmaf(g, g1, a1[k]);
           }
         }
       }
-      if (cur >= 0) flush(cur);
+      // flush: column (lane) gets a0 + the left neighbour's a1; lane 31 / the image's last column keep their a1 for column i1
+      const bool own_a1 = lane == 31 || i1 == lane;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (EXACT || k < C) {
+          float* tb = tile + (ch0 + k) * kRLP;
+          const float left = __shfl_up_sync(0xffffffffu, a1[k], 1);
+          float mine = a0[k] + (lane > 0 ? left : 0.f);
+          if (i1 == lane) { mine += a1[k]; }                   // last image column: both taps are column c
+          atomicAdd(tb + r0 + lane, mine * wy0);
+          atomicAdd(tb + r1 + lane, mine * wy1);
+          if (own_a1 && i1 != lane) { atomicAdd(tb + r0 + i1, a1[k] * wy0); atomicAdd(tb + r1 + i1, a1[k] * wy1); }
+        }
+      }
     }
     // boundary head (one channel): same run accumulation
     {
@@ -772,33 +918,28 @@ __global__ void __launch_bounds__(256, CMAX <= 20 ? 2 : 1) crit_backward_run_ker
       const float om_pos = static_cast<float>(p.accum[A_NNEG] / nb), om_neg = static_cast<float>(p.accum[A_NPOS] / nb);
       const float c_bce = static_cast<float>(p.coeff_bce / nhw);
       float b0 = 0.f, b1 = 0.f;
-      int cur = -1;
-      float* tb = tile + 2 * p.C * kRLP;
-      const float* q = lo + 2 * p.C * kRLP;
-      auto flush = [&](int col) {
-        const int c1 = min(col + 1, p.w - 1);
-        if (b0 != 0.f) { atomicAdd(tb + r0 + col, b0 * wy0); atomicAdd(tb + r1 + col, b0 * wy1); }
-        if (b1 != 0.f) { atomicAdd(tb + r0 + c1, b1 * wy0); atomicAdd(tb + r1 + c1, b1 * wy1); }
-        b0 = b1 = 0.f;
-      };
+      float* tb = tile + 2 * C * kRLP;
+      const float* q = lo + 2 * C * kRLP;
+      const float q0 = fmaf(wy1, q[r1 + lane], wy0 * q[r0 + lane]);
+      const float qd = fmaf(wy1, q[r1 + i1], wy0 * q[r0 + i1]) - q0;
 #pragma unroll 1
       for (int j = 0; j < npx; ++j) {
         const float z = my_z[j];
         const float om = z == 1.f ? om_pos : (z == 0.f ? om_neg : 0.f);
         if (om == 0.f) continue;
-        const Lerp lx = lerp_ac(x0 + j, p.w, p.W);
-        if (lx.i0 != cur) {
-          if (cur >= 0) flush(cur);
-          cur = lx.i0;
-        }
-        const float w00 = wy0 * (1.f - lx.l), w01 = wy0 * lx.l, w10 = wy1 * (1.f - lx.l), w11 = wy1 * lx.l;
-        const float xd = fmaf(w00, q[r0 + lx.i0], fmaf(w01, q[r0 + lx.i1], fmaf(w10, q[r1 + lx.i0], w11 * q[r1 + lx.i1])));
+        const float l = t.scale * static_cast<float>(xs + j) - fc;
+        const float xd = fmaf(l, qd, q0);
         const float sg = 1.f / (1.f + __expf(-xd));
         const float g = c_bce * om * (sg - z);
-        b0 = fmaf(g, 1.f - lx.l, b0);
-        b1 = fmaf(g, lx.l, b1);
+        b0 = fmaf(g, 1.f - l, b0);
+        b1 = fmaf(g, l, b1);
       }
-      if (cur >= 0) flush(cur);
+      const float left = __shfl_up_sync(0xffffffffu, b1, 1);
+      float mine = b0 + (lane > 0 ? left : 0.f);
+      if (i1 == lane) mine += b1;
+      atomicAdd(tb + r0 + lane, mine * wy0);
+      atomicAdd(tb + r1 + lane, mine * wy1);
+      if (lane == 31 && i1 != lane) { atomicAdd(tb + r0 + i1, b1 * wy0); atomicAdd(tb + r1 + i1, b1 * wy1); }
     }
   }
   __syncthreads();
@@ -809,9 +950,9 @@ __global__ void __launch_bounds__(256, CMAX <= 20 ? 2 : 1) crit_backward_run_ker
     const int ch = i / kRLP, r = i - ch * kRLP;
     const int gy = t.ly0 + r / kRLW, gx = t.lx0 + r % kRLW;
     if (gy >= p.h || gx >= p.w) continue;
-    float* dst = ch < p.C ? p.g_p + (static_cast<size_t>(t.n) * p.C + ch) * plane
-                          : (ch < 2 * p.C ? p.g_m + (static_cast<size_t>(t.n) * p.C + (ch - p.C)) * plane
-                                          : p.g_d + static_cast<size_t>(t.n) * plane);
+    float* dst = ch < C ? p.g_p + (static_cast<size_t>(t.n) * C + ch) * plane
+                        : (ch < 2 * C ? p.g_m + (static_cast<size_t>(t.n) * C + (ch - C)) * plane
+                                      : p.g_d + static_cast<size_t>(t.n) * plane);
     atomicAdd(dst + static_cast<size_t>(gy) * p.w + gx, g);
   }
 }
@@ -822,28 +963,38 @@ inline bool footprint_fits(const CritParams& p, int tw, int th, int lw, int lh) 
   const long sw = std::min<long>(span(std::min(tw, p.W), p.w, p.W), p.w), sh = std::min<long>(span(std::min(th, p.H), p.h, p.H), p.h);
   return sw <= lw && sh <= lh;
 }
-template <int CMAX>
+// column-owned run kernels: 8 label rows must span <= kRLH low-res rows and a low-res column <= kMaxRun label pixels
+inline bool column_runs_fit(const CritParams& p) {
+  auto span = [](int t, int in, int out) { return out > 1 ? (static_cast<long>(t - 1) * (in - 1)) / (out - 1) + 3 : 1; };
+  const long sh = std::min<long>(span(std::min(kRH, p.H), p.h, p.H), p.h);
+  if (p.w < 2 || p.W < 2) return false;
+  const long per_col = (static_cast<long>(p.W) - 1 + (p.w - 2)) / (p.w - 1) + 1;    // ceil((W-1)/(w-1)) + 1
+  return sh <= kRLH && per_col <= kMaxRun;
+}
+template <int CMAX, bool EXACT>
 cudaError_t launch_run_kernels(const CritParams& p, const SelState* sel, bool backward, cudaStream_t st) {
-  const unsigned blocks = static_cast<unsigned>(p.N) * ((p.W + kRW - 1) / kRW) * ((p.H + kRH - 1) / kRH);
+  const unsigned blocks = static_cast<unsigned>(p.N) * ((p.w + kCT - 1) / kCT) * ((p.H + kRH - 1) / kRH);
   const size_t lo_bytes = static_cast<size_t>(2 * p.C + 1) * kRLP * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     const int max_bytes = (2 * CMAX + 1) * kRLP * static_cast<int>(sizeof(float));
-    cudaError_t e = cudaFuncSetAttribute(crit_pixel_run_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes);
+    cudaError_t e = cudaFuncSetAttribute(crit_pixel_run_kernel<CMAX, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(crit_backward_run_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             2 * max_bytes + 2 * kRH * kRS * 4);
+    e = cudaFuncSetAttribute(crit_backward_run_kernel<CMAX, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             2 * max_bytes + 2 * kRH * kCS * 4);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  if (!backward) crit_pixel_run_kernel<CMAX><<<blocks, 256, lo_bytes, st>>>(p);
-  else crit_backward_run_kernel<CMAX><<<blocks, 256, 2 * lo_bytes + 2 * kRH * kRS * 4, st>>>(p, sel);
+  if (!backward) crit_pixel_run_kernel<CMAX, EXACT><<<blocks, 256, lo_bytes, st>>>(p);
+  else crit_backward_run_kernel<CMAX, EXACT><<<blocks, 256, 2 * lo_bytes + 2 * kRH * kCS * 4, st>>>(p, sel);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const CritParams& p, const SelState* sel, bool backward, cudaStream_t st) {
-  if (p.C <= 12) return launch_run_kernels<12>(p, sel, backward, st);
-  if (p.C <= 20) return launch_run_kernels<20>(p, sel, backward, st);
-  return launch_run_kernels<kMaxC>(p, sel, backward, st);
+  if (p.C == 19) return launch_run_kernels<19, true>(p, sel, backward, st);    // Cityscapes
+  if (p.C == 11) return launch_run_kernels<11, true>(p, sel, backward, st);    // CamVid
+  if (p.C <= 12) return launch_run_kernels<12, false>(p, sel, backward, st);
+  if (p.C <= 20) return launch_run_kernels<20, false>(p, sel, backward, st);
+  return launch_run_kernels<kMaxC, false>(p, sel, backward, st);
 }
 
 // --------------------------------------------------------------------------------------- post-processing
@@ -1068,7 +1219,7 @@ cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaS
   cudaError_t e;
   if ((e = cudaMemsetAsync(p.accum, 0, A_COUNT * sizeof(double) + 512 + 2 * 4096 * sizeof(unsigned) + 256, st)) != cudaSuccess) return e;
   const unsigned blocks = static_cast<unsigned>((npix + 255) / 256);
-  const bool run_path = footprint_fits(p, kRW, kRH, kRLW, kRLH);
+  const bool run_path = column_runs_fit(p);
   if (run_path) { if ((e = launch_run(p, nullptr, false, st)) != cudaSuccess) return e; }
   else if (p.C <= 12) crit_pixel_kernel<12><<<blocks, 256, 0, st>>>(p);
   else if (p.C <= 20) crit_pixel_kernel<20><<<blocks, 256, 0, st>>>(p);

@@ -271,6 +271,7 @@ struct BnFwdParams {
   View x, res, z;
   const float *gamma, *beta, *conv_bias;
   float *run_mean, *run_var, *mean, *invstd;
+  float *scale, *shift;   // the folded per-channel affine this launch applied (the backward derives the ReLU mask from it)
   double* sums;      // [2C], zero on entry, cleared on exit
   unsigned* sync;    // [2], zero on entry, cleared on exit
   double count;
@@ -323,6 +324,8 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_fwd_fused_kernel(BnFwdParams
       if (blockIdx.x == 0) {
         p.mean[c] = static_cast<float>(m);
         p.invstd[c] = is;
+        p.scale[c] = red[c];
+        p.shift[c] = red[C + c];
         if (p.run_mean) {
           // the conv bias (stem convs) cancels in the normalisation but is part of the batch mean the reference tracks
           const float bm = static_cast<float>(m) + (p.conv_bias ? p.conv_bias[c] : 0.f);
@@ -371,13 +374,23 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_fwd_fused_kernel(BnFwdParams
 struct BnBwdParams {
   View x, dz, z, dx, dres;
   const float *mean, *invstd, *gamma;
+  const float *scale, *shift;   // forward's folded affine (mask_x)
   float *dgamma, *dbeta;
   double* sums;
   unsigned* sync;
   double count;
   long pix_per_block;
   int relu, acc_dx, acc_dres, stage_iters;
+  int mask_x;   // relu without a residual: z > 0  <=>  bf16(relu(scale * x + shift)) > 0, recomputed from x (already loaded)
+                // exactly as the forward evaluated it -- the output tensor z is not read at all
 };
+// z = bf16(max(fma(x, sc, sh), 0)) > 0  <=>  fma(x, sc, sh) > 0 (same fma as bn_fwd_fused_kernel; a positive fp32 value only
+// rounds to a zero bf16 below 2^-134, where either sub-gradient of the ReLU kink is valid): one fma + select per element, the
+// same instruction count as unpacking and testing z -- these kernels are issue-bound, not bandwidth-bound
+__device__ __forceinline__ void mask_from_x(F8& g, const F8& xv, const float (&sc)[8], const float (&sh)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) if (!(fmaf(xv.v[e], sc[e], sh[e]) > 0.f)) g.v[e] = 0.f;
+}
 __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams p) {
   extern __shared__ uint4 smem_v[];
   float* red = reinterpret_cast<float*>(smem_v);
@@ -387,12 +400,17 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
   const bool active = ln < lanes;
   const long npix = static_cast<long>(p.x.N) * p.x.H * p.x.W;
   const long p0 = static_cast<long>(blockIdx.x) * p.pix_per_block, p1 = min(p0 + p.pix_per_block, npix);
-  float a[8], b[8], mu[8], is[8];
+  float a[8], b[8], mu[8], is[8], msc[8], msh[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+  const bool relu_z = p.relu && !p.mask_x;   // the mask has to come from the stored output (residual blocks)
   if (active) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) { mu[e] = p.mean[cg * 8 + e]; is[e] = p.invstd[cg * 8 + e]; }
+    if (p.mask_x) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { msc[e] = p.scale[cg * 8 + e]; msh[e] = p.shift[cg * 8 + e]; }
+    }
     int it = 0;
     for (long q = p0 + ln; q < p1; q += static_cast<long>(lanes) * 2, it += 2) {
       uint4 ux[2], ug[2], uz[2];
@@ -402,13 +420,16 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
         const bool ok = qq < p1;
         ux[k] = ok ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
         ug[k] = ok ? __ldg(reinterpret_cast<const uint4*>(p.dz.ptr + qq * p.dz.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
-        uz[k] = (ok && p.relu) ? __ldg(reinterpret_cast<const uint4*>(p.z.ptr + qq * p.z.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
+        uz[k] = (ok && relu_z) ? __ldg(reinterpret_cast<const uint4*>(p.z.ptr + qq * p.z.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const F8 xv = unpack8(ux[k]);
         F8 g = unpack8(ug[k]);
-        if (p.relu) {
+        if (p.mask_x) {
+          mask_from_x(g, xv, msc, msh);
+          ug[k] = pack8(g);
+        } else if (p.relu) {
           const F8 zv = unpack8(uz[k]);
 #pragma unroll
           for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
@@ -457,7 +478,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
                        : (ok ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : zero);
         ug[k] = parked ? park[((it + k) * 2 + 1) * kBnThreads + threadIdx.x]
                        : (ok ? __ldg(reinterpret_cast<const uint4*>(p.dz.ptr + qq * p.dz.ps + cg * 8)) : zero);
-        uz[k] = (!parked && ok && p.relu) ? __ldg(reinterpret_cast<const uint4*>(p.z.ptr + qq * p.z.ps + cg * 8)) : zero;
+        uz[k] = (!parked && ok && relu_z) ? __ldg(reinterpret_cast<const uint4*>(p.z.ptr + qq * p.z.ps + cg * 8)) : zero;
         ur[k] = (ok && p.dres.ptr && p.acc_dres) ? *reinterpret_cast<const uint4*>(p.dres.ptr + qq * p.dres.ps + cg * 8) : zero;
         uo[k] = (ok && p.dx.ptr && p.acc_dx) ? *reinterpret_cast<const uint4*>(p.dx.ptr + qq * p.dx.ps + cg * 8) : zero;
       }
@@ -467,7 +488,9 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
         if (qq >= p1) break;
         const F8 xv = unpack8(ux[k]);
         F8 g = unpack8(ug[k]);
-        if (p.relu && !(it + k < p.stage_iters)) {   // parked gradients are already masked
+        if (p.mask_x && !(it + k < p.stage_iters)) {   // parked gradients are already masked
+          mask_from_x(g, xv, msc, msh);
+        } else if (p.relu && !(it + k < p.stage_iters)) {
           const F8 zv = unpack8(uz[k]);
 #pragma unroll
           for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
@@ -553,11 +576,19 @@ __device__ __forceinline__ void lerp_af(int dst, int in, int out, int& i0, int& 
   i1 = i0 + (i0 < in - 1 ? 1 : 0);
   l = src - static_cast<float>(i0);
 }
+// One output element group (low-res pixel x 8 channels) is gathered by LANES cooperating lanes: lane j takes the hi-res rows
+// y0 + j, y0 + j + LANES, ... of the window and the partial sums are combined with shuffles.  (One thread per output walked a
+// window of up to (2*scale+3)^2 hi-res pixels serially -- the whole 16x16 map for the global-pool branch of PAPPM -- with a few
+// hundred threads in flight: 0.1 ms for a few hundred KB.)
+template <int LANES>
 __global__ void __launch_bounds__(256) upsample_transpose_kernel(View dhi, View dlow, int accumulate) {
   const int groups = dlow.C >> 3;
   const long total = static_cast<long>(dlow.N) * dlow.H * dlow.W * groups;
-  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long idx_raw = gid / LANES;
+  const int sub = static_cast<int>(gid % LANES);
+  const bool live = idx_raw < total;
+  const long idx = live ? idx_raw : total - 1;     // surplus lanes of the last warp keep the shuffles convergent
   const int cg = static_cast<int>(idx % groups);
   const long p = idx / groups;
   const int lx = static_cast<int>(p % dlow.W);
@@ -571,7 +602,7 @@ __global__ void __launch_bounds__(256) upsample_transpose_kernel(View dhi, View 
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int y = y0; y <= y1; ++y) {
+  for (int y = y0 + sub; y <= y1; y += LANES) {
     int a0, a1; float la;
     lerp_af(y, dlow.H, dhi.H, a0, a1, la);
     float wy = 0.f;
@@ -591,6 +622,12 @@ __global__ void __launch_bounds__(256) upsample_transpose_kernel(View dhi, View 
       for (int e = 0; e < 8; ++e) acc[e] += w * g.v[e];
     }
   }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+  }
+  if (!live || sub != 0) return;
   F8 o;
   bf16* dst = dlow.ptr + p * dlow.ps + cg * 8;
   if (accumulate) {
@@ -983,8 +1020,8 @@ static cudaError_t bn_fused_geometry(const View& x, int num_sms, int vec_per_ite
 bool bn_fused_supported(int C) { return C % 8 == 0 && C / 8 >= 1 && C / 8 <= kBnThreads && 3 * C * sizeof(float) <= 40 * 1024; }
 
 cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma, const float* beta, const float* conv_bias,
-                                    float* mean, float* invstd, float* run_mean, float* run_var, double* sums, unsigned* sync,
-                                    int relu, int num_sms, cudaStream_t st) {
+                                    float* mean, float* invstd, float* scale, float* shift, float* run_mean, float* run_var,
+                                    double* sums, unsigned* sync, int relu, int num_sms, cudaStream_t st) {
   BnFwdParams p;
   unsigned blocks = 0;
   size_t smem = 0;
@@ -992,14 +1029,16 @@ cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma
   if (e != cudaSuccess) return e;
   p.x = x; p.res = res; p.z = z; p.gamma = gamma; p.beta = beta; p.conv_bias = conv_bias; p.mean = mean; p.invstd = invstd;
   p.run_mean = run_mean; p.run_var = run_var; p.sums = sums; p.sync = sync; p.relu = relu;
+  p.scale = scale; p.shift = shift;
   p.count = static_cast<double>(x.N) * x.H * x.W;
   bn_fwd_fused_kernel<<<blocks, kBnThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
-                                     const float* gamma, double* sums, unsigned* sync, int relu, int acc_dx, int acc_dres,
-                                     float* dgamma, float* dbeta, int num_sms, cudaStream_t st) {
+                                     const float* gamma, const float* scale, const float* shift, int mask_x, double* sums,
+                                     unsigned* sync, int relu, int acc_dx, int acc_dres, float* dgamma, float* dbeta, int num_sms,
+                                     cudaStream_t st) {
   BnBwdParams p;
   unsigned blocks = 0;
   size_t smem = 0;
@@ -1007,6 +1046,7 @@ cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres
   if (e != cudaSuccess) return e;
   p.x = x; p.dz = dz; p.z = z; p.dx = dx; p.dres = dres; p.mean = mean; p.invstd = invstd; p.gamma = gamma;
   p.dgamma = dgamma; p.dbeta = dbeta; p.sums = sums; p.sync = sync; p.relu = relu; p.acc_dx = acc_dx; p.acc_dres = acc_dres;
+  p.scale = scale; p.shift = shift; p.mask_x = (mask_x && relu) ? 1 : 0;
   p.count = static_cast<double>(x.N) * x.H * x.W;
   bn_bwd_fused_kernel<<<blocks, kBnThreads, smem, st>>>(p);
   return cudaGetLastError();
@@ -1138,7 +1178,11 @@ cudaError_t nchw_to_nhwc_launch(const float* x, int N, int C, int H, int W, View
 
 cudaError_t upsample_transpose_launch(View dhi, View dlow, int accumulate, cudaStream_t st) {
   const long total = static_cast<long>(dlow.N) * dlow.H * dlow.W * (dlow.C / 8);
-  upsample_transpose_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dhi, dlow, accumulate);
+  // rows of the gather window per output: split them over 32 / 8 cooperating lanes when the window is tall
+  const int rows = 2 * ((dhi.H + dlow.H - 1) / dlow.H) + 3;
+  if (rows >= 24 || total < 4096) upsample_transpose_kernel<32><<<blocks_for(total * 32, 256), 256, 0, st>>>(dhi, dlow, accumulate);
+  else if (rows >= 16) upsample_transpose_kernel<8><<<blocks_for(total * 8, 256), 256, 0, st>>>(dhi, dlow, accumulate);
+  else upsample_transpose_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(dhi, dlow, accumulate);
   return cudaGetLastError();
 }
 

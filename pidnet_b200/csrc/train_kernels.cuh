@@ -26,12 +26,15 @@ cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, cons
 // Fused single-launch forms (persistent grid + grid barrier, loaded vectors parked in shared memory between the
 // statistics pass and the apply pass).  `sync`: device unsigned[2], zero on entry (self-clearing like `sums`).
 bool bn_fused_supported(int C);
+// `scale` / `shift` ([C] each): the folded affine the forward applied, kept for the backward; mask_x = 1 (ReLU without a residual):
+// the backward recomputes the ReLU mask from x with that affine instead of reading the stored output z.
 cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma, const float* beta, const float* conv_bias,
-                                    float* mean, float* invstd, float* run_mean, float* run_var, double* sums, unsigned* sync,
-                                    int relu, int num_sms, cudaStream_t st);
+                                    float* mean, float* invstd, float* scale, float* shift, float* run_mean, float* run_var,
+                                    double* sums, unsigned* sync, int relu, int num_sms, cudaStream_t st);
 cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
-                                     const float* gamma, double* sums, unsigned* sync, int relu, int acc_dx, int acc_dres,
-                                     float* dgamma, float* dbeta, int num_sms, cudaStream_t st);
+                                     const float* gamma, const float* scale, const float* shift, int mask_x, double* sums,
+                                     unsigned* sync, int relu, int acc_dx, int acc_dres, float* dgamma, float* dbeta, int num_sms,
+                                     cudaStream_t st);
 
 // ---- fused SGD step over flat fp32 buffers (n a multiple of 4, pointers 16-byte aligned); `first` = no momentum history yet
 cudaError_t sgd_step_launch(float* p, const float* g, float* buf, long n, float lr, float momentum, float dampening, float wd,

@@ -70,8 +70,16 @@ def test_fused_matches_oracle_large(case):
     assert close(out[0].item(), losses.mean().item()), (out[0].item(), losses.mean().item())
     assert close(out[1].item(), ll[0].mean().item()) and close(out[2].item(), ll[1].item())
     assert abs(out[3].item() - acc.item()) < 1e-6
+    # A pixel whose target probability lies within fp32 rounding of the OHEM threshold can fall on either side of it (the oracle's
+    # softmax and the kernel's round differently): it moves <= (bw1 / K1 + sb / K2) * class weight of gradient into the 4 low-res
+    # cells x C channels it touches.  Everything else must agree to 2e-3 of the largest gradient.
+    wmax = float(weight.max()) if weight is not None else 1.0
+    flip = 2.0 * (1.0 / max(float(out[10]), 1.0) + 1.0 / max(float(out[11]), 1.0)) * wmax
     for gi, r in zip(g, ro):
-        assert (gi - r.grad).abs().max().item() <= 2e-3 * r.grad.abs().max().item()
+        d = (gi - r.grad).abs()
+        tight = 2e-3 * r.grad.abs().max().item()
+        assert d.max().item() <= tight + flip, (d.max().item(), tight, flip)
+        assert int((d > tight).sum()) <= 2 * 4 * ncls, 'more than two borderline pixels disagree with the oracle'
 
 
 def test_upsample_and_fullmodel_surface():

@@ -21,8 +21,16 @@ def short(name):
 
 
 def main(paths):
-    print('| # | kernel | ' + ' | '.join(c[1] for c in COLS) + ' |')
-    print('|---|---|' + '---|' * len(COLS))
+    global COLS
+    # tensor-pipe activity (tcgen05 MMAs): whichever of ncu's tensor-pipe metrics this capture holds
+    hdr0 = next(csv.reader(open(paths[0])))
+    want = [('sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed', 'tensor ops bf16->fp32 % of peak'),
+            ('TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor pipe active % (elapsed)'),
+            ('sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active', 'tensor hmma subpipe inst % (active)')]
+    COLS = COLS[:3] + [w for w in want if w[0] in hdr0] + COLS[3:]
+    derived = 'TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg' in hdr0
+    print('| # | kernel | ' + ' | '.join(c[1] for c in COLS) + (' | tensor sub-pipe cycles active / (4 x elapsed) |' if derived else ' |'))
+    print('|---|---|' + '---|' * (len(COLS) + (1 if derived else 0)))
     n = 0
     for path in paths:
         rows = list(csv.reader(open(path)))
@@ -41,6 +49,14 @@ def main(paths):
                     pass
                 u = units[i]
                 cells.append(f'{v} {u}'.strip() if u not in ('', '%') else v + (' %' if u == '%' else ''))
+            # tcgen05 activity: ncu reports it on the hmma sub-pipe counter (cycles summed over the SM's four tensor sub-pipes)
+            key_t, key_e = 'TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg', 'sm__cycles_elapsed.avg'
+            if key_t in hdr and key_e in hdr:
+                try:
+                    t = float(r[hdr.index(key_t)].replace(',', '')); e = float(r[hdr.index(key_e)].replace(',', ''))
+                    cells.append(f'{100 * t / (4 * e):.1f} %')
+                except ValueError:
+                    cells.append('-')
             print(f'| {n} | `{short(r[hdr.index("Kernel Name")])}` | ' + ' | '.join(cells) + ' |')
             n += 1
 
