@@ -278,6 +278,9 @@ struct BnFwdParams {
   long pix_per_block;
   int relu, stage_iters;
 };
+// (loops: each thread walks its own pixels -- q = p0 + ln + m * lanes -- with running pointers, full trips of 4 without
+// per-element bounds / parking tests and a scalar tail; ncu on the first form: 142 instructions per 16-byte vector, half of them
+// 64-bit index arithmetic and predicates, at 51 % issue-active)
 __global__ void __launch_bounds__(kBnThreads, 2) bn_fwd_fused_kernel(BnFwdParams p) {
   extern __shared__ uint4 smem_v[];
   float* red = reinterpret_cast<float*>(smem_v);
@@ -287,25 +290,39 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_fwd_fused_kernel(BnFwdParams
   const bool active = ln < lanes;
   const long npix = static_cast<long>(p.x.N) * p.x.H * p.x.W;
   const long p0 = static_cast<long>(blockIdx.x) * p.pix_per_block, p1 = min(p0 + p.pix_per_block, npix);
+  const int nmine = (active && p1 > p0 + ln) ? static_cast<int>((p1 - p0 - ln + lanes - 1) / lanes) : 0;   // my pixels
+  const int nfull = nmine & ~3;
+  const int stage = p.stage_iters;                   // multiple of 4
+  const bf16* xp = p.x.ptr + (p0 + ln) * p.x.ps + cg * 8;
+  const long xs = static_cast<long>(lanes) * p.x.ps;
+  uint4* mypark = park + threadIdx.x;
   float a[8], b[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
-  if (active) {
-    int it = 0;
-    for (long q = p0 + ln; q < p1; q += static_cast<long>(lanes) * 4, it += 4) {
+  {
+    const bf16* xq = xp;
+    int m = 0;
+    for (; m < nfull; m += 4, xq += 4 * xs) {
       uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long qq = q + static_cast<long>(k) * lanes;
-        u[k] = qq < p1 ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xq + k * xs));
+      if (m < stage) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mypark[(m + k) * kBnThreads] = u[k];
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (it + k < p.stage_iters) park[(it + k) * kBnThreads + threadIdx.x] = u[k];
         const F8 f = unpack8(u[k]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) { a[e] += f.v[e]; b[e] = fmaf(f.v[e], f.v[e], b[e]); }
       }
+    }
+    for (; m < nmine; ++m, xq += xs) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xq));
+      if (m < stage) mypark[m * kBnThreads] = u;
+      const F8 f = unpack8(u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a[e] += f.v[e]; b[e] = fmaf(f.v[e], f.v[e], b[e]); }
     }
   }
   block_channel_reduce(red, a, b, groups, lanes, cg, ln, active, C, p.sums);
@@ -337,36 +354,56 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_fwd_fused_kernel(BnFwdParams
     }
   }
   grid_depart(p.sync, p.sums, 2 * C, gridDim.x);   // (contains the __syncthreads that publishes the table)
-  if (active) {
+  if (nmine > 0) {
     float sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sc[e] = red[cg * 8 + e]; sh[e] = red[C + cg * 8 + e]; }
+    const bool has_res = p.res.ptr != nullptr;
+    const bf16* rp = has_res ? p.res.ptr + (p0 + ln) * p.res.ps + cg * 8 : nullptr;
+    const long rs = static_cast<long>(lanes) * p.res.ps;
+    bf16* zp = p.z.ptr + (p0 + ln) * p.z.ps + cg * 8;
+    const long zs = static_cast<long>(lanes) * p.z.ps;
+    const bool relu = p.relu != 0;
+    auto apply = [&](const uint4& u, const uint4& r, bf16* dst) {
+      F8 f = unpack8(u);
+      const F8 rv = unpack8(r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        f.v[e] = fmaf(f.v[e], sc[e], sh[e]) + rv.v[e];
+        if (relu) f.v[e] = fmaxf(f.v[e], 0.f);
+      }
+      st8(dst, f);
+    };
+    const uint4 zero = make_uint4(0, 0, 0, 0);
     // four pixels per trip: all loads of the batch are issued before the first use (the parked vectors cover only the
-    // first stage_iters trips; the rest comes back from L2)
-    int it = 0;
-    for (long q = p0 + ln; q < p1; q += static_cast<long>(lanes) * 4, it += 4) {
+    // first `stage` of a thread's pixels; the rest comes back from L2)
+    const bf16* xq = xp;
+    int m = 0;
+    for (; m < nfull; m += 4, xq += 4 * xs, zp += 4 * zs) {
       uint4 u[4], r[4];
+      if (m < stage) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long qq = q + static_cast<long>(k) * lanes;
-        const bool ok = qq < p1;
-        u[k] = it + k < p.stage_iters ? park[(it + k) * kBnThreads + threadIdx.x]
-                                      : (ok ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : make_uint4(0, 0, 0, 0));
-        r[k] = (ok && p.res.ptr) ? __ldg(reinterpret_cast<const uint4*>(p.res.ptr + qq * p.res.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < 4; ++k) u[k] = mypark[(m + k) * kBnThreads];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xq + k * xs));
+      }
+      if (has_res) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = __ldg(reinterpret_cast<const uint4*>(rp + k * rs));
+        rp += 4 * rs;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = zero;
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long qq = q + static_cast<long>(k) * lanes;
-        if (qq >= p1) break;
-        F8 f = unpack8(u[k]);
-        const F8 rv = unpack8(r[k]);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          f.v[e] = fmaf(f.v[e], sc[e], sh[e]) + rv.v[e];
-          if (p.relu) f.v[e] = fmaxf(f.v[e], 0.f);
-        }
-        st8(p.z.ptr + qq * p.z.ps + cg * 8, f);
-      }
+      for (int k = 0; k < 4; ++k) apply(u[k], r[k], zp + k * zs);
+    }
+    for (; m < nmine; ++m, xq += xs, zp += zs) {
+      const uint4 u = m < stage ? mypark[m * kBnThreads] : __ldg(reinterpret_cast<const uint4*>(xq));
+      uint4 r = zero;
+      if (has_res) { r = __ldg(reinterpret_cast<const uint4*>(rp)); rp += rs; }
+      apply(u, r, zp);
     }
   }
 }
@@ -391,6 +428,7 @@ __device__ __forceinline__ void mask_from_x(F8& g, const F8& xv, const float (&s
 #pragma unroll
   for (int e = 0; e < 8; ++e) if (!(fmaf(xv.v[e], sc[e], sh[e]) > 0.f)) g.v[e] = 0.f;
 }
+template <bool HAS_DR>   // a residual input receives the masked gradient too (residual blocks); compiled out otherwise
 __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams p) {
   extern __shared__ uint4 smem_v[];
   float* red = reinterpret_cast<float*>(smem_v);
@@ -400,48 +438,77 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
   const bool active = ln < lanes;
   const long npix = static_cast<long>(p.x.N) * p.x.H * p.x.W;
   const long p0 = static_cast<long>(blockIdx.x) * p.pix_per_block, p1 = min(p0 + p.pix_per_block, npix);
-  float a[8], b[8], mu[8], is[8], msc[8], msh[8];
+  const int nmine = (active && p1 > p0 + ln) ? static_cast<int>((p1 - p0 - ln + lanes - 1) / lanes) : 0;   // my pixels
+  const int nfull = nmine & ~1;
+  const int stage = p.stage_iters;                   // multiple of 2
+  const long first = p0 + ln;
+  const bf16* xp = p.x.ptr + first * p.x.ps + cg * 8;
+  const bf16* gp = p.dz.ptr + first * p.dz.ps + cg * 8;
+  const long xs = static_cast<long>(lanes) * p.x.ps, gs = static_cast<long>(lanes) * p.dz.ps;
+  const bool relu_z = p.relu && !p.mask_x;   // the mask has to come from the stored output (residual blocks)
+  const bool mask_x = p.mask_x != 0;
+  const bf16* zp = relu_z ? p.z.ptr + first * p.z.ps + cg * 8 : nullptr;
+  const long zs = static_cast<long>(lanes) * p.z.ps;
+  uint4* mypark = park + threadIdx.x;
+  float a[8], b[8], msc[8], msh[8];   // a = sum dz', b = sum dz' * x (centred and scaled after the grid barrier, in fp64)
 #pragma unroll
   for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
-  const bool relu_z = p.relu && !p.mask_x;   // the mask has to come from the stored output (residual blocks)
-  if (active) {
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  // masked gradient of one vector (ReLU backward), returned unpacked; `ug` is rewritten with the masked values
+  auto masked = [&](const F8& xv, uint4& ug, const uint4& uz) {
+    F8 g = unpack8(ug);
+    if (mask_x) {
+      mask_from_x(g, xv, msc, msh);
+      ug = pack8(g);
+    } else if (relu_z) {
+      const F8 zv = unpack8(uz);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { mu[e] = p.mean[cg * 8 + e]; is[e] = p.invstd[cg * 8 + e]; }
-    if (p.mask_x) {
+      for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
+      ug = pack8(g);
+    }
+    return g;
+  };
+  if (nmine > 0) {
+    if (mask_x) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) { msc[e] = p.scale[cg * 8 + e]; msh[e] = p.shift[cg * 8 + e]; }
     }
-    int it = 0;
-    for (long q = p0 + ln; q < p1; q += static_cast<long>(lanes) * 2, it += 2) {
+    const bf16 *xq = xp, *gq = gp, *zq = zp;
+    int m = 0;
+    for (; m < nfull; m += 2, xq += 2 * xs, gq += 2 * gs) {
       uint4 ux[2], ug[2], uz[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const long qq = q + static_cast<long>(k) * lanes;
-        const bool ok = qq < p1;
-        ux[k] = ok ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
-        ug[k] = ok ? __ldg(reinterpret_cast<const uint4*>(p.dz.ptr + qq * p.dz.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
-        uz[k] = (ok && relu_z) ? __ldg(reinterpret_cast<const uint4*>(p.z.ptr + qq * p.z.ps + cg * 8)) : make_uint4(0, 0, 0, 0);
+        ux[k] = __ldg(reinterpret_cast<const uint4*>(xq + k * xs));
+        ug[k] = __ldg(reinterpret_cast<const uint4*>(gq + k * gs));
+        uz[k] = relu_z ? __ldg(reinterpret_cast<const uint4*>(zq + k * zs)) : zero;
       }
+      if (relu_z) zq += 2 * zs;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const F8 xv = unpack8(ux[k]);
-        F8 g = unpack8(ug[k]);
-        if (p.mask_x) {
-          mask_from_x(g, xv, msc, msh);
-          ug[k] = pack8(g);
-        } else if (p.relu) {
-          const F8 zv = unpack8(uz[k]);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
-          ug[k] = pack8(g);
-        }
-        if (it + k < p.stage_iters) {
-          park[((it + k) * 2 + 0) * kBnThreads + threadIdx.x] = ux[k];
-          park[((it + k) * 2 + 1) * kBnThreads + threadIdx.x] = ug[k];
+        const F8 g = masked(xv, ug[k], uz[k]);
+        if (m < stage) {
+          mypark[((m + k) * 2 + 0) * kBnThreads] = ux[k];
+          mypark[((m + k) * 2 + 1) * kBnThreads] = ug[k];
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { a[e] += g.v[e]; b[e] = fmaf(g.v[e], (xv.v[e] - mu[e]) * is[e], b[e]); }
+        for (int e = 0; e < 8; ++e) { a[e] += g.v[e]; b[e] = fmaf(g.v[e], xv.v[e], b[e]); }
       }
+    }
+    for (; m < nmine; ++m, xq += xs, gq += gs) {
+      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(xq));
+      uint4 ug = __ldg(reinterpret_cast<const uint4*>(gq));
+      uint4 uz = zero;
+      if (relu_z) { uz = __ldg(reinterpret_cast<const uint4*>(zq)); zq += zs; }
+      const F8 xv = unpack8(ux);
+      const F8 g = masked(xv, ug, uz);
+      if (m < stage) {
+        mypark[(m * 2 + 0) * kBnThreads] = ux;
+        mypark[(m * 2 + 1) * kBnThreads] = ug;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a[e] += g.v[e]; b[e] = fmaf(g.v[e], xv.v[e], b[e]); }
     }
   }
   block_channel_reduce(red, a, b, groups, lanes, cg, ln, active, C, p.sums);
@@ -449,7 +516,9 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
   {
     const double inv = 1.0 / p.count;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const double sb = __ldcg(p.sums + c), sg = __ldcg(p.sums + C + c);
+      // sum dz' * xhat = invstd * (sum dz' * x - mean * sum dz')
+      const double sb = __ldcg(p.sums + c);
+      const double sg = (__ldcg(p.sums + C + c) - static_cast<double>(p.mean[c]) * sb) * static_cast<double>(p.invstd[c]);
       const float isf = p.invstd[c], A = p.gamma[c] * isf;
       const float B = -A * isf * static_cast<float>(sg * inv);
       red[c] = A;
@@ -462,54 +531,85 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_fused_kernel(BnBwdParams
     }
   }
   grid_depart(p.sync, p.sums, 2 * C, gridDim.x);   // (contains the __syncthreads that publishes the table)
-  if (active && (p.dx.ptr || p.dres.ptr)) {
-    float cA[8], cB[8], cD[8];
+  if (nmine > 0 && (p.dx.ptr || p.dres.ptr)) {
+    // (A = gamma * invstd is also the forward's scale: with mask_x the same registers serve the ReLU mask of unparked vectors)
+    float cB[8], cD[8];
+    float (&cA)[8] = msc;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { cA[e] = red[cg * 8 + e]; cB[e] = red[C + cg * 8 + e]; cD[e] = red[2 * C + cg * 8 + e]; }
-    int it = 0;
-    for (long q = p0 + ln; q < p1; q += static_cast<long>(lanes) * 2, it += 2) {   // two pixels per trip, loads first
+    const bool has_dx = p.dx.ptr != nullptr;
+    constexpr bool has_dr = HAS_DR;
+    const bool acc_dx = has_dx && p.acc_dx, acc_dr = has_dr && p.acc_dres;
+    bf16* dxp = has_dx ? p.dx.ptr + first * p.dx.ps + cg * 8 : nullptr;
+    bf16* drp = has_dr ? p.dres.ptr + first * p.dres.ps + cg * 8 : nullptr;
+    const long dxs = static_cast<long>(lanes) * p.dx.ps, drs = static_cast<long>(lanes) * p.dres.ps;
+    auto emit = [&](const uint4& ux, const F8& g, const uint4& uo, const uint4& ur, bf16* dxq, bf16* drq) {
+      if (has_dr) {
+        const F8 old = unpack8(ur);
+        F8 r;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r.v[e] = g.v[e] + old.v[e];
+        st8(drq, r);
+      }
+      if (has_dx) {
+        const F8 xv = unpack8(ux);
+        const F8 old = unpack8(uo);
+        F8 o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = fmaf(cA[e], g.v[e], fmaf(cB[e], xv.v[e], cD[e])) + old.v[e];
+        st8(dxq, o);
+      }
+    };
+    const bf16 *xq = xp, *gq = gp, *zq = zp;
+    int m = 0;
+    for (; m < nfull; m += 2, xq += 2 * xs, gq += 2 * gs) {   // two pixels per trip, loads first
       uint4 ux[2], ug[2], uz[2], ur[2], uo[2];
+      const bool parked = m < stage;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const long qq = q + static_cast<long>(k) * lanes;
-        const bool ok = qq < p1, parked = it + k < p.stage_iters;
-        const uint4 zero = make_uint4(0, 0, 0, 0);
-        ux[k] = parked ? park[((it + k) * 2 + 0) * kBnThreads + threadIdx.x]
-                       : (ok ? __ldg(reinterpret_cast<const uint4*>(p.x.ptr + qq * p.x.ps + cg * 8)) : zero);
-        ug[k] = parked ? park[((it + k) * 2 + 1) * kBnThreads + threadIdx.x]
-                       : (ok ? __ldg(reinterpret_cast<const uint4*>(p.dz.ptr + qq * p.dz.ps + cg * 8)) : zero);
-        uz[k] = (!parked && ok && relu_z) ? __ldg(reinterpret_cast<const uint4*>(p.z.ptr + qq * p.z.ps + cg * 8)) : zero;
-        ur[k] = (ok && p.dres.ptr && p.acc_dres) ? *reinterpret_cast<const uint4*>(p.dres.ptr + qq * p.dres.ps + cg * 8) : zero;
-        uo[k] = (ok && p.dx.ptr && p.acc_dx) ? *reinterpret_cast<const uint4*>(p.dx.ptr + qq * p.dx.ps + cg * 8) : zero;
+        if (parked) {
+          ux[k] = mypark[((m + k) * 2 + 0) * kBnThreads];
+          ug[k] = mypark[((m + k) * 2 + 1) * kBnThreads];
+          uz[k] = zero;
+        } else {
+          ux[k] = __ldg(reinterpret_cast<const uint4*>(xq + k * xs));
+          ug[k] = __ldg(reinterpret_cast<const uint4*>(gq + k * gs));
+          uz[k] = relu_z ? __ldg(reinterpret_cast<const uint4*>(zq + k * zs)) : zero;
+        }
+        ur[k] = acc_dr ? *reinterpret_cast<const uint4*>(drp + k * drs) : zero;
+        uo[k] = acc_dx ? *reinterpret_cast<const uint4*>(dxp + k * dxs) : zero;
       }
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const long qq = q + static_cast<long>(k) * lanes;
-        if (qq >= p1) break;
-        const F8 xv = unpack8(ux[k]);
-        F8 g = unpack8(ug[k]);
-        if (p.mask_x && !(it + k < p.stage_iters)) {   // parked gradients are already masked
-          mask_from_x(g, xv, msc, msh);
-        } else if (p.relu && !(it + k < p.stage_iters)) {
-          const F8 zv = unpack8(uz[k]);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) if (!(zv.v[e] > 0.f)) g.v[e] = 0.f;
-        }
-        if (p.dres.ptr) {
-          const F8 old = unpack8(ur[k]);
-          F8 r;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) r.v[e] = g.v[e] + old.v[e];
-          st8(p.dres.ptr + qq * p.dres.ps + cg * 8, r);
-        }
-        if (p.dx.ptr) {
-          const F8 old = unpack8(uo[k]);
-          F8 o;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o.v[e] = fmaf(cA[e], g.v[e], fmaf(cB[e], xv.v[e], cD[e])) + old.v[e];
-          st8(p.dx.ptr + qq * p.dx.ps + cg * 8, o);
-        }
+        F8 g;
+        if (parked) g = unpack8(ug[k]);               // parked gradients are already masked
+        else g = masked(unpack8(ux[k]), ug[k], uz[k]);
+        emit(ux[k], g, uo[k], ur[k], has_dx ? dxp + k * dxs : nullptr, has_dr ? drp + k * drs : nullptr);
       }
+      if (relu_z) zq += 2 * zs;
+      if (has_dx) dxp += 2 * dxs;
+      if (has_dr) drp += 2 * drs;
+    }
+    for (; m < nmine; ++m, xq += xs, gq += gs) {
+      const bool parked = m < stage;
+      uint4 ux, ug, uz = zero;
+      if (parked) {
+        ux = mypark[(m * 2 + 0) * kBnThreads];
+        ug = mypark[(m * 2 + 1) * kBnThreads];
+      } else {
+        ux = __ldg(reinterpret_cast<const uint4*>(xq));
+        ug = __ldg(reinterpret_cast<const uint4*>(gq));
+        if (relu_z) uz = __ldg(reinterpret_cast<const uint4*>(zq));
+      }
+      const uint4 ur = acc_dr ? *reinterpret_cast<const uint4*>(drp) : zero;
+      const uint4 uo = acc_dx ? *reinterpret_cast<const uint4*>(dxp) : zero;
+      F8 g;
+      if (parked) g = unpack8(ug);
+      else g = masked(unpack8(ux), ug, uz);
+      emit(ux, g, uo, ur, dxp, drp);
+      if (relu_z) zq += zs;
+      if (has_dx) dxp += dxs;
+      if (has_dr) drp += drs;
     }
   }
 }
@@ -1013,7 +1113,7 @@ static cudaError_t bn_fused_geometry(const View& x, int num_sms, int vec_per_ite
   ppb = (ppb + unit - 1) / unit * unit;
   const size_t red = static_cast<size_t>(bn_red_floats(x.C)) * sizeof(float);
   const size_t per_iter = static_cast<size_t>(kBnThreads) * 16 * vec_per_iter;
-  stage_iters = red < kBnSmemBudget ? static_cast<int>((kBnSmemBudget - red) / per_iter) : 0;
+  stage_iters = red < kBnSmemBudget ? static_cast<int>((kBnSmemBudget - red) / per_iter) & ~3 : 0;   // whole trips of the kernels' loops
   smem = red + stage_iters * per_iter;
   return cudaSuccess;
 }
@@ -1048,7 +1148,8 @@ cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres
   p.dgamma = dgamma; p.dbeta = dbeta; p.sums = sums; p.sync = sync; p.relu = relu; p.acc_dx = acc_dx; p.acc_dres = acc_dres;
   p.scale = scale; p.shift = shift; p.mask_x = (mask_x && relu) ? 1 : 0;
   p.count = static_cast<double>(x.N) * x.H * x.W;
-  bn_bwd_fused_kernel<<<blocks, kBnThreads, smem, st>>>(p);
+  if (dres.ptr) bn_bwd_fused_kernel<true><<<blocks, kBnThreads, smem, st>>>(p);
+  else bn_bwd_fused_kernel<false><<<blocks, kBnThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
