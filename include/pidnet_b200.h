@@ -215,6 +215,7 @@ int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd);
  *          "overlap_wgrad" 1 (default: weight-gradient GEMMs run on a side stream next to the dgrad chain) | 0;
  *          "fused_bn" 1 (default: single-launch BatchNorm kernels with a grid barrier) | 0 (3-kernel form; re-plan);
  *          "wgrad_halo" 1 (default: halo-patch weight-gradient kernel for 3x3 stride-1 convs) | 0 (tap-by-tap; re-plan);
+ *          "wgrad_stack" 1 (default: for Cout <= 64 the halo kernel's stacked-tap form, two filter taps per MMA) | 0 (re-plan);
  *          "bwd_segments" 4 (default) .. 16: number of ranges pidnet_train_backward splits the backward into */
 int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value);
 int pidnet_train_profile(pidnet_trainer* h, void* stream, const float* x_nchw, const int64_t* labels, const float* bd_gt,

@@ -1928,6 +1928,10 @@ int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value) {
       t.wgrad_halo = value != 0;
       t.planned = false;   // needs a re-plan
       t.drop_graphs();
+    } else if (std::string(name) == "wgrad_stack") {
+      t.wgrad_stack = value != 0;
+      t.planned = false;   // needs a re-plan
+      t.drop_graphs();
     } else if (std::string(name) == "fused_bn") {
       t.fused_bn = value != 0;
       t.planned = false;   // needs a re-plan

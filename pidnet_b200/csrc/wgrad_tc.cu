@@ -272,30 +272,192 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
 }
 constexpr size_t kHSmem = static_cast<size_t>(kHStages) * kHStageBytes + 256 + 1024;
 
-// dW[co][ci_off + ci][r][s] += sum over splits of the partial tiles (one thread per gradient element)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(WgradParams p, int T, int splits, int co_tiles, int nz) {
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 stride-1, Cout <= 64 per tile ("stacked taps"): with A = dY the M = 128 rows of the MMA are half empty for these layers
+// (most of PIDNet-S).  Here the roles are swapped: A = X, and TWO filter taps share one MMA -- the M = 128 rows are the 64
+// input channels of tap t0 followed by the 64 input channels of tap t1, which in the MN-major descriptor is just a leading
+// byte offset (LBO) equal to the distance between the two taps' windows inside the halo patch ((dr * 18 + ds) * 128 B);
+// B = dY (N = 64 output channels).  Five accumulators ([tap pair][ci] x co) cover all nine taps, so ONE CTA does what two
+// CTAs of wgrad_halo_kernel do with the same 40 MMAs per tile: half the tensor work and half the dY / patch traffic.
+constexpr int kSStages = 4;
+constexpr int kSABytes = 16384;                     // dY: one 64-co block of [128 px][128 B]
+constexpr int kSStageBytes = kSABytes + kHBBytes;   // 39936
+constexpr int kSPairs = 5;
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_stack_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + kSStages * kSStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kSStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kSStages);
+  const uint32_t tmem_slot = done_bar + 8u;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + kSStages * kSStageBytes + 8 * (2 * kSStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.y * 64, ci0 = blockIdx.z * 64;
+  const int per_img = p.tiles_w * p.tiles_h;
+  const int m_tiles = p.N * per_img;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+
+  int my_tiles = 0;
+  for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) ++my_tiles;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+        const int n = tile / per_img;
+        const int rem = tile - n * per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        const int w0 = tw * 16, h0 = th * 8;
+        const int st = it % kSStages;
+        const uint32_t ph = (it / kSStages) & 1;
+        mbar_wait(empty_bar(st), ph ^ 1);
+        mbar_arrive_expect_tx(full_bar(st), kSABytes + kHPatchBytes);
+        const uint32_t sb = base + st * kSStageBytes;
+        tma_load_4d(sb, &p.tmY, full_bar(st), co0, w0, h0, n);
+        tma_load_4d(sb + kSABytes, &p.tmX[0], full_bar(st), ci0, w0 - 1, h0 - 1, n);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+    // B (dY): one 64-co block, 8-pixel atoms 1024 B apart
+    constexpr uint64_t b_hi = (static_cast<uint64_t>(8192 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                              (1ull << 46) | (2ull << 61);
+    constexpr uint64_t a_hi0 = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);   // + LBO per tap pair
+    for (int it = 0; it < my_tiles; ++it) {
+      const int st = it % kSStages;
+      const uint32_t ph = (it / kSStages) & 1;
+      mbar_wait(full_bar(st), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sb = base + st * kSStageBytes;
+#pragma unroll
+        for (int j = 0; j < kSPairs; ++j) {
+          const int t0 = 2 * j, t1 = min(2 * j + 1, 8);
+          const int r0 = t0 / 3, s0 = t0 - 3 * r0, r1 = t1 / 3, s1 = t1 - 3 * r1;
+          const int delta = ((r1 - r0) * 18 + (s1 - s0)) * 128;          // > 0 for a real pair; the lone tap 8 reads itself twice
+          const uint64_t a_hi = a_hi0 | (static_cast<uint64_t>((delta > 0 ? delta : 128) >> 4) << 16);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {   // k = pixel row of the tile = 16 pixels = one K16 step
+            const uint64_t a_desc = a_hi | static_cast<uint64_t>(((sb + kSABytes + ((k + r0) * 18 + s0) * 128) & 0x3FFFF) >> 4);
+            const uint64_t b_desc = b_hi | static_cast<uint64_t>(((sb + k * 2048) & 0x3FFFF) >> 4);
+            umma_bf16(tmem + j * 64, a_desc, b_desc, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(st));
+        if (it == my_tiles - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+    }
+  } else if (my_tiles > 0) {
+    // epilogue: lane quarter q of TMEM = rows 32q..32q+31 = (tap of the pair, ci); columns = co
+    const int q = warp & 3;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* tile = p.ws + ((static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * gridDim.z + blockIdx.z) *
+                             (static_cast<size_t>(kSPairs) * kWgradTileFloats);
+    const int nco = min(64, p.Cout - co0);
+    for (int j = 0; j < kSPairs; ++j) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (g * 32 >= nco) break;   // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem + j * 64 + g * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(tile + (static_cast<size_t>(j) * 128 + q * 32 + lane) * 64 + g * 32);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                               __uint_as_float(v[4 * e + 3]));
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+constexpr size_t kSSmem = static_cast<size_t>(kSStages) * kSStageBytes + 256 + 1024;
+
+// split-K reduction of wgrad_stack_kernel's partial tiles ([pair][tap-in-pair * 64 + ci][co]): co fastest (coalesced workspace
+// reads), same block structure as wgrad_reduce_kernel below
+__global__ void __launch_bounds__(256) wgrad_stack_reduce_kernel(WgradParams p, int splits, int co_tiles, int ci_tiles) {
+  __shared__ float red[8][32];
+  const long total = static_cast<long>(9) * p.Cin * p.Cout;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long idx = static_cast<long>(blockIdx.x) * 32 + lane;
+  const bool live = idx < total;
+  const long id = live ? idx : total - 1;
+  const int co = static_cast<int>(id % p.Cout);
+  const int ci = static_cast<int>((id / p.Cout) % p.Cin);
+  const int tap = static_cast<int>(id / (static_cast<long>(p.Cout) * p.Cin));
+  const int j = tap >> 1, tp = tap & 1;
+  const size_t tile_floats = static_cast<size_t>(kSPairs) * kWgradTileFloats;
+  const float* src = p.ws + (static_cast<size_t>(co >> 6) * ci_tiles + (ci >> 6)) * tile_floats +
+                     (static_cast<size_t>(j) * 128 + tp * 64 + (ci & 63)) * 64 + (co & 63);
+  const size_t split_stride = static_cast<size_t>(co_tiles) * ci_tiles * tile_floats;
+  float s0 = 0.f, s1 = 0.f;
+  int sp = g;
+  for (; sp + 8 < splits; sp += 16) { s0 += src[sp * split_stride]; s1 += src[(sp + 8) * split_stride]; }
+  if (sp < splits) s0 += src[sp * split_stride];
+  red[g][lane] = s0 + s1;
+  __syncthreads();
+  if (g == 0 && live) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][lane];
+    const int r = tap / 3, q3 = tap - 3 * r;
+    p.dW[(static_cast<size_t>(co) * p.Cin_total + p.ci_off + ci) * 9 + r * 3 + q3] += t;
+  }
+}
+
+// dW[co][ci_off + ci][r][s] += sum over splits of the partial tiles.  A block owns 32 consecutive gradient elements; its eight
+// warps each sum every eighth split (coalesced 128-byte rows of the workspace) and the partial sums meet in shared memory --
+// one thread per element walking all ~148 splits serially was latency-bound at ~12 us per layer, as long as the GEMM itself.
+constexpr int kRedWarps = 8;
+__global__ void __launch_bounds__(32 * kRedWarps) wgrad_reduce_kernel(WgradParams p, int T, int splits, int co_tiles, int nz) {
+  __shared__ float red[kRedWarps][32];
   const long total = static_cast<long>(p.Cout) * p.ntaps * p.Cin;
-  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ci = static_cast<int>(idx % p.Cin);
-  const int tapi = static_cast<int>((idx / p.Cin) % p.ntaps);
-  const int co = static_cast<int>(idx / (static_cast<long>(p.Cin) * p.ntaps));
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long idx = static_cast<long>(blockIdx.x) * 32 + lane;
+  const bool live = idx < total;
+  const long id = live ? idx : total - 1;
+  const int ci = static_cast<int>(id % p.Cin);
+  const int tapi = static_cast<int>((id / p.Cin) % p.ntaps);
+  const int co = static_cast<int>(id / (static_cast<long>(p.Cin) * p.ntaps));
   const int ngroups = (p.ntaps + T - 1) / T;
   const int z = (ci >> 6) * ngroups + tapi / T, j = tapi % T;
   const size_t tile_floats = static_cast<size_t>(T) * kWgradTileFloats;
   const float* src = p.ws + (static_cast<size_t>(co >> 7) * nz + z) * tile_floats +
                      (static_cast<size_t>(co & 127) * T + j) * 64 + (ci & 63);
   const size_t split_stride = static_cast<size_t>(co_tiles) * nz * tile_floats;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int sp = 0;
-  for (; sp + 4 <= splits; sp += 4) {
-    s0 += src[(sp + 0) * split_stride]; s1 += src[(sp + 1) * split_stride];
-    s2 += src[(sp + 2) * split_stride]; s3 += src[(sp + 3) * split_stride];
+  float s0 = 0.f, s1 = 0.f;
+  int sp = g;
+  for (; sp + kRedWarps < splits; sp += 2 * kRedWarps) { s0 += src[sp * split_stride]; s1 += src[(sp + kRedWarps) * split_stride]; }
+  if (sp < splits) s0 += src[sp * split_stride];
+  red[g][lane] = s0 + s1;
+  __syncthreads();
+  if (g == 0 && live) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < kRedWarps; ++q) t += red[q][lane];
+    const uint32_t tp = p.taps[tapi];
+    const int r = (tp >> 24) & 0xF, s = (tp >> 28) & 0xF;
+    p.dW[(static_cast<size_t>(co) * p.Cin_total + p.ci_off + ci) * (p.k * p.k) + r * p.k + s] += t;
   }
-  for (; sp < splits; ++sp) s0 += src[sp * split_stride];
-  const uint32_t tp = p.taps[tapi];
-  const int r = (tp >> 24) & 0xF, s = (tp >> 28) & 0xF;
-  p.dW[(static_cast<size_t>(co) * p.Cin_total + p.ci_off + ci) * (p.k * p.k) + r * p.k + s] += (s0 + s1) + (s2 + s3);
 }
 
 template <int T>
@@ -309,10 +471,22 @@ cudaError_t wgrad_tc_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wg_smem<3>()));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHSmem));
+  e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHSmem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(wgrad_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSSmem));
 }
 
 cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
+  if (L.p.halo == 2) {   // stacked taps: grid (splits, co tiles of 64, ci tiles of 64), all nine taps per CTA
+    if (L.p.ntaps != 9 || L.taps_per_group != 2 * kSPairs) return cudaErrorInvalidValue;
+    wgrad_stack_kernel<<<L.grid, kWgThreads, kSSmem, st>>>(L.p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const long total = static_cast<long>(9) * L.p.Cin * L.p.Cout;
+    wgrad_stack_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 256, 0, st>>>(L.p, static_cast<int>(L.grid.x), static_cast<int>(L.grid.y),
+                                                                                         static_cast<int>(L.grid.z));
+    return cudaGetLastError();
+  }
   if (L.p.halo) {
     if (L.taps_per_group != kHT || L.p.ntaps != 9 || (L.grid.z & 1)) return cudaErrorInvalidValue;
     wgrad_halo_kernel<<<L.grid, kWgThreads, kHSmem, st>>>(L.p);
@@ -322,7 +496,7 @@ cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const long total = static_cast<long>(L.p.Cout) * L.p.ntaps * L.p.Cin;
-  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(L.p, L.taps_per_group, static_cast<int>(L.grid.x),
+  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 32 * kRedWarps, 0, st>>>(L.p, L.taps_per_group, static_cast<int>(L.grid.x),
                                                                                 static_cast<int>(L.grid.y), static_cast<int>(L.grid.z));
   return cudaGetLastError();
 }
