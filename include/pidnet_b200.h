@@ -102,7 +102,10 @@ int pidnet_op_info(pidnet_engine* h, int i, char* name, int name_cap, char* kern
  * "ws_stages" = 3 (default) | 2 staging buffers of the weight-stationary kernels; "use_stem2" = 2
  * (default: conv1.0 -> conv1.3 fused in one kernel, warp-specialised pipeline for 32-channel stems) | 1 (lock-step
  * fused kernel) | 0 (two kernels); "use_pyramid" = 1 (default: the pooled PAPPM / DAPPM branches from one summed-area-table
- * kernel) | 0 (one pooling kernel per branch).  The same switches can be set for a whole
+ * kernel) | 0 (one pooling kernel per branch); "fp32_head" = 0 (default) | 1: the final segmentation head (final_layer: the
+ * logits path, model_utils.py:100-112) in split-bf16 arithmetic -- fp32 weights as hi + lo bf16 pairs, the hidden tensor stored
+ * as hi + lo, three K-concatenated tcgen05 GEMM terms with fp32 accumulation: given its input the head then agrees with fp32
+ * arithmetic to ~1e-5 (north star: "fp32 logits within 1e-3"; the rest of the network stays bf16).  The same switches can be set for a whole
  * process with PIDNET_WS_PAIR / PIDNET_WS_STAGES / PIDNET_STEM2 (A/B measurements). */
 int pidnet_set_option(pidnet_engine* h, const char* name, int value);
 

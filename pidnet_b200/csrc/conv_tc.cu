@@ -164,48 +164,59 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, BK>::kAliasOut ? 2 : 1) conv
   const int row = threadIdx.x;  // tile row == TMEM lane
   const uint32_t t_row = tmem_acc + (static_cast<uint32_t>(warp * 32) << 16);
 
-  if (p.out_mode == kOutNHWCbf16) {
+  if (p.out_mode == kOutNHWCbf16 || p.out_mode == kOutNHWCsplit) {
     const uint32_t swz = (C::kSlabRowBytes == 128) ? (row & 7) : (C::kSlabRowBytes == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+    const int npass = p.out_mode == kOutNHWCsplit ? 2 : 1;   // split storage: pass 0 writes hi = bf16(y), pass 1 lo = bf16(y - hi)
+    for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll
-    for (int g = 0; g < BN / 32; ++g) {
-      uint32_t v[32];
-      tmem_ld32(t_row + g * 32, v);
-      tmem_ld_wait();
+      for (int g = 0; g < BN / 32; ++g) {
+        uint32_t v[32];
+        tmem_ld32(t_row + g * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = g * 32 + j * 8;
-        const int slab = c / C::kSlabC;
-        const int chunk = (c % C::kSlabC) / 8;
-        uint4* ptr = reinterpret_cast<uint4*>(out_gen + slab * C::kSlabBytes + row * C::kSlabRowBytes +
-                                              ((chunk ^ swz) << 4));
-        float f[8];
+        for (int j = 0; j < 4; ++j) {
+          const int c = g * 32 + j * 8;
+          const int slab = c / C::kSlabC;
+          const int chunk = (c % C::kSlabC) / 8;
+          uint4* ptr = reinterpret_cast<uint4*>(out_gen + slab * C::kSlabBytes + row * C::kSlabRowBytes +
+                                                ((chunk ^ swz) << 4));
+          float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + bias_s[c + e];
-        if (p.has_res) {
-          const uint4 r = *ptr;
-          f[0] += bf16lo(r.x); f[1] += bf16hi(r.x); f[2] += bf16lo(r.y); f[3] += bf16hi(r.y);
-          f[4] += bf16lo(r.z); f[5] += bf16hi(r.z); f[6] += bf16lo(r.w); f[7] += bf16hi(r.w);
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + bias_s[c + e];
+          if (p.has_res) {
+            const uint4 r = *ptr;
+            f[0] += bf16lo(r.x); f[1] += bf16hi(r.x); f[2] += bf16lo(r.y); f[3] += bf16hi(r.y);
+            f[4] += bf16lo(r.z); f[5] += bf16hi(r.z); f[6] += bf16lo(r.w); f[7] += bf16hi(r.w);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          if (pass == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] -= __bfloat162float(__float2bfloat16_rn(f[e]));
+          }
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+          o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+          *ptr = o;
         }
-        if (p.relu) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
+      tc_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int sl = 0; sl < C::kNumSlabs; ++sl) {
+          if (c_out0 + sl * C::kSlabC < p.Cout)
+            tma_store_4d(&p.tmD, out_base + sl * C::kSlabBytes, pass * p.Cout + c_out0 + sl * C::kSlabC, w0, h0, n0);
         }
-        uint4 o;
-        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-        o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-        *ptr = o;
+        tma_store_commit();
+        tma_store_wait_all();
       }
-    }
-    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int sl = 0; sl < C::kNumSlabs; ++sl) {
-        if (c_out0 + sl * C::kSlabC < p.Cout)
-          tma_store_4d(&p.tmD, out_base + sl * C::kSlabBytes, c_out0 + sl * C::kSlabC, w0, h0, n0);
+      if (pass + 1 < npass) {   // the staging tile is rewritten by the second pass: wait until the store has read it
+        __syncthreads();
+        tc_fence_after();
       }
-      tma_store_commit();
-      tma_store_wait_all();
     }
   } else {
     // fp32 NCHW planes (logits): thread == pixel; consecutive lanes == consecutive w -> coalesced per plane

@@ -27,7 +27,9 @@ struct ConvSrc {
   uint32_t taps[kConvMaxTaps];  // map index | (dh+8) << 8 | (dw+8) << 16
 };
 
-enum ConvOutMode { kOutNHWCbf16 = 0, kOutNCHWf32 = 1 };
+// kOutNHWCsplit: the fp32 result y is stored as TWO bf16 values, hi = bf16(y) in channels [0, Cout) and lo = bf16(y - hi) in
+// channels [Cout, 2 Cout) of a 2*Cout-channel NHWC tensor (split-bf16 storage, ~16 mantissa bits; the "fp32_head" mode)
+enum ConvOutMode { kOutNHWCbf16 = 0, kOutNCHWf32 = 1, kOutNHWCsplit = 2 };
 
 struct ConvParams {
   CUtensorMap tmA[kConvMaxMaps];  // activation maps

@@ -209,6 +209,7 @@ struct Builder {
   double flops = 0;
   std::map<std::string, T> named;
   const float* dev_bias_override = nullptr;   // training: conv bias read straight from the fp32 parameter
+  bool split_next = false;   // the next conv() stores its result in split-bf16 form ([hi | lo], 2*Cout channels; conv_tc.cuh)
   std::vector<PackJob> pack_jobs;   // training: device-side weight packing, run at the start of every step
 
   void reset(bool dry_) {
@@ -304,6 +305,9 @@ struct Builder {
   T conv(const std::string& name, const std::vector<ConvSrcSpec>& srcs, const std::vector<float>& bias, int Cout,
          bool relu, const T* res, const T* out_view, int out_slot) {
     if (srcs.empty() || srcs.size() > 2) fail(name + ": 1 or 2 sources supported");
+    const bool split = split_next;
+    split_next = false;
+    if (split && (conv_impl != 0 || res || out_view || out_slot >= 0)) fail(name + ": split-bf16 output needs the tcgen05 path, no residual and its own tensor");
     const T& in0 = srcs[0].in;
     const int N = in0.N;
     const bool xt = !srcs[0].xtaps.empty();
@@ -325,8 +329,8 @@ struct Builder {
     }
     T out;
     if (out_slot < 0) {
-      out = out_view ? *out_view : new_tensor(N, Ho, Wo, Cout);
-      if (out.N != N || out.H != Ho || out.W != Wo || out.C != Cout) fail(name + ": output view mismatch");
+      out = out_view ? *out_view : new_tensor(N, Ho, Wo, split ? 2 * Cout : Cout);
+      if (out.N != N || out.H != Ho || out.W != Wo || out.C != (split ? 2 * Cout : Cout)) fail(name + ": output view mismatch");
     } else {
       out.N = N; out.H = Ho; out.W = Wo; out.C = Cout;
     }
@@ -345,7 +349,7 @@ struct Builder {
     bool ws = false;
     int ws_mode = 0, ws_np = 0, ws_chunks = 0, ws_nstage = 2, ws_pair = 0;
     size_t ws_smem = 0;
-    if (conv_impl == 0 && use_ws && !(res && out_slot >= 0)) {
+    if (conv_impl == 0 && use_ws && !split && !(res && out_slot >= 0)) {
       bool all1x1 = true;
       for (const auto& sp : srcs) {
         ws_chunks += cdiv(sp.in.C, BK);
@@ -373,7 +377,7 @@ struct Builder {
     // @64x128) and 0.348 -> 0.238 ms (final_layer.conv1, 1.30 PFLOP/s).  The Cin = 64 layers stream more than they compute
     // and lose ~10-20 % to the pair's lock step (either CTA's memory stall holds both), so they stay single-CTA
     // (use_pair = 2 forces pairs wherever the instance exists; it also admits layers whose weights only fit when halved).
-    if (conv_impl == 0 && use_ws && use_pair && ws_mode == 0 && !(res && out_slot >= 0) && srcs.size() == 1 &&
+    if (conv_impl == 0 && use_ws && !split && use_pair && ws_mode == 0 && !(res && out_slot >= 0) && srcs.size() == 1 &&
         srcs[0].k == 3 && srcs[0].stride == 1 && Cout > 32 && conv3_ws_pair_available(0, 64, BK) &&
         (ws ? BN == 64 : use_pair >= 2) && (ws_chunks >= 2 || use_pair >= 2)) {
       const bool strided_io = xt || (out_view && !out_view->dense()) || (res && !res->dense());
@@ -402,7 +406,7 @@ struct Builder {
     p.N = gN; p.Ho = gH; p.Wo = gW; p.Cout = Cout;
     p.relu = relu ? 1 : 0;
     p.has_res = res ? 1 : 0;
-    p.out_mode = out_slot >= 0 ? kOutNCHWf32 : kOutNHWCbf16;
+    p.out_mode = out_slot >= 0 ? kOutNCHWf32 : (split ? kOutNHWCsplit : kOutNHWCbf16);
 
     // ---- activation maps + tap tables
     int nmaps = 0;
@@ -688,6 +692,7 @@ struct Engine {
   int conv_impl = 0;
   int use_ws = 1;
   int use_pair = -1, ws_stages = -1, use_stem2 = -1, use_pyramid = -1;   // -1: builder default (environment / built-in)
+  int fp32_head = 0;   // final_layer (the logits path) in split-bf16 arithmetic: weights and the hidden tensor as hi + lo pairs
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;  // capture origin (the caller's stream may be the legacy default stream)
   // uint8 input path: per-channel table of the reference's input_transform (datasets/base_dataset.py:36-44), evaluated
@@ -876,8 +881,48 @@ struct Engine {
     b.label(out.prod, "upadd", Builder::tbytes(a) + Builder::tbytes(blow) + Builder::tbytes(out));
     return out;
   }
+  // segmenthead in split-bf16 arithmetic ("fp32_head"): every fp32 weight w is used as w_hi + w_lo (two bf16 values, ~16
+  // mantissa bits) and the hidden tensor h = relu(bn2(conv1(x))) is stored as h_hi + h_lo, so that
+  //   conv1:  y = x * w_hi + x * w_lo                              (x is the bf16 tensor the network produced: exact)
+  //   conv2:  z = h_hi * w_hi + h_lo * w_hi + h_hi * w_lo (+ bias)  (the dropped h_lo * w_lo term is ~2^-16 relative)
+  // are plain K-concatenated tcgen05 GEMMs with fp32 accumulation: given its input, the head matches fp32 arithmetic to ~1e-5
+  // (the bf16 head: ~3e-3).  Costs 2x / 3x the MMAs of the two head convs.
+  void seghead_tail_split(const std::string& p, const T& xin, int slot) {
+    auto lo_of = [](const std::vector<float>& w) {
+      std::vector<float> r(w.size());
+      for (size_t i = 0; i < w.size(); ++i) r[i] = w[i] - bf2f(f2bf(w[i]));
+      return r;
+    };
+    const int Ch = static_cast<int>(P(p + ".conv1.weight").shape[0]);
+    T hl;
+    {
+      Affine a = bn(p + ".bn2");
+      std::vector<float> bias;
+      ConvSrcSpec hi = src_of(xin, p + ".conv1", &a, 3, 1, &bias);
+      ConvSrcSpec lo = hi;
+      lo.w = lo_of(hi.w);
+      b.split_next = true;
+      hl = b.conv(p + ".conv1[hi+lo]", {hi, lo}, bias, Ch, true, nullptr, nullptr, -1);
+    }
+    {
+      std::vector<float> w2, bias2;
+      fold(p + ".conv2", nullptr, w2, bias2);                 // [ncls][Ch]
+      const int ncls = static_cast<int>(P(p + ".conv2.weight").shape[0]);
+      ConvSrcSpec s0, s1;
+      s0.in = hl; s0.k = 1; s0.stride = 1;
+      s0.w.resize(static_cast<size_t>(ncls) * 2 * Ch);
+      for (int co = 0; co < ncls; ++co)
+        for (int ci = 0; ci < Ch; ++ci)
+          s0.w[static_cast<size_t>(co) * 2 * Ch + ci] = s0.w[static_cast<size_t>(co) * 2 * Ch + Ch + ci] = w2[static_cast<size_t>(co) * Ch + ci];
+      s1.in = Builder::slice(hl, 0, Ch); s1.k = 1; s1.stride = 1;
+      s1.w = lo_of(w2);
+      b.conv(p + ".conv2[hi+lo]", {s0, s1}, bias2, ncls, false, nullptr, nullptr, slot);
+    }
+  }
+
   // segmenthead (model_utils.py:100-112): `xin` must already hold relu(bn1(x)); writes fp32 NCHW slot
   void seghead_tail(const std::string& p, const T& xin, int slot) {
+    if (fp32_head && slot == 0 && conv_impl == 0) return seghead_tail_split(p, xin, slot);
     T h = conv_bn(p + ".conv1", xin, p + ".conv1", p + ".bn2", 3, 1, true);
     std::vector<float> bias;
     ConvSrcSpec s = src_of(h, p + ".conv2", nullptr, 1, 1, &bias);
@@ -1554,6 +1599,7 @@ int pidnet_set_option(pidnet_engine* h, const char* name, int value) {
     else if (k == "use_stem2") h->e.use_stem2 = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (k == "use_pyramid") h->e.use_pyramid = value ? 1 : 0;
     else if (k == "ws_stages") h->e.ws_stages = value == 2 ? 2 : 3;
+    else if (k == "fp32_head") h->e.fp32_head = value ? 1 : 0;
     else fail("unknown option '" + k + "'");
     h->e.planned = false;
   });

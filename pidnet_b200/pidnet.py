@@ -176,7 +176,8 @@ class PIDNet(nn.Module):
         'conv_impl': 0 tcgen05 (default) | 1 SIMT cross-check;  'lanes': 3 (default) | 1;  'use_ws': 1 | 0;
         'use_pair': 1 (CTA-pair conv kernel for Cin >= 128, default) | 0 | 2;  'ws_stages': 3 (default) | 2;
         'use_stem2': 2 (fused conv1.0 -> conv1.3 kernel, pipelined form for 32-channel stems; default) | 1 (lock-step) | 0;
-        'use_pyramid': 1 (single-launch pooling pyramid, default) | 0."""
+        'use_pyramid': 1 (single-launch pooling pyramid, default) | 0;
+        'fp32_head': 0 (default) | 1: final_layer in split-bf16 (hi + lo) arithmetic, fp32-accurate given its input."""
         self._options[name] = int(value)
         self._planned = None
 

@@ -193,3 +193,28 @@ def test_engine_options_agree(name, shape, opts):
     for a, b in zip(alt, ref):
         assert a.shape == b.shape
         assert O.rel_l2(a.float().cpu(), b.float().cpu()) < tol, (opts, O.rel_l2(a.float().cpu(), b.float().cpu()))
+
+
+@pytest.mark.parametrize('case', [('s', 19, 2, 256, 512), ('l', 19, 1, 128, 256), ('m', 11, 1, 360, 480)], ids=str)
+def test_fp32_head_matches_fp32_arithmetic(case):
+    """north star: "fp32 logits within 1e-3".  With 'fp32_head' the final segmentation head (the logits path, final_layer,
+    model_utils.py:100-112) runs in split-bf16 arithmetic (weights and the hidden tensor as hi + lo bf16 pairs, fp32
+    accumulation): recomputed in fp32 from the ENGINE's own input to the head, the logits must agree to 1e-3 (measured ~1e-5),
+    where the plain bf16 head sits at 2-5e-3.  The layers in front of the head stay bf16."""
+    dev = _dev()
+    name, ncls, N, H, W = case
+    x = torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(6))
+    errs = {}
+    for mode in (0, 1):
+        model, sd = build(name, ncls, True, seed=13, dev=dev, fp32_head=mode)
+        with torch.no_grad():
+            got = model(x.to(dev))
+        torch.cuda.synchronize()
+        dfm = model.debug_tensor('dfm')                       # relu(final_layer.bn1(dfm(...))) as the engine stored it (bf16)
+        with torch.no_grad():
+            loc = O.run_stage(sd, 'out', [dfm], x.shape[-2:])
+        errs[mode] = (O.rel_l2(got[1].cpu(), loc), float((got[1].cpu() - loc).abs().max() / loc.abs().max()))
+    print(f'[fp32 head {name} {H}x{W}] logits vs fp32 head on the same input: bf16 head rel-L2 {errs[0][0]:.3g} (max {errs[0][1]:.3g}), '
+          f'split-bf16 head rel-L2 {errs[1][0]:.3g} (max {errs[1][1]:.3g})')
+    assert errs[1][0] < 1e-3 and errs[1][1] < 1e-3, errs
+    assert errs[1][0] < 0.1 * errs[0][0], errs
