@@ -156,6 +156,10 @@ int pidnet_op_bag(void* stream, const void* p, const void* i_low, const void* d,
  *                   [13] = number of labels >= 0, [14..15] reserved.  An empty OHEM set (the reference raises IndexError,
  *                   utils/criterion.py:73) gives a NaN loss and contributes no gradient.
  *   grad_*        : optional device fp32 buffers shaped like the logits; receive d(loss.mean())/d(logits)
+ *   aux_ce_map    : optional device fp32 [N,H,W]: the per-pixel term of the reference's loss -- nn.CrossEntropyLoss(reduction=
+ *                   'none') of x_extra_p (weighted, 0 at ignored pixels; utils/criterion.py:50-60,94).  The reference's
+ *                   FullModel returns loss as a [1,N,H,W] MAP (that term times BALANCE_WEIGHTS[0] plus the scalar terms);
+ *                   callers that need the map shape rebuild it from this (pidnet_b200.FullModel(loss_map=True))
  * No host synchronisation; `workspace` needs pidnet_criterion_workspace_bytes(N,H,W) device bytes. */
 typedef struct pidnet_criterion_cfg {
   int64_t ignore_label;        /* TRAIN.IGNORE_LABEL (255) */
@@ -171,7 +175,7 @@ size_t pidnet_criterion_workspace_bytes(int N, int H, int W);
 int pidnet_criterion(void* stream, const float* x_p, const float* x_m, const float* x_d, int N, int C, int h, int w,
                      const int64_t* labels, const float* bd_gt, int H, int W, const float* class_weights,
                      const pidnet_criterion_cfg* cfg, void* workspace, size_t workspace_bytes, float* out16,
-                     float* grad_p, float* grad_m, float* grad_d);
+                     float* grad_p, float* grad_m, float* grad_d, float* aux_ce_map);
 /* F.interpolate(x, size=(H,W), mode='bilinear', align_corners=True) on fp32 NCHW (utils/utils.py:44-46) */
 int pidnet_upsample_align_corners(void* stream, const float* x, int NC, int h, int w, float* out, int H, int W);
 
@@ -194,7 +198,7 @@ int pidnet_train_plan(pidnet_trainer* h, int N, int H, int W, size_t* arena_byte
  *               (this is how `loss.backward()` of the reference loop, utils/function.py:47, triggers it). */
 int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x_nchw, const int64_t* labels, const float* bd_gt,
                       const float* class_weights, const pidnet_criterion_cfg* cfg, int backward, float* out16,
-                      float* out_main, float* out_p, float* out_d);
+                      float* out_main, float* out_p, float* out_d, float* aux_ce_map /* optional, as in pidnet_criterion */);
 /* Backward of the last train-mode forward of this handle (pidnet_train_forward, or pidnet_train_step with backward 0 / 2):
  * what autograd runs for `outputs = self.model(inputs)` (utils/utils.py:39) when a loss built on the three outputs calls
  * .backward().  g_main / g_p / g_d: device fp32 gradients w.r.t. x_ / x_extra_p / x_extra_d shaped like the logits, or all

@@ -50,13 +50,13 @@ SIGNATURES = {
     'pidnet_op_lightbag': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     'pidnet_criterion_workspace_bytes': (C.c_size_t, [_i, _i, _i]),
     'pidnet_criterion': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, C.POINTER(CriterionCfg), _vp,
-                              C.c_size_t, _vp, _vp, _vp, _vp]),
+                              C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
     'pidnet_upsample_align_corners': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i]),
     'pidnet_train_create': (_i, [C.POINTER(Cfg), C.POINTER(_vp)]),
     'pidnet_train_destroy': (_i, [_vp]),
     'pidnet_train_bind': (_i, [_vp, C.c_char_p, _vp, _vp, _i64p, _i]),
     'pidnet_train_plan': (_i, [_vp, _i, _i, _i, C.POINTER(C.c_size_t)]),
-    'pidnet_train_step': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(CriterionCfg), _i, _vp, _vp, _vp, _vp]),
+    'pidnet_train_step': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(CriterionCfg), _i, _vp, _vp, _vp, _vp, _vp]),
     'pidnet_train_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
     'pidnet_train_num_segments': (_i, [_vp]),
     'pidnet_train_segment_ranges': (_i, [_vp, _i, _vp, _i64p, _i, C.POINTER(_i)]),

@@ -6,9 +6,11 @@ Differences to the reference's surface, both deliberate:
   * the values the reference reads from the global yacs config (LOSS.BALANCE_WEIGHTS, LOSS.SB_WEIGHTS,
     MODEL.ALIGN_CORNERS, TRAIN.IGNORE_LABEL) are constructor arguments whose defaults are the values of
     the shipped YAMLs (SURVEY.md Appendix D);
-  * `FullModel.forward` returns `loss` / `loss_s` as 1-element tensors whose `.mean()` equals the
+  * by default `FullModel.forward` returns `loss` / `loss_s` as 1-element tensors whose `.mean()` equals the
     reference's `losses.mean()` / `loss_list[0].mean()` -- the only way every reference caller consumes
-    them (utils/function.py:44,56-59,118) -- rather than `[1,N,H,W]` / `[N,H,W]` maps.
+    them (utils/function.py:44,56-59,118).  `FullModel(..., loss_map=True)` returns the reference's exact shapes
+    instead: `loss` `[1,N,H,W]` and `loss_s` `[N,H,W]` (the per-pixel maps that `reduction='none'` broadcasting
+    produces, utils/criterion.py:50-60,94), rebuilt from the kernel's per-pixel aux-head CE.
 Gradients w.r.t. the three logit maps are produced by the same kernel family (`FusedCriterion.backward`).
 """
 from __future__ import annotations
@@ -59,7 +61,7 @@ class FusedCriterion:
         self.sem_loss = sem_loss
         self._ws = None
 
-    def __call__(self, outputs, labels, bd_gt, need_grads=False):
+    def __call__(self, outputs, labels, bd_gt, need_grads=False, aux_ce_map=None):
         lib = _lib.load()
         x_p, x_m, x_d = [o.contiguous().float() for o in outputs]
         if not x_m.is_cuda:
@@ -80,7 +82,7 @@ class FusedCriterion:
         with torch.cuda.device(x_m.device):
             _lib.check(lib.pidnet_criterion(C.c_void_p(stream), p(x_p), p(x_m), p(x_d), N, Cc, h, w, p(labels), p(bd_gt),
                                             H, W, p(wt), C.byref(self.cfg), p(self._ws), self._ws.numel(), p(out),
-                                            p(grads[0]), p(grads[1]), p(grads[2])))
+                                            p(grads[0]), p(grads[1]), p(grads[2]), p(aux_ce_map)))
         return out, grads
 
 
@@ -101,23 +103,37 @@ class FullModel(nn.Module):
     """reference utils/utils.py:21-57: wraps model + losses; forward(inputs, labels, bd_gt) ->
     (loss, [up(x_extra_p), up(x_)], acc, [loss_s, loss_b])."""
 
-    def __init__(self, model, sem_loss, bd_loss, balance_weights=(0.4, 1.0), sb_weights=1.0, return_outputs=True):
+    def __init__(self, model, sem_loss, bd_loss, balance_weights=(0.4, 1.0), sb_weights=1.0, return_outputs=True, loss_map=False):
         super().__init__()
         self.model = model
         self.sem_loss = sem_loss
         self.bd_loss = bd_loss
         self.return_outputs = return_outputs
+        self.loss_map = loss_map
+        self._bw0 = float(balance_weights[0])
         self._crit = FusedCriterion(sem_loss, bd_loss, balance_weights, sb_weights)
+
+    def _as_maps(self, loss, loss_s, aux_ce):
+        """The reference's shapes: loss_s = bw0 * CE_none(x_extra_p) + bw1 * ohem  [N,H,W]; loss = (loss_s + loss_b + loss_sb)
+        .unsqueeze(0)  [1,N,H,W].  The per-pixel part enters detached and mean-free, so `.mean()` is exactly the scalar the
+        kernel produced and the gradient flows through that scalar."""
+        pix = self._bw0 * aux_ce
+        dev = (pix - pix.mean()).detach()
+        return (loss.reshape(()) + dev).unsqueeze(0), loss_s.reshape(()) + dev
 
     def forward(self, inputs, labels, bd_gt, *args, **kwargs):
         if self.training and torch.is_grad_enabled():
             return self._train_forward(inputs, labels, bd_gt)
         outputs = self.model(inputs, *args, **kwargs)
-        out, _ = self._crit(outputs, labels, bd_gt)
+        aux = torch.empty(labels.shape, dtype=torch.float32, device=labels.device) if self.loss_map else None
+        out, _ = self._crit(outputs, labels, bd_gt, aux_ce_map=aux)
         h, w = labels.size(1), labels.size(2)
         ups = []
         if self.return_outputs:
             ups = [o if (o.size(2) == h and o.size(3) == w) else upsample_align_corners(o, (h, w)) for o in outputs[:-1]]
+        if self.loss_map:
+            loss, loss_s = self._as_maps(out[0:1], out[1], aux)
+            return loss, ups, out[3], [loss_s, out[2]]
         return out[0:1], ups, out[3], [out[1], out[2]]
 
     def _train_forward(self, inputs, labels, bd_gt):
@@ -130,10 +146,14 @@ class FullModel(nn.Module):
         trainer = self.model.engine_trainer()
         params = [p for _, p in self.model.named_parameters()]
         wt = self.sem_loss.criterion.weight
-        res = _TrainStepFn.apply(trainer, inputs, labels, bd_gt, wt, self._crit.cfg, *params)
+        aux = torch.empty(labels.shape, dtype=torch.float32, device=labels.device) if self.loss_map else None
+        res = _TrainStepFn.apply(trainer, inputs, labels, bd_gt, wt, self._crit.cfg, aux, *params)
         loss, out12, x_p, x_m, x_d = res
         h, w = labels.size(1), labels.size(2)
         ups = [upsample_align_corners(o, (h, w)) for o in (x_p, x_m)] if self.return_outputs else []
+        if self.loss_map:
+            loss, loss_s = self._as_maps(loss, out12[1], aux)
+            return loss, ups, out12[3], [loss_s, out12[2]]
         return loss, ups, out12[3], [out12[1], out12[2]]
 
     @property

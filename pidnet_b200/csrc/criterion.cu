@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(256) crit_pixel_kernel(CritParams p) {
 #pragma unroll
       for (int k = 0; k < CMAX; ++k) if (k < p.C) sp += expf(vm[k] - mp);
       acc[A_CE_P] = wt * (mp + logf(sp) - vtp);
+      if (p.aux_ce) p.aux_ce[pix] = acc[A_CE_P];
     }
     // boundary head
     const float xd = interp(p.x_d + static_cast<size_t>(c.n) * plane, c, p.w);
@@ -761,7 +762,9 @@ __global__ void __launch_bounds__(256, 3) crit_pixel_run_kernel(CritParams p) {
       const float ta = fmaf(wy1, qt[r1 + lane], wy0 * qt[r0 + lane]), tb = fmaf(wy1, qt[r1 + i1], wy0 * qt[r0 + i1]);
       const float vtp = fmaf(l, tb - ta, ta);
       const float wt = p.class_w ? __ldg(p.class_w + tg) : 1.f;
-      acc[A_CE_P] += wt * (fmaf(mp, kLog2e, lg2f(sp)) * kLn2 - vtp);
+      const float cep = wt * (fmaf(mp, kLog2e, lg2f(sp)) * kLn2 - vtp);
+      acc[A_CE_P] += cep;
+      if (p.aux_ce) p.aux_ce[(static_cast<long>(t.n) * p.H + y) * p.W + xs + j] = cep;   // (rare path: the map is pre-zeroed)
     }
   }
   __syncthreads();
@@ -1218,6 +1221,7 @@ cudaError_t criterion_launch(CritParams p, void* workspace, bool backward, cudaS
   unsigned* hist = reinterpret_cast<unsigned*>(ws + off);
   cudaError_t e;
   if ((e = cudaMemsetAsync(p.accum, 0, A_COUNT * sizeof(double) + 512 + 2 * 4096 * sizeof(unsigned) + 256, st)) != cudaSuccess) return e;
+  if (p.aux_ce && (e = cudaMemsetAsync(p.aux_ce, 0, npix * sizeof(float), st)) != cudaSuccess) return e;
   const unsigned blocks = static_cast<unsigned>((npix + 255) / 256);
   const bool run_path = column_runs_fit(p);
   if (run_path) { if ((e = launch_run(p, nullptr, false, st)) != cudaSuccess) return e; }

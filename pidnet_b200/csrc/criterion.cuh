@@ -20,6 +20,7 @@ struct CritParams {
   double bw0, bw1, sb, coeff_bce;
   float* out;             // device float[12]
   float *g_p, *g_m, *g_d; // low-res gradients of loss.mean() (backward only)
+  float* aux_ce;          // optional [N,H,W]: per-pixel weighted CE of the aux head (0 at ignored pixels) -- the reference's loss MAP
   int direct_scatter;     // backward: 1 = global atomics (footprint does not fit the smem tile)
   // workspace (filled by criterion_launch)
   float* ws_p;

@@ -1849,11 +1849,12 @@ int pidnet_train_plan(pidnet_trainer* h, int N, int H, int W, size_t* arena_byte
 }
 int pidnet_train_step(pidnet_trainer* h, void* stream, const float* x, const int64_t* labels, const float* bd_gt,
                       const float* class_weights, const pidnet_criterion_cfg* cfg, int backward, float* out12,
-                      float* out_main, float* out_p, float* out_d) {
+                      float* out_main, float* out_p, float* out_d, float* aux_ce_map) {
   return guard([&] {
     if (!h || !x || !labels || !bd_gt || !cfg) fail("null argument");
     TrainNet& t = reinterpret_cast<pidnet_trainer_*>(h)->t;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    t.aux_ce_map = aux_ce_map;
     if (backward < 0 || backward > 2) fail("pidnet_train_step: backward must be 0, 1 or 2");
     t.step(st, x, labels, bd_gt, class_weights, *cfg, backward);
     const size_t lp = static_cast<size_t>(t.N) * t.h8 * t.w8;
@@ -2035,7 +2036,7 @@ size_t pidnet_criterion_workspace_bytes(int N, int H, int W) { return criterion_
 int pidnet_criterion(void* stream, const float* x_p, const float* x_m, const float* x_d, int N, int C, int h, int w,
                      const int64_t* labels, const float* bd_gt, int H, int W, const float* class_weights,
                      const pidnet_criterion_cfg* cfg, void* workspace, size_t workspace_bytes, float* out12,
-                     float* grad_p, float* grad_m, float* grad_d) {
+                     float* grad_p, float* grad_m, float* grad_d, float* aux_ce_map) {
   return guard([&] {
     if (!x_p || !x_m || !x_d || !labels || !bd_gt || !cfg || !workspace || !out12) fail("null argument");
     if (workspace_bytes < criterion_workspace_bytes(N, H, W)) fail("criterion workspace too small");
@@ -2051,7 +2052,7 @@ int pidnet_criterion(void* stream, const float* x_p, const float* x_m, const flo
     p.min_kept = cfg->ohem_keep < 1 ? 1 : cfg->ohem_keep;
     p.bw0 = cfg->balance_weight_aux; p.bw1 = cfg->balance_weight_main; p.sb = cfg->sb_weight;
     p.coeff_bce = cfg->coeff_bce;
-    p.out = out12; p.g_p = grad_p; p.g_m = grad_m; p.g_d = grad_d;
+    p.out = out12; p.g_p = grad_p; p.g_m = grad_m; p.g_d = grad_d; p.aux_ce = aux_ce_map;
     CK(criterion_launch(p, workspace, bwd, reinterpret_cast<cudaStream_t>(stream)));
   });
 }

@@ -150,7 +150,7 @@ class EngineTrainer:
             self._seg_ranges = None
 
     # ----------------------------------------------------------------------- forward
-    def step(self, x, labels, bd_gt, class_weights, crit_cfg, backward=True, want_logits=True):
+    def step(self, x, labels, bd_gt, class_weights, crit_cfg, backward=True, want_logits=True, aux_ce_map=None):
         """Train-mode forward + criterion.  backward: True / 1 = also the whole network backward into self.flat_grad (no
         all-reduce); 2 = criterion values and logit gradients only (`backward()` runs the network backward later);
         False / 0 = values only.  Returns (out16, [x_extra_p, x_, x_extra_d])."""
@@ -171,7 +171,7 @@ class EngineTrainer:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             cw = class_weights.to(self.device, torch.float32).contiguous() if class_weights is not None else None
             _lib.check(self.lib.pidnet_train_step(self.h, C.c_void_p(stream), p(x), p(labels), p(bd_gt), p(cw), C.byref(crit_cfg),
-                                                  int(backward), p(self.out16), p(outs[1]), p(outs[0]), p(outs[2])))
+                                                  int(backward), p(self.out16), p(outs[1]), p(outs[0]), p(outs[2]), p(aux_ce_map)))
             self._record_out(True)
         self._after_forward()
         return self.out16, outs
@@ -300,8 +300,8 @@ class _TrainStepFn(torch.autograd.Function):
     """FullModel's train-mode forward: network + fused criterion now, network backward inside `loss.backward()`."""
 
     @staticmethod
-    def forward(ctx, trainer, x, labels, bd_gt, class_weights, crit_cfg, *params):
-        out16, outs = trainer.step(x, labels, bd_gt, class_weights, crit_cfg, backward=2)
+    def forward(ctx, trainer, x, labels, bd_gt, class_weights, crit_cfg, aux_ce_map, *params):
+        out16, outs = trainer.step(x, labels, bd_gt, class_weights, crit_cfg, backward=2, aux_ce_map=aux_ce_map)
         ctx.trainer, ctx.x, ctx.seq, ctx.done, ctx.nparam = trainer, x, trainer.seq, False, len(params)
         ctx.mark_non_differentiable(*[o for o in outs])
         return (out16[0:1].clone(), out16.clone(), *outs)
@@ -312,8 +312,8 @@ class _TrainStepFn(torch.autograd.Function):
         grads = ctx.trainer.backward_and_publish(ctx.x, g_loss.reshape(()))
         ctx.x = None
         if grads is None:
-            return (None,) * (6 + ctx.nparam)
-        return (None, None, None, None, None, None, *grads)
+            return (None,) * (7 + ctx.nparam)
+        return (None, None, None, None, None, None, None, *grads)
 
 
 class _TrainForwardFn(torch.autograd.Function):

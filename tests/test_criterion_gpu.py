@@ -103,3 +103,11 @@ def test_upsample_and_fullmodel_surface():
     assert close(loss.mean().item(), r[0].mean().item()) and close(ll[0].mean().item(), r[3][0].mean().item())
     assert close(ll[1].mean().item(), r[3][1].item()) and abs(acc.mean().item() - r[2].item()) < 1e-6
     assert len(ups) == 2 and all((a.cpu() - b).abs().max() < 1e-4 for a, b in zip(ups, r[1]))
+    # loss_map=True: the reference's exact return shapes -- loss [1,N,H,W], loss_list[0] [N,H,W] (per-pixel maps that the
+    # reduction='none' aux term broadcasts into, utils/criterion.py:50-60,94 / utils/utils.py:55-57)
+    fm2 = FullModel(Dummy([o.to(dev) for o in outs]), OhemCrossEntropy(255, 0.9, 131072, weight), BondaryLoss(), loss_map=True).eval()
+    loss2, _, acc2, ll2 = fm2(torch.zeros(1, device=dev), labels.to(dev), bd.to(dev))
+    assert tuple(loss2.shape) == tuple(r[0].shape) == (1, 2, 64, 128) and tuple(ll2[0].shape) == tuple(r[3][0].shape) == (2, 64, 128)
+    assert (loss2.cpu() - r[0]).abs().max() < 2e-4 * r[0].abs().max()
+    assert (ll2[0].cpu() - r[3][0]).abs().max() < 2e-4 * r[3][0].abs().max()
+    assert close(loss2.mean().item(), r[0].mean().item())

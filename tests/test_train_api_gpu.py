@@ -114,6 +114,26 @@ def test_zero_grad_in_place_between_forward_and_backward():
     assert float(g2.norm()) > 1.5 * float(g3.norm())
 
 
+def test_loss_map_surface_in_train_mode():
+    """FullModel(loss_map=True): the reference's return shapes ([1,N,H,W] loss, [N,H,W] loss_s); `.mean().backward()` delivers the
+    same gradients as the 1-element form."""
+    dev = _dev()
+    x, labels, bd = _batch(2, 128, 128, 90, dev)
+    weight = torch.tensor(CO.CITYSCAPES_CLASS_WEIGHTS)
+    grads, losses = [], []
+    for lm in (False, True):
+        model = _model(11, dev)
+        full = FullModel(model, OhemCrossEntropy(255, 0.9, 3000, weight), BondaryLoss(), return_outputs=False, loss_map=lm).to(dev).train()
+        loss, _, acc, ll = full(x, labels, bd)
+        if lm:
+            assert tuple(loss.shape) == (1, 2, 128, 128) and tuple(ll[0].shape) == (2, 128, 128)
+        loss.mean().backward()
+        grads.append(_flat(model)); losses.append(float(loss.mean()))
+    torch.cuda.synchronize()
+    assert abs(losses[0] - losses[1]) < 1e-4 * abs(losses[0])
+    assert _rel(grads[1], grads[0]) < 0.05
+
+
 def test_stale_or_repeated_backward_raises():
     dev = _dev()
     model = _model(5, dev)
