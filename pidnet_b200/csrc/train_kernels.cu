@@ -4,6 +4,7 @@
 // of the bilinear-upsample / average-pool operators.  Reference semantics: nn.BatchNorm2d(momentum=0.1,
 // eps=1e-5) in train mode (models/model_utils.py:8-9), SURVEY.md Appendix H.
 #include <cstdio>
+#include <cstdlib>
 #include "train_kernels.cuh"
 
 namespace pidnet {
@@ -1101,6 +1102,24 @@ cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, cons
 // ---- fused single-launch BatchNorm
 // shared memory per block (2 blocks per SM): small enough to co-reside with a wgrad CTA of the side stream
 static constexpr size_t kBnSmemBudget = 24 * 1024;
+// The fused BatchNorm kernels contain a grid barrier: they are launched COOPERATIVELY (cudaLaunchAttributeCooperative), so the
+// runtime guarantees that all 2 x num_sms blocks are co-resident (or rejects the launch) instead of the kernel assuming it.
+// PIDNET_BN_COOP=0 falls back to a plain launch (A/B measurements).
+template <class P>
+static cudaError_t launch_bn(void (*kernel)(P), unsigned blocks, size_t smem, cudaStream_t st, const P& p) {
+  static const bool coop = [] { const char* v = std::getenv("PIDNET_BN_COOP"); return !(v && v[0] == '0'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks, 1, 1);
+  cfg.blockDim = dim3(kBnThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = coop ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
 static cudaError_t bn_fused_geometry(const View& x, int num_sms, int vec_per_iter, unsigned& blocks, long& ppb, int& stage_iters,
                                      size_t& smem) {
   const int groups = x.C / 8;
@@ -1131,8 +1150,7 @@ cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma
   p.run_mean = run_mean; p.run_var = run_var; p.sums = sums; p.sync = sync; p.relu = relu;
   p.scale = scale; p.shift = shift;
   p.count = static_cast<double>(x.N) * x.H * x.W;
-  bn_fwd_fused_kernel<<<blocks, kBnThreads, smem, st>>>(p);
-  return cudaGetLastError();
+  return launch_bn(bn_fwd_fused_kernel, blocks, smem, st, p);
 }
 
 cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
@@ -1148,9 +1166,7 @@ cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres
   p.dgamma = dgamma; p.dbeta = dbeta; p.sums = sums; p.sync = sync; p.relu = relu; p.acc_dx = acc_dx; p.acc_dres = acc_dres;
   p.scale = scale; p.shift = shift; p.mask_x = (mask_x && relu) ? 1 : 0;
   p.count = static_cast<double>(x.N) * x.H * x.W;
-  if (dres.ptr) bn_bwd_fused_kernel<true><<<blocks, kBnThreads, smem, st>>>(p);
-  else bn_bwd_fused_kernel<false><<<blocks, kBnThreads, smem, st>>>(p);
-  return cudaGetLastError();
+  return dres.ptr ? launch_bn(bn_bwd_fused_kernel<true>, blocks, smem, st, p) : launch_bn(bn_bwd_fused_kernel<false>, blocks, smem, st, p);
 }
 
 cudaError_t pack_weights_launch(const PackJob& j, cudaStream_t st) {
