@@ -707,7 +707,7 @@ def run_train(a, dev, world, rank, peaks):
                     else 'single rank: no exchange',
         'conv_tflops': tfl, 'frac_of_tc_sustained': tfl / peaks['tc_sustained'], 'frac_of_tc_burst': tfl / peaks['tc_burst'],
         'algorithmic_gflop_per_step_per_gpu': flops / 1e9, 'launches': {'forward': f.value, 'backward': b.value},
-        'gpu_launches': (f.value + b.value + 12) * steps, 'loss': float(loss), 'scaling': 'weak',
+        'gpu_launches': (f.value + b.value + 12) * steps, 'loss': float(loss.detach()), 'scaling': 'weak',
         'dtype': 'bf16 activations / gradients, fp32 master weights and weight gradients', 'data': 'synthetic',
         'api': 'pidnet_b200.FullModel -> losses.mean().backward() -> FusedSGD.step() (the reference loop, utils/function.py:43-49)',
         'config': {'workload': f'PIDNet-S train fwd + OHEM/boundary loss + bwd + SGD, {B}x3x{H}x{W} per GPU, OHEM 0.9/131072, '
@@ -716,7 +716,70 @@ def run_train(a, dev, world, rank, peaks):
     }
     del full, tr, opt, model
     torch.cuda.empty_cache()
+    if world == 1 and rank == 0 and not a.skip_ref_gpu:
+        try:
+            rec['ref_gpu_eager'] = run_ref_gpu_train(dev, x, labels, bd, weight, ms_api)
+        except Exception as exc:   # noqa: BLE001
+            rec['ref_gpu_eager'] = {'unavailable': f'{type(exc).__name__}: {str(exc)[:160]}'}
+        torch.cuda.empty_cache()
     return rec
+
+
+def run_ref_gpu_train(dev, x, labels, bd, weight, ours_ms):
+    """The same training step through torch autograd / cuDNN on this GPU: the reference's PIDNet module (baseline/_ref, train mode,
+    augment=True) when vendored, else the oracle's restatement of it; the loss is the oracle's restatement of FullModel /
+    OhemCrossEntropy / BondaryLoss (the reference's utils import a yacs config that is absent here) -- it materialises the
+    full-resolution logits exactly as the reference does; torch.optim.SGD.  fp32 (TF32 off, as shipped) and bf16 autocast."""
+    from oracle import criterion_oracle as CO
+    from oracle import pidnet_oracle as O
+    ref = load_reference_models()
+    out = {'runs': [], 'criterion': 'oracle/criterion_oracle.py (restatement of utils/utils.py:37-57 + utils/criterion.py)',
+           'model': 'baseline/_ref models/pidnet.py PIDNet(augment=True).train()' if ref is not None else 'oracle/pidnet_oracle.py (port)'}
+    wd = weight.to(dev)
+    for label, tf32, autocast in (('fp32, TF32 off (as shipped)', False, False), ('fp32, TF32 on', True, False), ('bf16 autocast', True, True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.manual_seed(0)
+        if ref is not None:
+            net = ref.PIDNet(m=2, n=3, num_classes=19, planes=32, ppm_planes=96, head_planes=128, augment=True).to(dev).train()
+            params = list(net.parameters())
+            fwd = lambda inp: net(inp)
+        else:
+            cfg = O.config_for('pidnet_s', 19, True)
+            sd = {k: v.to(dev) for k, v in O.make_state_dict(cfg, 0, randomize_bn=False).items()}
+            params = [v for k, v in sd.items() if v.dtype.is_floating_point and 'running_' not in k]
+            for p_ in params:
+                p_.requires_grad_(True)
+            fwd = lambda inp: O.pidnet_forward(sd, inp, training=True)
+        opt = torch.optim.SGD(params, lr=0.01, momentum=0.9, weight_decay=5e-4)
+
+        def step():
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+                outs = fwd(x)
+            losses, _, _, _ = CO.full_model_forward([o.float() for o in outs], labels, bd, wd, dict(ohem_keep=131072))
+            loss = losses.mean()
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        try:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            out['runs'].append({'variant': label, 'ms_per_step': ms, 'img_per_s': x.shape[0] * 1e3 / ms, 'speedup_of_ours': ms / ours_ms})
+        except Exception as exc:   # noqa: BLE001
+            out['runs'].append({'variant': label, 'error': f'{type(exc).__name__}: {str(exc)[:120]}'})
+        del opt, params
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return out
 
 
 def main():
