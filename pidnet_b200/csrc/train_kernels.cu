@@ -3,6 +3,7 @@
 // K-major layouts of the conv kernels, forward and dgrad orientation), layout converters and the transposes
 // of the bilinear-upsample / average-pool operators.  Reference semantics: nn.BatchNorm2d(momentum=0.1,
 // eps=1e-5) in train mode (models/model_utils.py:8-9), SURVEY.md Appendix H.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include "train_kernels.cuh"
@@ -1126,7 +1127,12 @@ static cudaError_t bn_fused_geometry(const View& x, int num_sms, int vec_per_ite
   if (groups < 1 || groups > kBnThreads || x.C % 8) return cudaErrorInvalidValue;
   const int lanes = kBnThreads / groups;
   const long npix = static_cast<long>(x.N) * x.H * x.W;
-  blocks = static_cast<unsigned>(2 * num_sms);
+  // full machine (2 blocks per SM) for the large tensors; small maps get fewer blocks -- every thread still has >= ~8 vectors and
+  // the grid barrier collects fewer arrivals (its latency is most of a small launch)
+  const long vectors = npix * groups;
+  long want = (vectors + static_cast<long>(kBnThreads) * 8 - 1) / (static_cast<long>(kBnThreads) * 8);
+  want = std::max<long>(std::min<long>(want, 2L * num_sms), std::max(1, num_sms / 4));
+  blocks = static_cast<unsigned>(want);
   const long unit = static_cast<long>(lanes) * 4;
   ppb = (npix + blocks - 1) / blocks;
   ppb = (ppb + unit - 1) / unit * unit;
