@@ -564,6 +564,114 @@ __global__ void __launch_bounds__(256) pag_fuse_flat_kernel(View x, View low, Vi
   if (valid) st8(out.ptr + pix * out.ps + cg * 8, o);
 }
 
+// ---- wide form: 16 channels per thread, mixed-precision FMAs
+// fma.rn.f32.bf16 (sm_100: FHFMA.BF16) multiplies two bf16 values and accumulates in fp32, reading either half of a 32-bit
+// register directly: the loaded vectors are never unpacked.  The bilinear weights must then be bf16 values -- exact when the
+// low-res field is upsampled by 2, 4 or 8 (the weights and their pairwise products are dyadic rationals of at most 8 significant
+// bits), which is every PagFM of the network at power-of-two input sizes; other geometries keep the fp32-weight kernel above.
+// Products bf16 x bf16 are exact in fp32, so the result differs from the unpacked form only by summation order.
+// The flat form was instruction-issue bound (74 % issue-active at 35 % of HBM): ~270 instructions per 8 channels, a quarter of
+// them unpacking, another fifth the per-thread index decode that 16 channels per thread now amortise twice as far.
+__device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b_lo, float c) {   // a.lo * b.lo + c
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.bf16 %0, al, bl, %3;\n\t}"
+      : "=f"(d) : "r"(a), "r"(b_lo), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fhfma_hi(uint32_t a, uint32_t b_lo, float c) {   // a.hi * b.lo + c
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.bf16 %0, ah, bl, %3;\n\t}"
+      : "=f"(d) : "r"(a), "r"(b_lo), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fhfma_ll(uint32_t a, uint32_t b, float c) { return fhfma_lo(a, b, c); }
+__device__ __forceinline__ float fhfma_hh(uint32_t a, uint32_t b, float c) {      // a.hi * b.hi + c
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.bf16 %0, ah, bh, %3;\n\t}"
+      : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf16_bits(float w) {   // bf16(w) in the low half (w is exactly representable)
+  return __float_as_uint(w) >> 16;
+}
+// acc[e] += w * v[e] for the 8 bf16 of v (w: bf16 bits in the low half)
+__device__ __forceinline__ void axpy8(float (&acc)[8], const uint4& v, uint32_t w) {
+  acc[0] = fhfma_lo(v.x, w, acc[0]); acc[1] = fhfma_hi(v.x, w, acc[1]);
+  acc[2] = fhfma_lo(v.y, w, acc[2]); acc[3] = fhfma_hi(v.y, w, acc[3]);
+  acc[4] = fhfma_lo(v.z, w, acc[4]); acc[5] = fhfma_hi(v.z, w, acc[5]);
+  acc[6] = fhfma_lo(v.w, w, acc[6]); acc[7] = fhfma_hi(v.w, w, acc[7]);
+}
+// d += sum_e a[e] * b[e] over the 8 bf16 pairs (two partial sums to shorten the dependency chain)
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float d) {
+  float d0 = fhfma_ll(a.x, b.x, d), d1 = fhfma_hh(a.x, b.x, 0.f);
+  d0 = fhfma_ll(a.y, b.y, d0); d1 = fhfma_hh(a.y, b.y, d1);
+  d0 = fhfma_ll(a.z, b.z, d0); d1 = fhfma_hh(a.z, b.z, d1);
+  d0 = fhfma_ll(a.w, b.w, d0); d1 = fhfma_hh(a.w, b.w, d1);
+  return d0 + d1;
+}
+__device__ __forceinline__ uint32_t blend_pack(uint32_t xw, float y0, float y1, float g, int relu) {
+  const float x0 = __uint_as_float(xw << 16), x1 = __uint_as_float(xw & 0xFFFF0000u);
+  const float o0 = fmaf(g, y0 - x0, x0), o1 = fmaf(g, y1 - x1, x1);
+  uint32_t r;
+  if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(o1), "f"(o0));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(o1), "f"(o0));
+  return r;
+}
+template <int LP>  // lanes per pixel = C/16
+__global__ void __launch_bounds__(256) pag_fuse_wide_kernel(View x, View low, View out, int relu, Dec dec) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned npix = static_cast<unsigned>(x.N) * x.H * x.W;
+  const bool valid = gid / LP < npix;
+  int cg, w, h, n;
+  unsigned pixu;
+  decode_idx(valid ? gid : (npix - 1) * LP + gid % LP, dec, LP, x.W, x.H, cg, w, h, n, pixu);
+  const int C = x.C, c0 = cg * 16;
+  const Lerp lh = lerp_of(h, low.H, dec.sh), lw = lerp_of(w, low.W, dec.sw);
+  const float w00 = (1.f - lh.l) * (1.f - lw.l), w01 = (1.f - lh.l) * lw.l, w10 = lh.l * (1.f - lw.l), w11 = lh.l * lw.l;
+  const uint32_t b00 = bf16_bits(w00), b01 = bf16_bits(w01), b10 = bf16_bits(w10), b11 = bf16_bits(w11);
+  const int ps = static_cast<int>(low.ps);
+  const bf16* lb = low.ptr + static_cast<long>(n) * (low.H * low.W * ps);
+  const int o00 = (lh.i0 * low.W + lw.i0) * ps, o01 = (lh.i0 * low.W + lw.i1) * ps;
+  const int o10 = (lh.i1 * low.W + lw.i0) * ps, o11 = (lh.i1 * low.W + lw.i1) * ps;
+  const bf16* xp = x.ptr + static_cast<long>(pixu) * x.ps + c0;
+  uint4 xv[2];
+  float y[2][8];
+  float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const int c = c0 + v * 8;
+    xv[v] = __ldg(reinterpret_cast<const uint4*>(xp + v * 8));
+    const uint4 y00 = __ldg(reinterpret_cast<const uint4*>(lb + o00 + c)), y01 = __ldg(reinterpret_cast<const uint4*>(lb + o01 + c));
+    const uint4 y10 = __ldg(reinterpret_cast<const uint4*>(lb + o10 + c)), y11 = __ldg(reinterpret_cast<const uint4*>(lb + o11 + c));
+    const uint4 z00 = __ldg(reinterpret_cast<const uint4*>(lb + o00 + C + c)), z01 = __ldg(reinterpret_cast<const uint4*>(lb + o01 + C + c));
+    const uint4 z10 = __ldg(reinterpret_cast<const uint4*>(lb + o10 + C + c)), z11 = __ldg(reinterpret_cast<const uint4*>(lb + o11 + C + c));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[v][e] = 0.f;
+    axpy8(y[v], y00, b00); axpy8(y[v], y01, b01); axpy8(y[v], y10, b10); axpy8(y[v], y11, b11);
+    d00 = dot8(xv[v], z00, d00); d01 = dot8(xv[v], z01, d01); d10 = dot8(xv[v], z10, d10); d11 = dot8(xv[v], z11, d11);
+  }
+  float dot = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  // scalar term t (channel 2C of `low`)
+  const bf16* tb = lb + 2 * C;
+  const float tt = w00 * __bfloat162float(tb[o00]) + w01 * __bfloat162float(tb[o01]) + w10 * __bfloat162float(tb[o10]) +
+                   w11 * __bfloat162float(tb[o11]);
+  const float g = sigmoidf_(dot + tt);
+  if (valid) {
+    bf16* op = out.ptr + static_cast<long>(pixu) * out.ps + c0;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      uint4 o;
+      o.x = blend_pack(xv[v].x, y[v][0], y[v][1], g, relu); o.y = blend_pack(xv[v].y, y[v][2], y[v][3], g, relu);
+      o.z = blend_pack(xv[v].z, y[v][4], y[v][5], g, relu); o.w = blend_pack(xv[v].w, y[v][6], y[v][7], g, relu);
+      *reinterpret_cast<uint4*>(op + v * 8) = o;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) lightbag_uv_flat_kernel(View p, View il, View d, View out, Dec dec) {
   pdl_wait();
   pdl_launch_dependents();
@@ -675,10 +783,26 @@ cudaError_t stem_conv_launch(const float* x, int N, int H, int W, View out, cons
   return cudaGetLastError();
 }
 
+// up-sampling factor 2, 4 or 8 in both directions: every bilinear weight (and product of two) is a bf16 value
+static bool pow2_upsample(int in, int out) { return out == 2 * in || out == 4 * in || out == 8 * in; }
 cudaError_t pag_fuse_launch(View x, View low, View out, int relu, cudaStream_t st) {
-  const int LP = x.C / 8;
-  if (static_cast<long>(x.N) * x.H * x.W * LP + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic
+  if (static_cast<long>(x.N) * x.H * x.W * (x.C / 8) + 256 >= (1L << 32)) return cudaErrorInvalidValue;   // 32-bit index arithmetic
   if (static_cast<long>(low.H) * low.W * low.ps >= (1L << 31)) return cudaErrorInvalidValue;   // 32-bit offsets inside an image
+  static const bool wide_ok = [] { const char* v = std::getenv("PIDNET_PAG_WIDE"); return !(v && v[0] == '0'); }();
+  if (wide_ok && x.C % 16 == 0 && pow2_upsample(low.H, x.H) && pow2_upsample(low.W, x.W)) {
+    const int LP = x.C / 16;
+    const Dec dec = make_dec(LP, x.W, x.H, low.H, x.H, low.W, x.W);
+    const dim3 grid(blocks_for(static_cast<long>(x.N) * x.H * x.W * LP, 256), 1, 1), block(256, 1, 1);
+    switch (LP) {
+      case 1: return launch_pdl(pag_fuse_wide_kernel<1>, grid, block, 0, st, x, low, out, relu, dec);
+      case 2: return launch_pdl(pag_fuse_wide_kernel<2>, grid, block, 0, st, x, low, out, relu, dec);
+      case 4: return launch_pdl(pag_fuse_wide_kernel<4>, grid, block, 0, st, x, low, out, relu, dec);
+      case 8: return launch_pdl(pag_fuse_wide_kernel<8>, grid, block, 0, st, x, low, out, relu, dec);
+      case 16: return launch_pdl(pag_fuse_wide_kernel<16>, grid, block, 0, st, x, low, out, relu, dec);
+      default: break;   // other widths: the flat kernel below
+    }
+  }
+  const int LP = x.C / 8;
   const Dec dec = make_dec(LP, x.W, x.H, low.H, x.H, low.W, x.W);
   const dim3 grid(blocks_for(static_cast<long>(x.N) * x.H * x.W * LP, 256), 1, 1), block(256, 1, 1);
   switch (LP) {

@@ -24,8 +24,11 @@ cudaError_t bn_backward_launch(View x, View dz, View z, View dx, View dres, cons
                                int acc_dres, float* dgamma, float* dbeta, int num_sms, cudaStream_t st);
 
 // Fused single-launch forms (persistent grid + grid barrier, loaded vectors parked in shared memory between the
-// statistics pass and the apply pass).  `sync`: device unsigned[2], zero on entry (self-clearing like `sums`).
+// statistics pass and the apply pass).  Each launch gets its own accumulator block of bn_fused_acc_bytes(C) bytes (`sums` at its
+// start, `sync` at bn_fused_sync_offset(C)); the kernels never clear it -- the caller zeroes all blocks of a pass with one memset.
 bool bn_fused_supported(int C);
+size_t bn_fused_acc_bytes(int C);
+size_t bn_fused_sync_offset(int C);
 // `scale` / `shift` ([C] each): the folded affine the forward applied, kept for the backward; mask_x = 1 (ReLU without a residual):
 // the backward recomputes the ReLU mask from x with that affine instead of reading the stored output z.
 cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma, const float* beta, const float* conv_bias,

@@ -9,6 +9,7 @@
 // second kernel sums the split-K partials into the torch-layout gradient (scattered fp32 atomics from every CTA
 // were the bottleneck of the first version: up to 7 M atomics per layer).  Stride-2 convs use the same parity
 // tensor maps as the forward kernel; zero padding / ragged tiles are TMA out-of-bounds fills.
+#include <cstdlib>
 #include "train_kernels.cuh"
 #include "ptx.cuh"
 
@@ -115,6 +116,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const int co = co0 + q * 32 + lane;
     mbar_wait(done_bar, 0);
     tc_fence_after();
+    // the split-K reduction may be scheduled from here on (it waits for this grid's completion itself): its launch latency
+    // hides behind the accumulator read-out.  Not earlier -- waiting reduction blocks would hold the thread slots the
+    // BatchNorm kernels of the main stream need.
+    pdl_launch_dependents();
     // partial tile of this CTA: [row = co within the tile][tap j][64 ci]
     float* tile = p.ws + ((static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * gridDim.z + blockIdx.z) *
                              (static_cast<size_t>(T) * kWgradTileFloats);
@@ -245,6 +250,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
     const int co = co0 + q * 32 + lane;
     mbar_wait(done_bar, 0);
     tc_fence_after();
+    // the split-K reduction may be scheduled from here on (it waits for this grid's completion itself): its launch latency
+    // hides behind the accumulator read-out.  Not earlier -- waiting reduction blocks would hold the thread slots the
+    // BatchNorm kernels of the main stream need.
+    pdl_launch_dependents();
     float* tile = p.ws + ((static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * gridDim.z + blockIdx.z) *
                              (static_cast<size_t>(kHT) * kWgradTileFloats);
     const int nci = min(64, p.Cin - ci0);
@@ -367,6 +376,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_stack_kernel(const __grid
     const int q = warp & 3;
     mbar_wait(done_bar, 0);
     tc_fence_after();
+    // the split-K reduction may be scheduled from here on (it waits for this grid's completion itself): its launch latency
+    // hides behind the accumulator read-out.  Not earlier -- waiting reduction blocks would hold the thread slots the
+    // BatchNorm kernels of the main stream need.
+    pdl_launch_dependents();
     float* tile = p.ws + ((static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * gridDim.z + blockIdx.z) *
                              (static_cast<size_t>(kSPairs) * kWgradTileFloats);
     const int nco = min(64, p.Cout - co0);
@@ -392,10 +405,36 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_stack_kernel(const __grid
 }
 constexpr size_t kSSmem = static_cast<size_t>(kSStages) * kSStageBytes + 256 + 1024;
 
+// One warp's share of a split-K sum: splits g, g + NW, g + 2 NW, ... with EIGHT loads in flight (the ~19 loads of a warp are
+// L2 round trips; two at a time made the reduction as long as the GEMM it follows)
+template <int NW>
+__device__ __forceinline__ float sum_splits(const float* src, size_t split_stride, int g, int splits, int wide = 1) {
+  float acc = 0.f;
+  if (!wide) {
+    float s0 = 0.f, s1 = 0.f;
+    int sp = g;
+    for (; sp + NW < splits; sp += 2 * NW) { s0 += src[sp * split_stride]; s1 += src[(sp + NW) * split_stride]; }
+    if (sp < splits) s0 += src[sp * split_stride];
+    return s0 + s1;
+  }
+  for (int base = g; base < splits; base += 8 * NW) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int sp = base + u * NW;
+      v[u] = sp < splits ? __ldcg(src + static_cast<size_t>(sp) * split_stride) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
+  return acc;
+}
+
 // split-K reduction of wgrad_stack_kernel's partial tiles ([pair][tap-in-pair * 64 + ci][co]): co fastest (coalesced workspace
 // reads), same block structure as wgrad_reduce_kernel below
-__global__ void __launch_bounds__(256) wgrad_stack_reduce_kernel(WgradParams p, int splits, int co_tiles, int ci_tiles) {
+__global__ void __launch_bounds__(256) wgrad_stack_reduce_kernel(WgradParams p, int splits, int co_tiles, int ci_tiles, int wide) {
   __shared__ float red[8][32];
+  pdl_wait();   // launched while the GEMM drains (programmatic dependent launch); its partial tiles are complete after this
   const long total = static_cast<long>(9) * p.Cin * p.Cout;
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const long idx = static_cast<long>(blockIdx.x) * 32 + lane;
@@ -409,11 +448,7 @@ __global__ void __launch_bounds__(256) wgrad_stack_reduce_kernel(WgradParams p, 
   const float* src = p.ws + (static_cast<size_t>(co >> 6) * ci_tiles + (ci >> 6)) * tile_floats +
                      (static_cast<size_t>(j) * 128 + tp * 64 + (ci & 63)) * 64 + (co & 63);
   const size_t split_stride = static_cast<size_t>(co_tiles) * ci_tiles * tile_floats;
-  float s0 = 0.f, s1 = 0.f;
-  int sp = g;
-  for (; sp + 8 < splits; sp += 16) { s0 += src[sp * split_stride]; s1 += src[(sp + 8) * split_stride]; }
-  if (sp < splits) s0 += src[sp * split_stride];
-  red[g][lane] = s0 + s1;
+  red[g][lane] = sum_splits<8>(src, split_stride, g, splits, wide);
   __syncthreads();
   if (g == 0 && live) {
     float t = 0.f;
@@ -428,8 +463,9 @@ __global__ void __launch_bounds__(256) wgrad_stack_reduce_kernel(WgradParams p, 
 // warps each sum every eighth split (coalesced 128-byte rows of the workspace) and the partial sums meet in shared memory --
 // one thread per element walking all ~148 splits serially was latency-bound at ~12 us per layer, as long as the GEMM itself.
 constexpr int kRedWarps = 8;
-__global__ void __launch_bounds__(32 * kRedWarps) wgrad_reduce_kernel(WgradParams p, int T, int splits, int co_tiles, int nz) {
+__global__ void __launch_bounds__(32 * kRedWarps) wgrad_reduce_kernel(WgradParams p, int T, int splits, int co_tiles, int nz, int wide) {
   __shared__ float red[kRedWarps][32];
+  pdl_wait();
   const long total = static_cast<long>(p.Cout) * p.ntaps * p.Cin;
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const long idx = static_cast<long>(blockIdx.x) * 32 + lane;
@@ -444,11 +480,7 @@ __global__ void __launch_bounds__(32 * kRedWarps) wgrad_reduce_kernel(WgradParam
   const float* src = p.ws + (static_cast<size_t>(co >> 7) * nz + z) * tile_floats +
                      (static_cast<size_t>(co & 127) * T + j) * 64 + (ci & 63);
   const size_t split_stride = static_cast<size_t>(co_tiles) * nz * tile_floats;
-  float s0 = 0.f, s1 = 0.f;
-  int sp = g;
-  for (; sp + kRedWarps < splits; sp += 2 * kRedWarps) { s0 += src[sp * split_stride]; s1 += src[(sp + kRedWarps) * split_stride]; }
-  if (sp < splits) s0 += src[sp * split_stride];
-  red[g][lane] = s0 + s1;
+  red[g][lane] = sum_splits<kRedWarps>(src, split_stride, g, splits, wide);
   __syncthreads();
   if (g == 0 && live) {
     float t = 0.f;
@@ -477,15 +509,21 @@ cudaError_t wgrad_tc_init() {
 }
 
 cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
+  static const int red_wide = [] { const char* v = std::getenv("PIDNET_WG_WIDE"); return v && v[0] == '0' ? 0 : 1; }();
+  static const bool red_pdl = [] { const char* v = std::getenv("PIDNET_WG_PDL"); return !(v && v[0] == '0'); }();
   if (L.p.halo == 2) {   // stacked taps: grid (splits, co tiles of 64, ci tiles of 64), all nine taps per CTA
     if (L.p.ntaps != 9 || L.taps_per_group != 2 * kSPairs) return cudaErrorInvalidValue;
     wgrad_stack_kernel<<<L.grid, kWgThreads, kSSmem, st>>>(L.p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const long total = static_cast<long>(9) * L.p.Cin * L.p.Cout;
-    wgrad_stack_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 256, 0, st>>>(L.p, static_cast<int>(L.grid.x), static_cast<int>(L.grid.y),
-                                                                                         static_cast<int>(L.grid.z));
-    return cudaGetLastError();
+    if (!red_pdl) {
+      wgrad_stack_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 256, 0, st>>>(L.p, static_cast<int>(L.grid.x), static_cast<int>(L.grid.y),
+                                                                                           static_cast<int>(L.grid.z), red_wide);
+      return cudaGetLastError();
+    }
+    return launch_pdl(wgrad_stack_reduce_kernel, dim3(static_cast<unsigned>((total + 31) / 32)), dim3(256), 0, st, L.p,
+                      static_cast<int>(L.grid.x), static_cast<int>(L.grid.y), static_cast<int>(L.grid.z), red_wide);
   }
   if (L.p.halo) {
     if (L.taps_per_group != kHT || L.p.ntaps != 9 || (L.grid.z & 1)) return cudaErrorInvalidValue;
@@ -496,9 +534,13 @@ cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const long total = static_cast<long>(L.p.Cout) * L.p.ntaps * L.p.Cin;
-  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 32 * kRedWarps, 0, st>>>(L.p, L.taps_per_group, static_cast<int>(L.grid.x),
-                                                                                static_cast<int>(L.grid.y), static_cast<int>(L.grid.z));
-  return cudaGetLastError();
+  if (!red_pdl) {
+    wgrad_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 32 * kRedWarps, 0, st>>>(L.p, L.taps_per_group, static_cast<int>(L.grid.x),
+                                                                                  static_cast<int>(L.grid.y), static_cast<int>(L.grid.z), red_wide);
+    return cudaGetLastError();
+  }
+  return launch_pdl(wgrad_reduce_kernel, dim3(static_cast<unsigned>((total + 31) / 32)), dim3(32 * kRedWarps), 0, st, L.p,
+                    L.taps_per_group, static_cast<int>(L.grid.x), static_cast<int>(L.grid.y), static_cast<int>(L.grid.z), red_wide);
 }
 
 }  // namespace pidnet

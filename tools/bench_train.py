@@ -29,6 +29,8 @@ def main():
     tr = EngineTrainer(model)
     if os.environ.get('GRAPH', '1') == '0':
         tr.set_option('use_graph', 0)
+    if os.environ.get('OVERLAP', '1') == '0':
+        tr.set_option('overlap_wgrad', 0)
     weight = torch.tensor(CW)
     crit = FusedCriterion(OhemCrossEntropy(255, 0.9, 131072, weight), BondaryLoss())
     g = torch.Generator().manual_seed(100 + rank)
