@@ -221,6 +221,9 @@ int pidnet_train_num_launches(pidnet_trainer* h, int* fwd, int* bwd);
 /* options: "use_graph" 1 (default: the step replays two CUDA graphs after one eager step) | 0 (eager launches);
  *          "overlap_wgrad" 1 (default: weight-gradient GEMMs run on a side stream next to the dgrad chain) | 0;
  *          "fused_bn" 1 (default: single-launch BatchNorm kernels with a grid barrier) | 0 (3-kernel form; re-plan);
+ *          "conv_stats" bit mask (default 7): the forward batch statistics of a conv -> BatchNorm pair are accumulated by the conv
+ *                       kernel itself (bit 0: 3x3 weight-stationary kernel, bit 1: 1x1 weight-stationary kernel, bit 2: stem kernel) and
+ *                       the BatchNorm launch only applies them | 0 (every BatchNorm makes its own statistics pass); re-plan;
  *          "wgrad_halo" 1 (default: halo-patch weight-gradient kernel for 3x3 stride-1 convs) | 0 (tap-by-tap; re-plan);
  *          "wgrad_stack" 1 (default: for Cout <= 64 the halo kernel's stacked-tap form, two filter taps per MMA) | 0 (re-plan);
  *          "bwd_segments" 4 (default) .. 16: number of ranges pidnet_train_backward splits the backward into */

@@ -274,6 +274,108 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv3_ws_kernel(const __grid_co
       }
     }
     __syncwarp();
+  } else if (warp == 11 && p.stats != nullptr) {
+    // ============================== TMA store warp + BatchNorm statistics (training forward) ==============================
+    // Same protocol as the plain store warp below (lane 0 issues the stores and owns the bulk-async groups), but while the TMA
+    // engine reads the staged tile out, the WHOLE warp reads it too and accumulates, per output channel, sum x and sum x^2 of
+    // the bf16 values exactly as they are stored: lane l owns the 32-bit word l of a 128-byte row (two channels; 64-byte rows:
+    // two rows per trip), which is bank-conflict free under any swizzle.  Rows outside the image (ragged tiles, the extra tile
+    // of a last pair) are clipped by the TMA store and skipped here.  One fp64 atomic per channel and CTA at the end: the
+    // BatchNorm that follows needs no statistics pass and no grid barrier.
+    if (p.out_mode == kOutNHWCbf16) {
+      // 16-byte loads: lane = (row within a group of kRowsPerLd rows, logical 8-channel chunk j); the physical chunk is
+      // j ^ swizzle(row), so a quarter-warp always reads 128 contiguous bytes (no bank conflicts) and a lane always sees the
+      // same eight channels.  (32-bit loads, one row per instruction, cost ~28 cycles each next to the saturated MMA operand
+      // fetch of the C = 64 layers: +19 us on a 24 us conv; this form issues a quarter of the requests.)
+      constexpr int kChunks = kSlabRowBytes / 16;        // 8 (128-byte rows) or 4 (64-byte rows)
+      constexpr int kRowsPerLd = 32 / kChunks;           // 4 or 8 rows per warp-wide load
+      constexpr int kBatch = kNumSlabs == 1 ? 8 : 4;     // loads in flight per slab
+      const int j = lane % kChunks, rq = lane / kChunks;
+      float s1[kNumSlabs][8], s2[kNumSlabs][8];
+#pragma unroll
+      for (int sl = 0; sl < kNumSlabs; ++sl)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s1[sl][e] = s2[sl][e] = 0.f;
+      const long total_rows = static_cast<long>(p.N) * p.Ho * p.Wo;
+      for (int i = 0; in_range(i); ++i) {
+        int w0, h0, n;
+        tile_coord(tile_of(i), w0, h0, n);
+        const int sb = stage_of(i);
+        mbar_wait(stage_ready(sb), static_cast<uint32_t>(i / nstage) & 1);
+        if (lane == 0) {
+          for (int sl = 0; sl < kNumSlabs; ++sl)
+            if (c_out0 + sl * kSlabC < p.Cout)
+              tma_store_4d(&p.tmD, stage_base + sb * kStageBytes + sl * kSlabBytes, c_out0 + sl * kSlabC, w0, h0, n);
+          tma_store_commit();
+        }
+        __syncwarp();
+        if (tile_of(i) < static_cast<long>(m_tiles)) {
+          // valid rows of the tile: MODE 0 rows are (h0 + r / 8, w0 + r % 8); MODE 1 rows are consecutive pixels
+          int vrows = 128, vcols = kTW;
+          if (MODE == 0) {
+            vrows = min(kTH, p.Ho - h0) * kTW;
+            vcols = min(kTW, p.Wo - w0);
+          } else {
+            vrows = static_cast<int>(min(128L, total_rows - static_cast<long>(w0)));
+          }
+          const uint8_t* stage = stage_gen + sb * kStageBytes;
+          constexpr uint32_t kOnes = 0x3F803F80u;   // bf16 (1.0, 1.0)
+          for (int r0 = 0; r0 < vrows; r0 += kBatch * kRowsPerLd) {
+            uint4 v[kBatch][kNumSlabs];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+              const int r = r0 + u * kRowsPerLd + rq;   // <= 127: inside the staging buffer whatever vrows is
+              const uint32_t swz_r = (kSlabRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
+              const uint32_t off = static_cast<uint32_t>(r) * kSlabRowBytes + ((static_cast<uint32_t>(j) ^ swz_r) << 4);
+#pragma unroll
+              for (int sl = 0; sl < kNumSlabs; ++sl) v[u][sl] = *reinterpret_cast<const uint4*>(stage + sl * kSlabBytes + off);
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+              const int r = r0 + u * kRowsPerLd + rq;
+              const bool ok = r < vrows && (MODE != 0 || (r & (kTW - 1)) < vcols);
+#pragma unroll
+              for (int sl = 0; sl < kNumSlabs; ++sl) {
+                const uint32_t x[4] = {ok ? v[u][sl].x : 0u, ok ? v[u][sl].y : 0u, ok ? v[u][sl].z : 0u, ok ? v[u][sl].w : 0u};
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) {
+                  s1[sl][2 * q2] = fma_bf16_ll(x[q2], kOnes, s1[sl][2 * q2]);
+                  s2[sl][2 * q2] = fma_bf16_ll(x[q2], x[q2], s2[sl][2 * q2]);
+                  s1[sl][2 * q2 + 1] = fma_bf16_hh(x[q2], kOnes, s1[sl][2 * q2 + 1]);
+                  s2[sl][2 * q2 + 1] = fma_bf16_hh(x[q2], x[q2], s2[sl][2 * q2 + 1]);
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();   // every lane is done with the buffer before lane 0 hands it on
+        if (lane == 0) {
+          tma_store_wait_read();
+          mbar_arrive(stage_free(sb, (i + nstage) & 1));
+        }
+      }
+      if (lane == 0) tma_store_wait_all();
+      __syncwarp();
+      double* tab = p.stats + static_cast<size_t>(blockIdx.x % kBnStatReplicas) * 2 * p.stats_C;
+#pragma unroll
+      for (int sl = 0; sl < kNumSlabs; ++sl) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float a = s1[sl][e], b2 = s2[sl][e];
+#pragma unroll
+          for (int o = kChunks; o < 32; o <<= 1) {   // the lanes that share chunk j hold different rows of the same channels
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+          }
+          const int c = c_out0 + sl * kSlabC + j * 8 + e;
+          if (rq == 0 && c < p.Cout) {
+            atomicAdd(tab + c, static_cast<double>(a));
+            atomicAdd(tab + p.stats_C + c, static_cast<double>(b2));
+          }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 11) {
     // ============================== TMA store warp ==============================
     if (p.out_mode == kOutNHWCbf16 && elect_one()) {

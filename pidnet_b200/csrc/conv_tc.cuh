@@ -70,7 +70,13 @@ struct Conv3Params {
   int relu, has_res, out_mode;
   const float* bias;
   float* out_f32;
+  // training: per-channel batch statistics of the stored (bf16-rounded) output, accumulated by the store warp from the staged
+  // tiles -- sum x into stats[r][c], sum x^2 into stats[r][stats_C + c] for replica r = blockIdx.x % kBnStatReplicas of a
+  // [kBnStatReplicas][2 * stats_C] fp64 table (the accumulator block of the BatchNorm that follows, train_kernels.cu); or null
+  double* stats;
+  int stats_C;
 };
+constexpr int kBnStatReplicas = 8;
 
 struct Conv3Launch {
   Conv3Params p;

@@ -210,6 +210,11 @@ struct Builder {
   std::map<std::string, T> named;
   const float* dev_bias_override = nullptr;   // training: conv bias read straight from the fp32 parameter
   bool split_next = false;   // the next conv() stores its result in split-bf16 form ([hi | lo], 2*Cout channels; conv_tc.cuh)
+  // training: the next conv() feeds a BatchNorm whose fp64 accumulator table is `stats_next` ([kBnStatReplicas][2 * Cout]); if the
+  // conv lands on a kernel that can accumulate the batch statistics in its epilogue (conv3_ws.cu) it does, and stats_taken says so
+  double* stats_next = nullptr;
+  bool stats_taken = false;
+  int stats_kinds = 3;   // bit 0: 3x3 halo-patch kernel, bit 1: 1x1 flat-tile kernel
   std::vector<PackJob> pack_jobs;   // training: device-side weight packing, run at the start of every step
 
   void reset(bool dry_) {
@@ -307,6 +312,9 @@ struct Builder {
     if (srcs.empty() || srcs.size() > 2) fail(name + ": 1 or 2 sources supported");
     const bool split = split_next;
     split_next = false;
+    double* const stats = stats_next;
+    stats_next = nullptr;
+    stats_taken = false;
     if (split && (conv_impl != 0 || res || out_view || out_slot >= 0)) fail(name + ": split-bf16 output needs the tcgen05 path, no residual and its own tensor");
     const T& in0 = srcs[0].in;
     const int N = in0.N;
@@ -576,6 +584,10 @@ struct Builder {
       q.N = N; q.Cout = Cout; q.Ho = Ho; q.Wo = Wo;
       q.relu = p.relu; q.has_res = p.has_res; q.out_mode = p.out_mode;
       q.bias = bdev;
+      if (stats && !res && out_slot < 0 && !relu && conv_impl == 0 && ((stats_kinds >> ws_mode) & 1)) {   // raw conv output -> BatchNorm: statistics in the store warp
+        q.stats = stats; q.stats_C = Cout;
+        stats_taken = true;
+      }
       const long rows = static_cast<long>(N) * Ho * Wo;
       long mt;
       if (ws_mode == 0) {
@@ -1981,6 +1993,10 @@ int pidnet_train_set_option(pidnet_trainer* h, const char* name, int value) {
       t.drop_graphs();
     } else if (std::string(name) == "fused_bn") {
       t.fused_bn = value != 0;
+      t.planned = false;   // needs a re-plan
+      t.drop_graphs();
+    } else if (std::string(name) == "conv_stats") {
+      t.conv_stats = value;
       t.planned = false;   // needs a re-plan
       t.drop_graphs();
     } else if (std::string(name) == "overlap_wgrad") {

@@ -37,6 +37,7 @@ struct StemParams {
   int H, W, Ho, Wo;
   long rows, tiles;     // N*Ho*Wo, ceil(rows / 128)
   int relu;             // 1: inference (bias + ReLU); 0: training (raw conv output, BatchNorm follows)
+  double* stats;        // training: [kBnStatReplicas][2 * Cout] fp64 table receiving sum x / sum x^2 of the stored output (or null)
 };
 cudaError_t stem_tc_launch(const StemParams& p, int Cout, int num_sms, cudaStream_t st);
 // ---- fused stem (stem2_tc.cu): conv1.0+BN+ReLU -> conv1.3+BN+ReLU, the C-channel half-resolution intermediate stays in smem

@@ -291,4 +291,19 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Mixed-precision FMA on packed bf16 halves: c + a.lo * b.lo / c + a.hi * b.hi in fp32, ONE instruction, no unpacking
+// (products of two bf16 are exact in fp32).
+__device__ __forceinline__ float fma_bf16_ll(uint32_t a, uint32_t b, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.bf16 %0, al, bl, %3;\n\t}"
+      : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fma_bf16_hh(uint32_t a, uint32_t b, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.bf16 %0, ah, bh, %3;\n\t}"
+      : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+
 }  // namespace pidnet

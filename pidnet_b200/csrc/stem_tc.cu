@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ St
   const int a_swz = (row >> 1) & 3;
   const uint32_t o_swz = (kRowB == 128) ? (row & 7) : ((row >> 1) & 3);
   uint32_t phase = 0;
+  // batch statistics of the stored tile (training): warp w reads rows 32w..32w+31 of the staged tile, lane = 32-bit word of a row
+  constexpr int kWords = kRowB / 4, kRowsPerTrip = 32 / kWords;
+  const int lane = threadIdx.x & 31, wl = lane % kWords, rsub = lane / kWords;
+  float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
 
   for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     // ---- A producer: im2col row of output pixel `pix`
@@ -151,9 +155,51 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ St
     if (threadIdx.x == 0) {
       tma_store_4d(&p.tmD, o_addr, 0, static_cast<int>(tile * 128), 0, 0);
       tma_store_commit();
-      tma_store_wait_read();   // o_s (and, by program order, a_s) may be overwritten by the next tile
+    }
+    if (p.stats) {   // while the TMA engine reads the tile out (rows past the end of the tensor are clipped by the store, skipped here)
+      const int vrows = static_cast<int>(min(128L, p.rows - tile * 128));
+      constexpr uint32_t kOnes = 0x3F803F80u;   // bf16 (1.0, 1.0)
+      for (int t0 = 0; t0 < 32; t0 += 8 * kRowsPerTrip) {   // eight loads in flight per trip
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = warp * 32 + t0 + u * kRowsPerTrip + rsub;
+          const uint32_t swz_r = (kRowB == 128) ? (r & 7) : ((r >> 1) & 3);
+          v[u] = *reinterpret_cast<const uint32_t*>(o_s + r * kRowB + (((static_cast<uint32_t>(wl) >> 2) ^ swz_r) << 4) + (wl & 3) * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = warp * 32 + t0 + u * kRowsPerTrip + rsub;
+          const uint32_t x = r < vrows ? v[u] : 0u;
+          st1[0] = fma_bf16_ll(x, kOnes, st1[0]); st2[0] = fma_bf16_ll(x, x, st2[0]);
+          st1[1] = fma_bf16_hh(x, kOnes, st1[1]); st2[1] = fma_bf16_hh(x, x, st2[1]);
+        }
+      }
+    }
+    if (threadIdx.x == 0) tma_store_wait_read();   // o_s (and, by program order, a_s) may be overwritten by the next tile
+    __syncthreads();
+  }
+  if (p.stats) {   // combine the four warps in shared memory (the staging tile is free), then one fp64 atomic per channel and CTA
+    float* red = reinterpret_cast<float*>(o_s);   // [4 warps][2 (sum, sum sq)][BN]
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float a = st1[e], b2 = st2[e];
+      if (kRowsPerTrip == 2) {
+        a += __shfl_down_sync(0xffffffffu, a, 16);
+        b2 += __shfl_down_sync(0xffffffffu, b2, 16);
+      }
+      if (rsub == 0) {
+        red[(warp * 2 + 0) * BN + 2 * wl + e] = a;
+        red[(warp * 2 + 1) * BN + 2 * wl + e] = b2;
+      }
     }
     __syncthreads();
+    if (threadIdx.x < 2 * BN) {
+      const int which = threadIdx.x / BN, c = threadIdx.x % BN;
+      const float t = red[(0 * 2 + which) * BN + c] + red[(1 * 2 + which) * BN + c] + red[(2 * 2 + which) * BN + c] +
+                      red[(3 * 2 + which) * BN + c];
+      atomicAdd(p.stats + static_cast<size_t>(blockIdx.x % kBnStatReplicas) * 2 * BN + which * BN + c, static_cast<double>(t));
+    }
   }
   if (threadIdx.x == 0) tma_store_wait_all();
   tc_fence_before();

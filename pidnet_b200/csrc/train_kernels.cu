@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View x, View dz, View
 // hold an SM always terminate on their own, so the barrier cannot deadlock; the spin is bounded and traps.
 constexpr int kBnThreads = 384;   // 2 blocks x 384 threads x 64 regs leave register room for a co-resident wgrad CTA
 constexpr int kBnBwdThreadsMin = 256;   // backward: 2 blocks x 256 threads (<= 96 registers) co-reside with a 192-thread wgrad CTA
-constexpr int kBnReplicas = 8, kBnArriveSlots = 16, kBnArriveStride = 64;   // (stride in unsigned: 256 B)
+constexpr int kBnReplicas = kBnStatReplicas, kBnArriveSlots = 16, kBnArriveStride = 64;   // (stride in unsigned: 256 B; the replica count is shared with the conv kernels that accumulate the forward statistics in their epilogue)
 constexpr int kBnRedMin = kBnThreads * 4;                    // block reduction scratch: four rounds of 512 x 4 values
 __host__ __device__ inline int bn_red_floats(int C) { return 3 * C > kBnRedMin ? (3 * C + 3) / 4 * 4 : kBnRedMin; }   // also the coefficient table (3 x C)
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -281,6 +281,8 @@ struct BnFwdParams {
   double count;
   long pix_per_block;
   int relu, stage_iters;
+  int pre;           // 1: `sums` already holds the statistics (accumulated by the producing conv's store warp, conv3_ws.cu):
+                     // no statistics pass, no grid barrier, plain (non-cooperative) launch, stage_iters == 0
 };
 // (loops: each thread walks its own pixels -- q = p0 + ln + m * lanes -- with running pointers, full trips of 4 without
 // per-element bounds / parking tests and a scalar tail; ncu on the first form: 142 instructions per 16-byte vector, half of them
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_fwd_fused_kernel(BnFwdParams
   float a[8], b[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
-  {
+  if (!p.pre) {
     const bf16* xq = xp;
     int m = 0;
     for (; m < nfull; m += 4, xq += 4 * xs) {
@@ -329,8 +331,10 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_fwd_fused_kernel(BnFwdParams
       for (int e = 0; e < 8; ++e) { a[e] += f.v[e]; b[e] = fmaf(f.v[e], f.v[e], b[e]); }
     }
   }
-  block_channel_reduce(red, a, b, groups, lanes, cg, ln, active, C, p.sums + (blockIdx.x % kBnReplicas) * 2 * C);
-  grid_barrier(p.sync, gridDim.x);
+  if (!p.pre) {
+    block_channel_reduce(red, a, b, groups, lanes, cg, ln, active, C, p.sums + (blockIdx.x % kBnReplicas) * 2 * C);
+    grid_barrier(p.sync, gridDim.x);
+  }
   // per-channel coefficients once per block (fp64 only for mean / variance), shared through the scratch table
   {
     const double inv = 1.0 / p.count;
@@ -1156,7 +1160,7 @@ bool bn_fused_supported(int C) { return C % 8 == 0 && C / 8 >= 1 && C / 8 <= kBn
 
 cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma, const float* beta, const float* conv_bias,
                                     float* mean, float* invstd, float* scale, float* shift, float* run_mean, float* run_var,
-                                    double* sums, unsigned* sync, int relu, int num_sms, cudaStream_t st) {
+                                    double* sums, unsigned* sync, int relu, int num_sms, cudaStream_t st, int pre) {
   BnFwdParams p;
   unsigned blocks = 0;
   size_t smem = 0;
@@ -1166,6 +1170,14 @@ cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma
   p.run_mean = run_mean; p.run_var = run_var; p.sums = sums; p.sync = sync; p.relu = relu;
   p.scale = scale; p.shift = shift;
   p.count = static_cast<double>(x.N) * x.H * x.W;
+  p.pre = pre ? 1 : 0;
+  if (pre) {
+    // statistics come from the conv epilogue: a plain streaming launch (no barrier => no co-residency requirement, nothing parked)
+    p.stage_iters = 0;
+    smem = static_cast<size_t>(bn_red_floats(x.C)) * sizeof(float);
+    bn_fwd_fused_kernel<<<blocks, kBnThreads, smem, st>>>(p);
+    return cudaGetLastError();
+  }
   return launch_bn(bn_fwd_fused_kernel, blocks, kBnThreads, smem, st, p);
 }
 

@@ -33,7 +33,9 @@ size_t bn_fused_sync_offset(int C);
 // the backward recomputes the ReLU mask from x with that affine instead of reading the stored output z.
 cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma, const float* beta, const float* conv_bias,
                                     float* mean, float* invstd, float* scale, float* shift, float* run_mean, float* run_var,
-                                    double* sums, unsigned* sync, int relu, int num_sms, cudaStream_t st);
+                                    double* sums, unsigned* sync, int relu, int num_sms, cudaStream_t st, int pre = 0);
+// (pre = 1: `sums` was filled by the store warp of the conv that produced x -- Conv3Params::stats -- so the launch only derives
+// the coefficients and applies them: one read of x, no grid barrier, no cooperative launch)
 cudaError_t bn_backward_fused_launch(View x, View dz, View z, View dx, View dres, const float* mean, const float* invstd,
                                      const float* gamma, const float* scale, const float* shift, int mask_x, double* sums,
                                      unsigned* sync, int relu, int acc_dx, int acc_dres, float* dgamma, float* dbeta, int num_sms,
