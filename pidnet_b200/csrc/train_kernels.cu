@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "train_kernels.cuh"
+#include "ptx.cuh"
 
 namespace pidnet {
 namespace {
@@ -1175,6 +1176,8 @@ cudaError_t bn_forward_fused_launch(View x, View res, View z, const float* gamma
     // statistics come from the conv epilogue: a plain streaming launch (no barrier => no co-residency requirement, nothing parked)
     p.stage_iters = 0;
     smem = static_cast<size_t>(bn_red_floats(x.C)) * sizeof(float);
+    // (programmatic dependent launch was measured here: no gain, 3.455 vs 3.403 ms forward -- a conv CTA leaves no room for
+    // staged BatchNorm blocks on its SM)
     bn_fwd_fused_kernel<<<blocks, kBnThreads, smem, st>>>(p);
     return cudaGetLastError();
   }
