@@ -103,6 +103,9 @@ struct WgradParams {
   float* ws;                       // split-K partials: [split][co tile][z][128 rows][T taps][64 ci] fp32
   int halo;                        // 1: 3x3 stride-1 halo-patch kernel (16x8-pixel tiles: tmY box {64,16,8,1}, tmX[0] box {64,18,10,1},
                                    //    5 taps per CTA, grid.z = ci tiles * 2)
+  int direct;                      // 1x1 convs: every CTA adds its partial tile straight into dW with 16-byte vector reductions
+                                   //    (red.global.add.v4.f32: a thread's 32 consecutive ci of one co row are contiguous in dW);
+                                   //    no workspace, no reduction launch
 };
 constexpr int kWgradTileFloats = 128 * 64;   // per tap
 struct WgradLaunch {

@@ -124,6 +124,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     float* tile = p.ws + ((static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * gridDim.z + blockIdx.z) *
                              (static_cast<size_t>(T) * kWgradTileFloats);
     const int nci = min(64, p.Cin - ci0);
+    if (T == 1 && p.direct) {
+      // 1x1 conv: dW[co][ci_off + ci0 ..] is contiguous along ci -> the split-K sum is 16-byte vector reductions at L2 (the
+      // separate reduction launch cost as much as these small GEMMs themselves: 7-21 us against 7-23 us)
+      float* row = p.dW + static_cast<size_t>(co) * p.Cin_total + p.ci_off + ci0;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (g * 32 >= nci) break;   // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem + g * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (g * 32 + 4 * e < nci)   // (channel counts are multiples of 8)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + g * 32 + 4 * e), "f"(__uint_as_float(v[4 * e])),
+                           "f"(__uint_as_float(v[4 * e + 1])), "f"(__uint_as_float(v[4 * e + 2])), "f"(__uint_as_float(v[4 * e + 3]))
+                           : "memory");
+        }
+      }
+    } else
     for (int j = 0; j < ntap; ++j) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -533,6 +553,7 @@ cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
   else return cudaErrorInvalidValue;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (L.p.direct) return cudaSuccess;   // the GEMM reduced its split-K partials into dW itself
   const long total = static_cast<long>(L.p.Cout) * L.p.ntaps * L.p.Cin;
   if (!red_pdl) {
     wgrad_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 32 * kRedWarps, 0, st>>>(L.p, L.taps_per_group, static_cast<int>(L.grid.x),

@@ -13,7 +13,7 @@ run() {  # name, extra args...
   fi
   echo "$name rc=$? $(cut -c1-160 $O/$name.json)"
 }
-run bench_pidnet_s_1024x2048 --steps 20 --warmup 5
+if [ "$N" = 1 ]; then run bench_pidnet_s_1024x2048 --steps 20 --warmup 5; else run bench_pidnet_s_1024x2048 --steps 20 --warmup 5 --skip-ref-gpu --skip-cpu-baseline; fi
 run bench_pidnet_m_720x960 --model pidnet_m --classes 11 --batch 32 --height 720 --width 960 --steps 20 --warmup 5 --skip-train --skip-ref-gpu --skip-cpu-baseline
 run bench_pidnet_l_1024x2048 --model pidnet_l --classes 19 --batch 16 --height 1024 --width 2048 --steps 20 --warmup 5 --skip-train --skip-ref-gpu --skip-cpu-baseline
 if [ "$N" -ge 2 ]; then
