@@ -80,7 +80,11 @@ class EngineTrainer:
         self.planned = None
         self.out16 = torch.zeros(16, dtype=torch.float32, device=dev)
         self.seq = 0                    # train-mode forwards so far: a backward must belong to the latest one
-        self.overlap_allreduce = True   # bucketed all-reduce behind the backward ranges (False: one all-reduce at the end)
+        # False (default): ONE all-reduce of the flat gradient after the backward (30.9 MB: 0.25 ms exposed at 8 GPUs over NVSwitch).
+        # True: bucketed all-reduces behind the backward ranges.  Measured at 8 x B200 (profiles/r02/final/scale_n8):
+        # 11.87 ms/step bucketed vs 11.41 ms single vs 11.16 ms without exchange -- the 26 NCCL kernels compete for SMs with
+        # backward kernels that are sized to own the whole GPU (persistent, one CTA per SM), which costs more than the overlap hides.
+        self.overlap_allreduce = False
         self._seg_ranges = None
         self._pending = None            # (event, pinned copy of out16) of the last criterion call: deferred error report
         self._host16 = torch.zeros(16, dtype=torch.float32).pin_memory()
