@@ -113,7 +113,23 @@ struct WgradLaunch {
   dim3 grid;  // (pixel splits, co tiles, ci tiles * tap groups)
   int taps_per_group;
 };
-cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st);
+// defer_reduce: leave the split-K partial tiles in L.p.ws (the caller sums many layers with ONE wgrad_reduce_all_launch)
+cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st, bool defer_reduce = false);
 cudaError_t wgrad_tc_init();
+
+// One deferred split-K reduction: everything the reduction of a layer needs, without the tensor maps of WgradParams
+struct WgReduceJob {
+  const float* ws;
+  float* dW;
+  int Cout, Cin, Cin_total, ci_off, k, ntaps;
+  unsigned char tap_rs[kConvMaxTaps];   // (r << 4) | s of tap i
+  int stack;                            // 1: partial tiles of wgrad_stack_kernel, 0: of wgrad_tc_kernel<T> / wgrad_halo_kernel
+  int T, splits, co_tiles, nz;          // taps per CTA, grid.x, grid.y, grid.z
+};
+bool wgrad_reduce_job(const WgradLaunch& L, WgReduceJob* job);   // false: this launch reduces itself (direct mode)
+unsigned wgrad_reduce_job_blocks(const WgReduceJob& j);
+// jobs / block_start: device arrays; block_start[i] = first block of job i in a numbering where job 0 starts at `base`
+cudaError_t wgrad_reduce_all_launch(const WgReduceJob* dev_jobs, const unsigned* dev_block_start, int njobs, unsigned base,
+                                    unsigned total_blocks, cudaStream_t st);
 
 }  // namespace pidnet

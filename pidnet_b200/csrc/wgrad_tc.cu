@@ -10,6 +10,7 @@
 // were the bottleneck of the first version: up to 7 M atomics per layer).  Stride-2 convs use the same parity
 // tensor maps as the forward kernel; zero padding / ragged tiles are TMA out-of-bounds fills.
 #include <cstdlib>
+#include <cstring>
 #include "train_kernels.cuh"
 #include "ptx.cuh"
 
@@ -450,14 +451,18 @@ __device__ __forceinline__ float sum_splits(const float* src, size_t split_strid
   return acc;
 }
 
-// split-K reduction of wgrad_stack_kernel's partial tiles ([pair][tap-in-pair * 64 + ci][co]): co fastest (coalesced workspace
-// reads), same block structure as wgrad_reduce_kernel below
-__global__ void __launch_bounds__(256) wgrad_stack_reduce_kernel(WgradParams p, int splits, int co_tiles, int ci_tiles, int wide) {
-  __shared__ float red[8][32];
-  pdl_wait();   // launched while the GEMM drains (programmatic dependent launch); its partial tiles are complete after this
+// ---------------------------------------------------------------------------------------------------------------
+// Split-K reductions.  A block owns 32 consecutive gradient elements; its eight warps each sum every eighth split (coalesced
+// 128-byte rows of the workspace) and the partial sums meet in shared memory -- one thread per element walking all ~148 splits
+// serially was latency-bound at ~12 us per layer, as long as the GEMM itself.  The same two bodies serve the per-layer launches
+// (programmatic dependent launch behind their GEMM) and the batched launch that sums every deferred layer of a backward range
+// at once (wgrad_reduce_all_kernel: ~46 latency-bound launches of 7-15 us become one bandwidth-bound launch).
+constexpr int kRedWarps = 8;
+// partial tiles of wgrad_stack_kernel ([pair][tap-in-pair * 64 + ci][co]): co fastest (coalesced workspace reads)
+__device__ __forceinline__ void reduce_stack_body(const WgReduceJob& p, unsigned blk, float (*red)[32], int wide) {
   const long total = static_cast<long>(9) * p.Cin * p.Cout;
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const long idx = static_cast<long>(blockIdx.x) * 32 + lane;
+  const long idx = static_cast<long>(blk) * 32 + lane;
   const bool live = idx < total;
   const long id = live ? idx : total - 1;
   const int co = static_cast<int>(id % p.Cout);
@@ -465,51 +470,70 @@ __global__ void __launch_bounds__(256) wgrad_stack_reduce_kernel(WgradParams p, 
   const int tap = static_cast<int>(id / (static_cast<long>(p.Cout) * p.Cin));
   const int j = tap >> 1, tp = tap & 1;
   const size_t tile_floats = static_cast<size_t>(kSPairs) * kWgradTileFloats;
+  const int ci_tiles = p.nz;
   const float* src = p.ws + (static_cast<size_t>(co >> 6) * ci_tiles + (ci >> 6)) * tile_floats +
                      (static_cast<size_t>(j) * 128 + tp * 64 + (ci & 63)) * 64 + (co & 63);
-  const size_t split_stride = static_cast<size_t>(co_tiles) * ci_tiles * tile_floats;
-  red[g][lane] = sum_splits<8>(src, split_stride, g, splits, wide);
-  __syncthreads();
-  if (g == 0 && live) {
-    float t = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) t += red[q][lane];
-    const int r = tap / 3, q3 = tap - 3 * r;
-    p.dW[(static_cast<size_t>(co) * p.Cin_total + p.ci_off + ci) * 9 + r * 3 + q3] += t;
-  }
-}
-
-// dW[co][ci_off + ci][r][s] += sum over splits of the partial tiles.  A block owns 32 consecutive gradient elements; its eight
-// warps each sum every eighth split (coalesced 128-byte rows of the workspace) and the partial sums meet in shared memory --
-// one thread per element walking all ~148 splits serially was latency-bound at ~12 us per layer, as long as the GEMM itself.
-constexpr int kRedWarps = 8;
-__global__ void __launch_bounds__(32 * kRedWarps) wgrad_reduce_kernel(WgradParams p, int T, int splits, int co_tiles, int nz, int wide) {
-  __shared__ float red[kRedWarps][32];
-  pdl_wait();
-  const long total = static_cast<long>(p.Cout) * p.ntaps * p.Cin;
-  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const long idx = static_cast<long>(blockIdx.x) * 32 + lane;
-  const bool live = idx < total;
-  const long id = live ? idx : total - 1;
-  const int ci = static_cast<int>(id % p.Cin);
-  const int tapi = static_cast<int>((id / p.Cin) % p.ntaps);
-  const int co = static_cast<int>(id / (static_cast<long>(p.Cin) * p.ntaps));
-  const int ngroups = (p.ntaps + T - 1) / T;
-  const int z = (ci >> 6) * ngroups + tapi / T, j = tapi % T;
-  const size_t tile_floats = static_cast<size_t>(T) * kWgradTileFloats;
-  const float* src = p.ws + (static_cast<size_t>(co >> 7) * nz + z) * tile_floats +
-                     (static_cast<size_t>(co & 127) * T + j) * 64 + (ci & 63);
-  const size_t split_stride = static_cast<size_t>(co_tiles) * nz * tile_floats;
-  red[g][lane] = sum_splits<kRedWarps>(src, split_stride, g, splits, wide);
+  const size_t split_stride = static_cast<size_t>(p.co_tiles) * ci_tiles * tile_floats;
+  red[g][lane] = sum_splits<kRedWarps>(src, split_stride, g, p.splits, wide);
   __syncthreads();
   if (g == 0 && live) {
     float t = 0.f;
 #pragma unroll
     for (int q = 0; q < kRedWarps; ++q) t += red[q][lane];
-    const uint32_t tp = p.taps[tapi];
-    const int r = (tp >> 24) & 0xF, s = (tp >> 28) & 0xF;
+    const int r = tap / 3, q3 = tap - 3 * r;
+    p.dW[(static_cast<size_t>(co) * p.Cin_total + p.ci_off + ci) * 9 + r * 3 + q3] += t;
+  }
+}
+// partial tiles of wgrad_tc_kernel<T> / wgrad_halo_kernel ([co row][tap j][64 ci]):
+// dW[co][ci_off + ci][r][s] += sum over splits of the partial tiles
+__device__ __forceinline__ void reduce_tc_body(const WgReduceJob& p, unsigned blk, float (*red)[32], int wide) {
+  const long total = static_cast<long>(p.Cout) * p.ntaps * p.Cin;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long idx = static_cast<long>(blk) * 32 + lane;
+  const bool live = idx < total;
+  const long id = live ? idx : total - 1;
+  const int ci = static_cast<int>(id % p.Cin);
+  const int tapi = static_cast<int>((id / p.Cin) % p.ntaps);
+  const int co = static_cast<int>(id / (static_cast<long>(p.Cin) * p.ntaps));
+  const int T = p.T;
+  const int ngroups = (p.ntaps + T - 1) / T;
+  const int z = (ci >> 6) * ngroups + tapi / T, j = tapi % T;
+  const size_t tile_floats = static_cast<size_t>(T) * kWgradTileFloats;
+  const float* src = p.ws + (static_cast<size_t>(co >> 7) * p.nz + z) * tile_floats +
+                     (static_cast<size_t>(co & 127) * T + j) * 64 + (ci & 63);
+  const size_t split_stride = static_cast<size_t>(p.co_tiles) * p.nz * tile_floats;
+  red[g][lane] = sum_splits<kRedWarps>(src, split_stride, g, p.splits, wide);
+  __syncthreads();
+  if (g == 0 && live) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < kRedWarps; ++q) t += red[q][lane];
+    const int r = p.tap_rs[tapi] >> 4, s = p.tap_rs[tapi] & 0xF;
     p.dW[(static_cast<size_t>(co) * p.Cin_total + p.ci_off + ci) * (p.k * p.k) + r * p.k + s] += t;
   }
+}
+__global__ void __launch_bounds__(32 * kRedWarps) wgrad_reduce_kernel(const __grid_constant__ WgReduceJob job, int wide) {
+  __shared__ float red[kRedWarps][32];
+  pdl_wait();   // launched while the GEMM drains (programmatic dependent launch); its partial tiles are complete after this
+  if (job.stack) reduce_stack_body(job, blockIdx.x, red, wide);
+  else reduce_tc_body(job, blockIdx.x, red, wide);
+}
+// every deferred layer of a backward range in one launch: block_start[i] - base = first block of job i
+__global__ void __launch_bounds__(32 * kRedWarps) wgrad_reduce_all_kernel(const WgReduceJob* __restrict__ jobs,
+                                                                          const unsigned* __restrict__ block_start, int njobs,
+                                                                          unsigned base, int wide) {
+  __shared__ float red[kRedWarps][32];
+  __shared__ WgReduceJob job;
+  const unsigned blk = blockIdx.x + base;
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {   // last job whose first block is <= blk
+    const int mid = (lo + hi + 1) >> 1;
+    if (block_start[mid] <= blk) lo = mid; else hi = mid - 1;
+  }
+  if (threadIdx.x < sizeof(WgReduceJob) / 4) reinterpret_cast<uint32_t*>(&job)[threadIdx.x] = reinterpret_cast<const uint32_t*>(jobs + lo)[threadIdx.x];
+  __syncthreads();
+  if (job.stack) reduce_stack_body(job, blk - block_start[lo], red, wide);
+  else reduce_tc_body(job, blk - block_start[lo], red, wide);
 }
 
 template <int T>
@@ -528,24 +552,41 @@ cudaError_t wgrad_tc_init() {
   return cudaFuncSetAttribute(wgrad_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSSmem));
 }
 
-cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
+bool wgrad_reduce_job(const WgradLaunch& L, WgReduceJob* job) {
+  if (L.p.direct) return false;
+  WgReduceJob j;
+  std::memset(&j, 0, sizeof(j));
+  j.ws = L.p.ws; j.dW = L.p.dW;
+  j.Cout = L.p.Cout; j.Cin = L.p.Cin; j.Cin_total = L.p.Cin_total; j.ci_off = L.p.ci_off; j.k = L.p.k; j.ntaps = L.p.ntaps;
+  for (int i = 0; i < L.p.ntaps && i < kConvMaxTaps; ++i)
+    j.tap_rs[i] = static_cast<unsigned char>((((L.p.taps[i] >> 24) & 0xF) << 4) | ((L.p.taps[i] >> 28) & 0xF));
+  j.stack = L.p.halo == 2 ? 1 : 0;
+  j.T = L.p.halo == 2 ? kSPairs : (L.p.halo ? kHT : L.taps_per_group);
+  j.splits = static_cast<int>(L.grid.x); j.co_tiles = static_cast<int>(L.grid.y); j.nz = static_cast<int>(L.grid.z);
+  *job = j;
+  return true;
+}
+unsigned wgrad_reduce_job_blocks(const WgReduceJob& j) {
+  const long total = j.stack ? static_cast<long>(9) * j.Cin * j.Cout : static_cast<long>(j.Cout) * j.ntaps * j.Cin;
+  return static_cast<unsigned>((total + 31) / 32);
+}
+static int reduce_wide() {
   static const int red_wide = [] { const char* v = std::getenv("PIDNET_WG_WIDE"); return v && v[0] == '0' ? 0 : 1; }();
+  return red_wide;
+}
+cudaError_t wgrad_reduce_all_launch(const WgReduceJob* dev_jobs, const unsigned* dev_block_start, int njobs, unsigned base,
+                                    unsigned total_blocks, cudaStream_t st) {
+  if (njobs <= 0 || total_blocks == 0) return cudaSuccess;
+  wgrad_reduce_all_kernel<<<total_blocks, 32 * kRedWarps, 0, st>>>(dev_jobs, dev_block_start, njobs, base, reduce_wide());
+  return cudaGetLastError();
+}
+
+cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st, bool defer_reduce) {
   static const bool red_pdl = [] { const char* v = std::getenv("PIDNET_WG_PDL"); return !(v && v[0] == '0'); }();
   if (L.p.halo == 2) {   // stacked taps: grid (splits, co tiles of 64, ci tiles of 64), all nine taps per CTA
     if (L.p.ntaps != 9 || L.taps_per_group != 2 * kSPairs) return cudaErrorInvalidValue;
     wgrad_stack_kernel<<<L.grid, kWgThreads, kSSmem, st>>>(L.p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    const long total = static_cast<long>(9) * L.p.Cin * L.p.Cout;
-    if (!red_pdl) {
-      wgrad_stack_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 256, 0, st>>>(L.p, static_cast<int>(L.grid.x), static_cast<int>(L.grid.y),
-                                                                                           static_cast<int>(L.grid.z), red_wide);
-      return cudaGetLastError();
-    }
-    return launch_pdl(wgrad_stack_reduce_kernel, dim3(static_cast<unsigned>((total + 31) / 32)), dim3(256), 0, st, L.p,
-                      static_cast<int>(L.grid.x), static_cast<int>(L.grid.y), static_cast<int>(L.grid.z), red_wide);
-  }
-  if (L.p.halo) {
+  } else if (L.p.halo) {
     if (L.taps_per_group != kHT || L.p.ntaps != 9 || (L.grid.z & 1)) return cudaErrorInvalidValue;
     wgrad_halo_kernel<<<L.grid, kWgThreads, kHSmem, st>>>(L.p);
   } else if (L.taps_per_group == 1) wgrad_tc_kernel<1><<<L.grid, kWgThreads, wg_smem<1>(), st>>>(L.p);
@@ -553,15 +594,15 @@ cudaError_t wgrad_tc_launch(const WgradLaunch& L, cudaStream_t st) {
   else return cudaErrorInvalidValue;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (L.p.direct) return cudaSuccess;   // the GEMM reduced its split-K partials into dW itself
-  const long total = static_cast<long>(L.p.Cout) * L.p.ntaps * L.p.Cin;
+  WgReduceJob job;
+  if (!wgrad_reduce_job(L, &job)) return cudaSuccess;   // direct mode: the GEMM reduced its split-K partials into dW itself
+  if (defer_reduce) return cudaSuccess;                 // the caller sums this layer with wgrad_reduce_all_launch
+  const unsigned blocks = wgrad_reduce_job_blocks(job);
   if (!red_pdl) {
-    wgrad_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 32 * kRedWarps, 0, st>>>(L.p, L.taps_per_group, static_cast<int>(L.grid.x),
-                                                                                  static_cast<int>(L.grid.y), static_cast<int>(L.grid.z), red_wide);
+    wgrad_reduce_kernel<<<blocks, 32 * kRedWarps, 0, st>>>(job, reduce_wide());
     return cudaGetLastError();
   }
-  return launch_pdl(wgrad_reduce_kernel, dim3(static_cast<unsigned>((total + 31) / 32)), dim3(32 * kRedWarps), 0, st, L.p,
-                    L.taps_per_group, static_cast<int>(L.grid.x), static_cast<int>(L.grid.y), static_cast<int>(L.grid.z), red_wide);
+  return launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(32 * kRedWarps), 0, st, job, reduce_wide());
 }
 
 }  // namespace pidnet
