@@ -173,12 +173,26 @@ class EngineTrainer:
                         torch.empty(N, 1, H // 8, W // 8, device=self.device)]
             p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            cw = class_weights.to(self.device, torch.float32).contiguous() if class_weights is not None else None
+            cw = self._device_class_weights(class_weights)
             _lib.check(self.lib.pidnet_train_step(self.h, C.c_void_p(stream), p(x), p(labels), p(bd_gt), p(cw), C.byref(crit_cfg),
                                                   int(backward), p(self.out16), p(outs[1]), p(outs[0]), p(outs[2]), p(aux_ce_map)))
             self._record_out(True)
         self._after_forward()
         return self.out16, outs
+
+    def _device_class_weights(self, w):
+        """fp32 device copy of the criterion's class weights, cached: the reference keeps them in a CPU tensor
+        (datasets/cityscapes.py:55-59), and a `.to(device)` from pageable memory every step is a synchronous copy behind all queued
+        work -- a full host/device synchronisation per step that keeps the host from running ahead of the GPU."""
+        if w is None:
+            return None
+        if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.device == self.device:
+            return w
+        key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype)
+        c = getattr(self, '_cw_cache', None)
+        if c is None or c[0] != key or c[1] is not w:
+            self._cw_cache = c = (key, w, w.detach().to(self.device, torch.float32).contiguous())
+        return c[2]
 
     def forward_train(self, x):
         """Train-mode forward only (batch statistics, running-stat update): [x_extra_p, x_, x_extra_d]."""
